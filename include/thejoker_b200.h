@@ -1,0 +1,144 @@
+/*
+ * thejoker_b200.h -- C ABI of libthejoker_b200.so, the sm_100a implementation of
+ * The Joker's hot path (prior stream -> Kepler solve per epoch -> design matrix ->
+ * Gaussian-marginal log-likelihood -> rejection accept -> linear-parameter draw).
+ *
+ * The entry points are what a binding of the reference's operator boundary,
+ * `cdef class CJokerHelper` (thejoker/src/fast_likelihood.pyx:70-576), needs:
+ * plain pointers and sizes, no torch / numpy / Python types.  All functions
+ * return 0 on success and a negative TJB_E_* code on failure; the message of the
+ * last failure on the calling thread is available from tjb_last_error().
+ *
+ * Pointer arguments named d_* are DEVICE pointers on the handle's GPU (the host
+ * layer allocates them as torch tensors and passes data_ptr()); h_* are HOST
+ * pointers.  All work is enqueued on the stream set with tjb_set_stream()
+ * (default: the legacy default stream).  Functions taking only device pointers are
+ * asynchronous with respect to the host; functions with h_* outputs synchronise
+ * the stream before returning.  A handle may be used by one host thread at a time.
+ *
+ * There is no CPU path: every entry point fails with TJB_E_CUDA when no sm_100
+ * device is usable.
+ */
+#ifndef THEJOKER_B200_H
+#define THEJOKER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TJB_VERSION 100
+#define TJB_MAX_LINEAR 8
+
+enum {
+  TJB_OK = 0,
+  TJB_E_INVALID = -1, /* bad argument / unsupported shape */
+  TJB_E_CUDA = -2,    /* CUDA runtime error, or no usable device */
+  TJB_E_NOMEM = -3
+};
+
+/* What CJokerHelper.__init__ extracts from (data, prior, trend_M)
+ * (fast_likelihood.pyx:125-253).  All arrays are HOST pointers, copied by
+ * tjb_create.  Linear-parameter order: [K, v0, dv0_1.., v1, v2, ..]
+ * (pyx:143-148, 204-252). */
+typedef struct TjbSpec {
+  int32_t n_times;       /* N = len(data) (pyx:155) */
+  int32_t n_linear;      /* L = 1 + poly_trend + n_offsets (pyx:158), 1..TJB_MAX_LINEAR */
+  double t_ref;          /* data._t_ref_bmjd (pyx:162) */
+  const double *t;       /* [N] BMJD (pyx:163) */
+  const double *rv;      /* [N] (pyx:164) */
+  const double *ivar;    /* [N] inverse variance, 1/rv_unit^2 (pyx:165-166) */
+  const double *trend_M; /* [N, L-1] row-major (pyx:167, 174-184) */
+  double mu[TJB_MAX_LINEAR];     /* prior means (pyx:204, 219, 243-252) */
+  double Lambda[TJB_MAX_LINEAR]; /* prior variances (pyx:205, 220, 246-251); [0] unused if K_prior_kind==0 */
+  int32_t K_prior_kind;  /* 0 = FixedCompanionMass (pyx:225-226), 1 = Normal */
+  double sigma_K0;       /* pyx:239 */
+  double P0;             /* pyx:240-241, in days */
+  double max_K;          /* pyx:242 */
+  int32_t jitter_mode;   /* 0 = as the reference is written: s ignored (pyx:458 is a dead store);
+                            1 = s enters the covariance, ivar/(1 + s^2 ivar) (pyx:48-67) */
+} TjbSpec;
+
+typedef struct TjbHandle TjbHandle;
+
+/* ---- lifecycle -------------------------------------------------------- */
+/* replaces CJokerHelper.__init__ (pyx:125-253) */
+int tjb_create(const TjbSpec *spec, int device, TjbHandle **out);
+void tjb_destroy(TjbHandle *h);
+int tjb_set_stream(TjbHandle *h, void *cuda_stream);
+const char *tjb_last_error(void);
+int tjb_version(void);
+/* number of SMs and the kernel's resident CTAs per SM on the handle's device */
+int tjb_device_info(TjbHandle *h, int *n_sm, int *ctas_per_sm, int *cc_major, int *cc_minor);
+
+/* ---- batch_marginal_ln_likelihood (pyx:428-469) --------------------- */
+/* Prior columns as separate device arrays (SoA).  d_s may be NULL: then every
+ * sample has jitter s_const.  d_ll[n] receives the log-likelihoods.  If
+ * d_llmax_key is not NULL the int64 it points to is max-updated with the
+ * order-preserving key of every ll written (see tjb_key_to_double); initialise it
+ * with tjb_llmax_reset.  Keys are plain int64, so shards on several GPUs combine
+ * with an integer MAX all-reduce. */
+int tjb_marginal_ll_soa(TjbHandle *h, const double *d_P, const double *d_e,
+                        const double *d_omega, const double *d_M0, const double *d_s,
+                        double s_const, int64_t n, double *d_ll, int64_t *d_llmax_key);
+/* Prior rows packed as the reference packs them: d_chunk[n,5] row-major
+ * [P, e, omega, M0, s] (pyx:41, 448-451).  uniform_s != 0 promises that column 4
+ * is the same for all rows (the host layer checks), enabling the constant-jitter
+ * kernel. */
+int tjb_marginal_ll_aos(TjbHandle *h, const double *d_chunk, int uniform_s, int64_t n,
+                        double *d_ll, int64_t *d_llmax_key);
+/* Literal drop-in for batch_marginal_ln_likelihood on HOST buffers: copies the
+ * chunk to the device in slices, runs the kernel and copies ll back, overlapping
+ * the three on two streams.  Pinned host buffers give full PCIe bandwidth. */
+int tjb_marginal_ll_host(TjbHandle *h, const double *h_chunk, int64_t n, double *h_ll);
+
+/* ---- accept step (likelihood_helpers.py:107-109; multiproc_helpers.py:256-258) */
+int tjb_llmax_reset(TjbHandle *h, int64_t *d_llmax_key);
+/* max-update *d_llmax_key with d_ll[0..n) (for ll arrays not produced above) */
+int tjb_llmax_update(TjbHandle *h, const double *d_ll, int64_t n, int64_t *d_llmax_key);
+int tjb_llmax_get(TjbHandle *h, const int64_t *d_llmax_key, double *h_max);
+double tjb_key_to_double(int64_t key);
+int64_t tjb_double_to_key(double x);
+
+/* good = where(exp(ll - max) > u)[0][:max_keep], ascending.  Exactly one of
+ * d_uniforms / pcg != NULL.  With pcg, u[i] is the (pcg_offset + i)-th double a
+ * numpy Generator(PCG64) in state (state, inc) would return from .random(), bit
+ * for bit (so rng.uniform(size=n) never has to exist on the host).  index_base is
+ * added to the written indices (shard offset).  Outputs: d_idx[max_keep] device;
+ * h_counts[0] = number accepted in [0,n) before truncation, h_counts[1] = number
+ * written, h_counts[2] = number of samples with |exp(ll-max) - u| <= near_tol. */
+typedef struct TjbPcg64 {
+  uint64_t state_hi, state_lo, inc_hi, inc_lo;
+} TjbPcg64;
+int tjb_accept(TjbHandle *h, const double *d_ll, int64_t n, const int64_t *d_llmax_key,
+               const double *d_uniforms, const TjbPcg64 *pcg, int64_t pcg_offset,
+               int64_t index_base, int64_t max_keep, double near_tol, int64_t *d_idx,
+               int64_t *h_counts);
+/* the uniforms themselves (tests; parity with numpy) */
+int tjb_pcg64_uniform(TjbHandle *h, const TjbPcg64 *pcg, int64_t offset, int64_t n,
+                      double *d_out);
+
+/* ---- batch_get_posterior_samples / test_likelihood_worker (pyx:471-576) */
+/* For k rows h_rows[k,5]: ll, posterior mean a[k,L] and covariance A[k,L,L] of the
+ * linear parameters (pyx:394-423, 530).  clamp_K != 0 applies the max_K clamp to
+ * Lambda_K; the reference does not in these two entry points (pyx:519-521,
+ * 569-571). Any output pointer may be NULL. */
+int tjb_posterior_aA(TjbHandle *h, const double *h_rows, int64_t k, int clamp_K,
+                     double *h_ll, double *h_a, double *h_A);
+/* Draw n_per linear-parameter vectors per row: x = a + chol(A) z with
+ * h_normals[k, n_per, L] standard normals supplied by the host RNG, and pack
+ * rows [P, e, omega, M0, s, x...] (pyx:532-542).  h_out[k*n_per, 5+L]. */
+int tjb_posterior_draw(TjbHandle *h, const double *h_rows, int64_t k, int n_per, int clamp_K,
+                       const double *h_normals, double *h_out, double *h_ll);
+/* row 0 of M_T for one sample (pyx:453-455): z[N]; h_stats[3] (optional) returns
+ * extra FP32 steps, extra FP64 steps, non-converged epochs of the solver. */
+int tjb_design_column(TjbHandle *h, const double *h_row, double *h_z, int32_t *h_stats);
+
+/* ---- measurement helper: FP64 FMA-chain peak of the device, TFLOP/s ---- */
+int tjb_fp64_peak(TjbHandle *h, int iters, double *h_tflops, double *h_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THEJOKER_B200_H */

@@ -1,0 +1,114 @@
+"""Shared builders for the test-suite: synthetic stars in the shape of the reference's
+fixtures, prior chunks, and the host-emulation loader (tools/host_emulation.cpp)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+import thejoker_b200 as tj
+from thejoker_b200 import units as u
+from thejoker_b200.data_helpers import validate_prepare_data
+from thejoker_b200.helper import extract_spec
+from thejoker_b200.prior import Normal
+from thejoker_b200.synthetic import default_prior_columns, make_data, make_noisy_data
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def default_prior(poly_trend=1, sigma_K0=30.0, P_min=2.0, P_max=1024.0, v0_offsets=None, s=None,
+                  pars=None):
+    sv = [100 * u.km / u.s, 0.5 * u.km / u.s / u.day, 1e-2 * u.km / u.s / u.day**2][:poly_trend]
+    if poly_trend == 1:
+        sv = sv[0]
+    return tj.JokerPrior.default(P_min=P_min * u.day, P_max=P_max * u.day,
+                                 sigma_K0=sigma_K0 * u.km / u.s if sigma_K0 is not None else None,
+                                 sigma_v=sv, poly_trend=poly_trend, v0_offsets=v0_offsets, s=s,
+                                 pars=pars)
+
+
+def star_spec(n_times=16, poly_trend=1, seed=42, K=None, sigma=0.5, jitter_mode="apply",
+              normal_K=None, n_surveys=1, v1=None):
+    """(spec dict, data, prior) for a synthetic star."""
+    pars = None
+    if normal_K is not None:
+        pars = {"K": Normal("K", 0.0, normal_K, u.km / u.s)}
+    offsets = [Normal(f"dv0_{i}", 0.0, 5.0, u.km / u.s) for i in range(1, n_surveys)]
+    prior = default_prior(poly_trend, sigma_K0=None if normal_K is not None else 30.0,
+                          v0_offsets=offsets or None, pars=pars)
+    if n_surveys == 1:
+        data, _ = make_noisy_data(n_times, seed=seed, K=K, sigma=sigma, v1=v1)
+    else:
+        rng = np.random.default_rng(seed)
+        full, _ = make_noisy_data(n_times, seed=seed, K=K, sigma=sigma, v1=v1)
+        cuts = np.sort(rng.choice(np.arange(2, n_times - 1), size=n_surveys - 1, replace=False))
+        data, lo = [], 0
+        for k, hi in enumerate(list(cuts) + [n_times]):
+            off = 0.0 if k == 0 else rng.normal(0, 5.0)
+            data.append(tj.RVData(full._t_bmjd[lo:hi], (full.rv.value[lo:hi] + off) * u.km / u.s,
+                                  full.rv_err[lo:hi]))
+            lo = hi
+    all_data, ids, trend_M = validate_prepare_data(data, prior.poly_trend, prior.n_offsets)
+    return extract_spec(all_data, prior, trend_M, jitter_mode), data, prior
+
+
+def prior_chunk(n, seed=123, s_lognormal=None, s_const=None):
+    cols = list(default_prior_columns(n, seed=seed, s_lognormal=s_lognormal))
+    if s_const is not None:
+        cols[4] = np.full(n, float(s_const))
+    return np.ascontiguousarray(np.stack(cols, axis=1))
+
+
+_emu = None
+
+
+def host_emulation():
+    """CPU build of the device math (tools/host_emulation.cpp); debug tooling only."""
+    global _emu
+    if _emu is None:
+        so = os.path.join(ROOT, "tools", "libhost_emulation.so")
+        src = os.path.join(ROOT, "tools", "host_emulation.cpp")
+        deps = [src] + [os.path.join(ROOT, "thejoker_b200", "csrc", f) for f in
+                        ("kepler.cuh", "linalg.cuh", "marginal_ll.cuh", "star_tables.hpp",
+                         "accept.cuh")]
+        if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared",
+                            "-ffp-contract=off", src, "-o", so], check=True)
+        lib = ctypes.CDLL(so)
+        dp = ctypes.POINTER(ctypes.c_double)
+        lib.emu_design_column.argtypes = [ctypes.c_double] * 4 + [dp, ctypes.c_int, dp,
+                                                                  ctypes.POINTER(ctypes.c_int)]
+        lib.emu_marginal_ll.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, dp, dp, dp, dp,
+                                        dp, dp, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                        ctypes.c_double, ctypes.c_int, ctypes.c_int, dp,
+                                        ctypes.c_long, dp]
+        lib.emu_ll_to_key.restype = ctypes.c_longlong
+        lib.emu_ll_to_key.argtypes = [ctypes.c_double]
+        lib.emu_key_to_ll.restype = ctypes.c_double
+        lib.emu_key_to_ll.argtypes = [ctypes.c_longlong]
+        lib.emu_pcg64_double.restype = ctypes.c_double
+        lib.emu_pcg64_double.argtypes = [ctypes.c_ulonglong] * 5
+        lib.emu_sincos_quarter.argtypes = [ctypes.c_double, ctypes.c_int, dp, dp]
+        _emu = lib
+    return _emu
+
+
+def emu_marginal_ll(spec, chunk, force_jit=False):
+    lib = host_emulation()
+    dp = ctypes.POINTER(ctypes.c_double)
+    p = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(dp)
+    chunk = np.ascontiguousarray(chunk, dtype=np.float64)
+    ll = np.zeros(len(chunk))
+    keep = [np.ascontiguousarray(spec[k], dtype=np.float64) for k in
+            ("t", "rv", "ivar", "trend_M", "mu", "Lambda")]
+    max_K = spec["max_K"] if np.isfinite(spec["max_K"]) else 1e300
+    rc = lib.emu_marginal_ll(spec["n_times"], spec["n_linear"], spec["t0"],
+                             *[k.ctypes.data_as(dp) for k in keep], spec["K_prior_kind"],
+                             spec["sigma_K0"], spec["P0"], max_K, spec["jitter_mode"],
+                             int(force_jit), p(chunk), len(chunk), ll.ctypes.data_as(dp))
+    assert rc == 0
+    return ll
+
+
+def rel_err(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)

@@ -1,0 +1,284 @@
+// kepler.cuh -- fixed-work Kepler solver and unit-amplitude RV column for one
+// (prior sample, epoch), written for the sm_100a FP64 pipe.
+//
+// Replaces twobody.c::c_rv_from_elements as called from
+// thejoker/src/fast_likelihood.pyx:453-455, 511-513, 561-563 (K = 1):
+//     M   = 2 pi (t - t0) / P - M0
+//     E   : E - e sin E = M
+//     z   = cos(f + omega) + e cos(omega),  f = true anomaly
+//
+// Design.  The FP64 pipe issues one warp instruction
+// every two cycles per SM sub-partition, so the kernel is bound by the number of
+// FP64 instructions per epoch as long as everything else fits in the other half
+// of the issue slots.  Hence:
+//  * angles are carried in quarter-revolutions so the argument reduction is an
+//    exact magic-number rounding (no Payne-Hanek, no multiples of 2 pi);
+//  * the starter and one Householder refinement run on the FP32 / MUFU pipes
+//    (sin.approx, cos.approx, rsqrt.approx, rcp.approx) with no branches;
+//  * one third-order Householder step in FP64 takes the FP32 estimate
+//    (error ~1e-6) to below 1e-20; sin E / cos E are carried through the step
+//    by an angle-addition update, so only one full double sincos is evaluated;
+//  * polynomial coefficients live in __constant__ memory and are consumed as
+//    constant-bank operands of DFMA (no register moves in the loop);
+//  * z is formed without atan2:  cos f = (cosE - e)/(1 - e cosE),
+//    sin f = sqrt(1-e^2) sinE/(1 - e cosE);
+//  * the FP64 step is closed by a warp-uniform convergence test (|delta|), so
+//    high-eccentricity lanes near pericentre cost extra passes only in their warp.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define TJB_HD __host__ __device__ __forceinline__
+#define TJB_D __device__ __forceinline__
+#else
+#define TJB_HD inline
+#define TJB_D inline
+#endif
+
+namespace tjb {
+
+// 1.5 * 2^52 (1.5 * 2^23): adding it rounds to the nearest integer and leaves
+// that integer in the low mantissa bits.
+constexpr double kMagic = 6755399441055744.0;
+constexpr float kMagicF = 12582912.0f;
+constexpr double kTwoOverPi = 0.63661977236758134308;  // 2/pi
+
+// sin(w pi/2) = w * sum_k S[k] w^2k,  cos(w pi/2) = sum_k C[k] w^2k on |w| <= 1/2:
+// the fdlibm __kernel_sin/__kernel_cos minimax coefficients (|x| <= pi/4) with the
+// powers of pi/2 folded in (tests/test_host_math.py checks the result).
+#if defined(__CUDA_ARCH__)
+#define TJB_COEF __constant__
+#else
+#define TJB_COEF static const
+#endif
+TJB_COEF double kSinC[7] = {1.570796326794896619231322,     -0.6459640975062449269023451,
+                            0.07969262624606334392301012,   -0.004681754132625933413797963,
+                            0.0001604411526673809583408432, -0.000003598649570240691901625632,
+                            5.634704113884750951753422e-8};
+TJB_COEF double kCosC[8] = {1.0,
+                            -1.233700550136169827354311,
+                            0.2536695079010476193552061,
+                            -0.02086348076333075982186824,
+                            0.000919260274390553378473447,
+                            -0.00002520203791691774237050555,
+                            0.0000004710641505803501879438872,
+                            -6.324746678866069891109223e-9};
+// 1/6, 1/24, Householder repeat threshold, 2/pi, pi/2 as constant-bank operands
+TJB_COEF double kMisc[5] = {1.0 / 6.0, 1.0 / 24.0, 1.0e-4, 0.63661977236758134308,
+                            1.57079632679489661923};
+
+// ---- bit helpers / pipe-specific primitives -------------------------------
+#if defined(__CUDA_ARCH__)
+TJB_D int lo32(double x) { return __double2loint(x); }
+TJB_D int hi32(double x) { return __double2hiint(x); }
+TJB_D double mk64(int hi, int lo) { return __hiloint2double(hi, lo); }
+TJB_D float fsin_approx(float x) { return __sinf(x); }
+TJB_D float fcos_approx(float x) { return __cosf(x); }
+TJB_D float frsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+TJB_D float frcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// reciprocal of a positive, normal double: MUFU.RCP64H seed + 2 Newton steps.
+// The argument here is always 1 - e cosE in (1-e, 1+e], so none of the
+// denormal / overflow handling of a general division is needed.
+TJB_D double rcp_pos(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double t = fma(-x, r, 1.0);
+  r = fma(r, t, r);
+  t = fma(-x, r, 1.0);
+  r = fma(r, t, r);
+  return r;
+}
+#else
+inline int lo32(double x) { int64_t b; memcpy(&b, &x, 8); return (int)(uint32_t)(b & 0xffffffff); }
+inline int hi32(double x) { int64_t b; memcpy(&b, &x, 8); return (int)(uint32_t)((uint64_t)b >> 32); }
+inline double mk64(int hi, int lo) {
+  uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double x; memcpy(&x, &b, 8); return x;
+}
+inline float fsin_approx(float x) { return sinf(x); }
+inline float fcos_approx(float x) { return cosf(x); }
+inline float frsqrt_approx(float x) { return 1.0f / sqrtf(x); }
+inline float frcp_approx(float x) { return 1.0f / x; }
+inline double rcp_pos(double x) { return 1.0 / x; }
+#endif
+
+// The polynomial coefficients, pinned in registers for the whole epoch loop.
+// ptxas otherwise re-loads each of them from the constant bank on every epoch
+// (17 LDC per iteration), which makes the loop issue-bound instead of FP64-bound.
+struct TrigCoef {
+  double s[7], c[8], m[5];
+  // `zero` must be a run-time 0.0 (a kernel parameter): coefficient + zero is an
+  // FP64 result ptxas will not rematerialise, so the values stay in registers.
+  TJB_HD void load(double zero) {
+#pragma unroll
+    for (int i = 0; i < 7; i++) s[i] = kSinC[i] + zero;
+#pragma unroll
+    for (int i = 0; i < 8; i++) c[i] = kCosC[i] + zero;
+#pragma unroll
+    for (int i = 0; i < 5; i++) m[i] = kMisc[i] + zero;
+  }
+};
+
+// sin and cos of (k + w) * pi/2 for |w| <= 0.5 and integer quadrant k (any int).
+TJB_HD void sincos_quarter(const TrigCoef &tc, double w, int k, double &s, double &c) {
+  const double w2 = w * w;
+  double ps = fma(tc.s[6], w2, tc.s[5]);
+  double pc = fma(tc.c[7], w2, tc.c[6]);
+  ps = fma(ps, w2, tc.s[4]);
+  pc = fma(pc, w2, tc.c[5]);
+  ps = fma(ps, w2, tc.s[3]);
+  pc = fma(pc, w2, tc.c[4]);
+  ps = fma(ps, w2, tc.s[2]);
+  pc = fma(pc, w2, tc.c[3]);
+  ps = fma(ps, w2, tc.s[1]);
+  pc = fma(pc, w2, tc.c[2]);
+  ps = fma(ps, w2, tc.s[0]);
+  pc = fma(pc, w2, tc.c[1]);
+  const double sx = ps * w;
+  const double cx = fma(pc, w2, 1.0);
+  // quadrant rotation: k=0 (s,c) k=1 (c,-s) k=2 (-s,-c) k=3 (-c,s)
+  const bool swap = k & 1;
+  const double s0 = swap ? cx : sx;
+  const double c0 = swap ? sx : cx;
+  // sign flips on the high words (integer pipe): bit1 of k for sin, bit1 of k+1 for cos
+  s = mk64(hi32(s0) ^ ((k << 30) & 0x80000000), lo32(s0));
+  c = mk64(hi32(c0) ^ (((k + 1) << 30) & 0x80000000), lo32(c0));
+}
+
+// per-sample constants of the Kepler / RV evaluation
+struct OrbitConsts {
+  double nu4;   // 4 / P            [quarter-revolutions per day]
+  double ph4;   // M0 * 2/pi        [quarter-revolutions]
+  double e;     // eccentricity
+  double e6;    // e / 6
+  double a;     // cos(omega)
+  double b;     // -sqrt(1-e^2) sin(omega)
+  double ea;    // e cos(omega)
+  float ef;     // (float) e
+  float g0f;    // (float)(1 + e^2)
+};
+
+TJB_HD OrbitConsts make_orbit_consts(double P, double e, double omega, double M0) {
+  OrbitConsts oc;
+  oc.nu4 = 4.0 / P;
+  oc.ph4 = M0 * kTwoOverPi;
+  oc.e = e;
+  oc.e6 = e * (1.0 / 6.0);
+  double so, co;
+#if defined(__CUDA_ARCH__)
+  sincos(omega, &so, &co);
+#else
+  so = sin(omega); co = cos(omega);
+#endif
+  oc.a = co;
+  oc.b = -sqrt(fma(-e, e, 1.0)) * so;
+  oc.ea = e * co;
+  oc.ef = fminf((float)e, 0.99999994f);  // keep the FP32 starter finite as e -> 1
+  oc.g0f = (float)fma(e, e, 1.0);
+  return oc;
+}
+
+// warp-uniform "any lane" vote; on the host emulation a lane is its own warp
+#if defined(__CUDA_ARCH__)
+TJB_D bool any_lane(bool p) { return __any_sync(0xffffffffu, p); }
+#else
+inline bool any_lane(bool p) { return p; }
+#endif
+
+struct SolveStats {
+  int extra_f32;  // unused (the FP32 stage is fixed-work); kept for the ABI
+  int extra_f64;  // FP64 Householder passes beyond the first
+  int not_converged;
+};
+
+// A third-order Householder step maps an error eps to ~C eps^4 with C = O(1) for
+// e <~ 0.95 (tools/kepler_solver_study.py): the pass is repeated while any lane of
+// the warp moved by more than 1e-4 (tc.m[2]).
+constexpr int kF64MaxIter = 16;
+
+// One epoch.  dt = t_n - t_ref [day].  Returns z_n; all lanes of a warp must call together.
+template <bool kCountStats>
+TJB_HD double rv_unit_column(const OrbitConsts &oc, const TrigCoef &tc, double dt, SolveStats *st) {
+  // mean anomaly in quarter-revolutions (unreduced)
+  const double x4 = fma(dt, oc.nu4, -oc.ph4);
+
+  // ---- FP32: reduce, starter D0 = e sinM / sqrt(1 - 2 e cosM + e^2), one
+  //      third-order Householder step.  Errors of this stage (including the
+  //      ~1e-5 from rounding x4 to float) only move the FP64 starting point.
+  const float ef = oc.ef;
+  const float x4f = (float)x4;
+  const float r4 = (x4f * 0.25f + kMagicF) - kMagicF;      // nearest whole revolution
+  const float Mf = fmaf(r4, -4.0f, x4f) * 1.57079632679f;  // M in [-pi, pi]
+  float Df;
+  {
+    const float sM = fsin_approx(Mf), cM = fcos_approx(Mf);
+    Df = ef * sM * frsqrt_approx(fmaf(-2.0f * ef, cM, oc.g0f));
+    const float Ef = Mf + Df;
+    const float es = ef * fsin_approx(Ef), ec = ef * fcos_approx(Ef);
+    const float r = frcp_approx(1.0f - ec);
+    const float t = es * r;           // f''/f'
+    const float u = fmaf(-Df, r, t);  // -f/f'
+    const float q = fmaf(0.5f * t, t, ec * r * (-1.0f / 6.0f));
+    const float del = u * fmaf(u, fmaf(u, q, -0.5f * t), 1.0f);
+    Df = fminf(fmaxf(Df + del, -ef), ef);  // |E - M| <= e holds for the root
+  }
+
+  // ---- FP64: exact reduction of E0 = M + D0 and one full sincos -----------
+  const double d4 = (double)(Df * 0.63661977236f);  // D0 in quarter-revolutions
+  const double v = x4 + d4;
+  const double tv = v + kMagic;
+  const double w = v - (tv - kMagic);  // in [-0.5, 0.5]
+  double sE, cE;
+  sincos_quarter(tc, w, lo32(tv), sE, cE);
+  double D = d4 * tc.m[4];  // E0 - M [rad]
+
+  // ---- third-order Householder step with angle-addition update -------------
+  // Normal case: one pass.  If any lane of the warp moved by more than 1e-4,
+  // (sinE, cosE) are re-evaluated in full at the updated E and the pass repeats
+  // (warp-uniform branch; rare: e >~ 0.8 near pericentre).
+  for (int it = 0;; ++it) {
+    const double es = oc.e * sE;
+    const double r = rcp_pos(fma(-oc.e, cE, 1.0));
+    const double t = es * r;             // f''/f'
+    const double u = fma(-D, r, t);      // Newton step -f/f' = (e sinE - D)/f'
+    const double b6 = (oc.e6 * cE) * r;  // f'''/(6 f')
+    const double th = 0.5 * t;
+    // delta = u (1 + u (-t/2 + u (t^2/2 - b6)))
+    const double q = fma(th, t, -b6);
+    const double del = u * fma(u, fma(u, q, -th), 1.0);
+    D += del;
+    const bool big = !(fabs(del) <= tc.m[2]);
+    if (!any_lane(big) || it + 1 >= kF64MaxIter) {
+      if (kCountStats && big) st->not_converged++;
+      // rotate (sinE, cosE) by delta, |delta| <= 1e-4: truncation error < 1e-21
+      const double d2 = del * del;
+      const double sd = del * fma(d2, -tc.m[0], 1.0);
+      const double cd = fma(d2, fma(d2, tc.m[1], -0.5), 1.0);
+      const double sN = fma(cE, sd, sE * cd);
+      cE = fma(-sE, sd, cE * cd);
+      sE = sN;
+      break;
+    }
+    if (kCountStats) st->extra_f64++;
+    const double v2 = fma(D, tc.m[3], x4);
+    const double tv2 = v2 + kMagic;
+    sincos_quarter(tc, v2 - (tv2 - kMagic), lo32(tv2), sE, cE);
+  }
+
+  // ---- z = [a (cosE - e) + b sinE] / (1 - e cosE) + e a ---------------------
+  const double r = rcp_pos(fma(-oc.e, cE, 1.0));
+  const double num = fma(oc.b, sE, fma(oc.a, cE, -oc.ea));
+  return fma(num, r, oc.ea);
+}
+
+}  // namespace tjb

@@ -1,0 +1,246 @@
+// marginal_ll.cuh -- the hot kernel: one thread per prior sample, all epochs of
+// the star staged once per CTA in shared memory, Gram sums in registers.
+//
+// Replaces CJokerHelper.batch_marginal_ln_likelihood
+// (thejoker/src/fast_likelihood.pyx:428-469) and everything it calls per sample
+// (c_rv_from_elements pyx:453-455, get_ivar pyx:458, Lambda_K pyx:461-464,
+// likelihood_worker pyx:359-425).
+#pragma once
+
+#include "linalg.cuh"
+
+namespace tjb {
+
+// Where the prior samples live.  Either SoA columns (coalesced 8-byte loads, the
+// native layout) or the reference's packed AoS rows [P, e, omega, M0, s].
+struct PriorView {
+  const double *P, *e, *omega, *M0, *s;  // SoA (s may be null)
+  const double *aos;                     // AoS rows of 5, or null
+  // constant-jitter kernel on AoS rows: rows whose s differs from s_expect raise
+  // *nonuniform (optimistic execution; the caller then reruns per-sample jitter)
+  double s_expect;
+  int *nonuniform;
+};
+
+// Per-star constants.  Passed by value as a kernel parameter (constant bank).
+//
+// Epoch table row n (stride row_stride(L) doubles, staged in shared memory):
+//   constant-jitter kernel (kJit=false): [dt_n, w_n, w_n y_n, w_n T_n1 .. w_n T_n,L-1]
+//        with w_n = ivar_n / (1 + s^2 ivar_n) for the one s of the call
+//   per-sample-jitter kernel (kJit=true): [dt_n, var_n, y_n, T_n1 .. T_n,L-1]
+//        with var_n = 1 / ivar_n
+// T = trend_M (pyx:167): T_1 is the constant column, then offsets, then dt^k.
+// y is centred by the host (y - c, mu_v0 - c) when column T_1 is all ones, which
+// leaves the marginal likelihood unchanged and removes most of the cancellation
+// in chi2.
+TJB_HD constexpr int row_stride(int L) { return (L + 2 + 1) & ~1; }
+
+struct StarParams {
+  int n_times;
+  const double *table;              // device, [N, row_stride(L)]
+  double Gc[kTri<kMaxLinear>];      // constant entries of Ainv, packed upper (kJit=false only)
+  double hc[kMaxLinear];            // constant entries of h (kJit=false), mu_i/Lambda_i (kJit=true)
+  double inv_Lambda[kMaxLinear];    // 1/Lambda_i, i >= 1 ([0] for a Normal K prior)
+  double quad0;                     // y^T C^-1 y + sum_{i>=1} mu_i^2/Lambda_i  (kJit: only the mu part)
+  double c0;                        // N log 2pi - sum log w + sum_{i>=1} log Lambda_i (kJit: no w part)
+  double mu_K;                      // prior mean of K (pyx:243)
+  double Lambda_K;                  // prior variance of K when K_prior_kind == 1
+  int K_prior_kind;                 // 0 FixedCompanionMass, 1 Normal
+  double sigma_K0_sq, inv_P0, max_K_sq;
+  int apply_jitter;                 // kJit kernels: 0 -> treat s as 0 (reference behaviour)
+  double zero;                      // run-time 0.0, see TrigCoef::load
+};
+
+// order-preserving int64 key of a double: key(a) < key(b) <=> a < b, NaN above +inf
+// (so a max-reduction propagates NaN the way numpy.max does).
+TJB_HD long long ll_to_key(double x) {
+  long long b;
+#if defined(__CUDA_ARCH__)
+  b = __double_as_longlong(x);
+#else
+  memcpy(&b, &x, 8);
+#endif
+  if (x != x) b = 0x7FF8000000000000LL;
+  return b >= 0 ? b : (b ^ 0x7FFFFFFFFFFFFFFFLL);
+}
+TJB_HD double key_to_ll(long long k) {
+  long long b = k >= 0 ? k : (k ^ 0x7FFFFFFFFFFFFFFFLL);
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double(b);
+#else
+  double x; memcpy(&x, &b, 8); return x;
+#endif
+}
+
+// multiply-accumulate a running product of positive doubles without overflow:
+// every 4th call the binary exponent is moved into an integer.
+struct LogProduct {
+  double mant;
+  int expo;
+  TJB_HD void init() { mant = 1.0; expo = 0; }
+  TJB_HD void mul(double v) { mant *= v; }
+  TJB_HD void renorm() {
+    const int hi = hi32(mant);
+    const int ex = ((hi >> 20) & 0x7ff) - 1023;
+    expo += ex;
+    mant = mk64(hi - (ex << 20), lo32(mant));
+  }
+  TJB_HD double log_value() const { return log(mant) + 0.69314718055994530942 * (double)expo; }
+};
+
+// ---- per-sample evaluation -------------------------------------------------
+// Returns ll for one prior sample.  `tab` is the staged epoch table.
+template <int L, bool kJit>
+TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab, double P, double e,
+                        double omega, double M0, double s) {
+  constexpr int RS = row_stride(L);
+  const OrbitConsts oc = make_orbit_consts(P, e, omega, M0);
+  TrigCoef tc;
+  tc.load(sp.zero);
+  const int N = sp.n_times;
+
+  double G[kTri<L>];
+  double h[L];
+  double quad0, logdet;
+
+  if (!kJit) {
+    // sums that involve the Kepler column z: z^T C^-1 z, z^T C^-1 y, z^T C^-1 T_k
+    double Szz = 0.0, Szy = 0.0;
+    double SzT[L];
+#pragma unroll
+    for (int k = 1; k < L; k++) SzT[k] = 0.0;
+    const double *row = tab;
+    for (int n = 0; n < N; n++, row += RS) {
+      const double z = rv_unit_column<false>(oc, tc, row[0], nullptr);
+      Szz = fma(z * z, row[1], Szz);
+      Szy = fma(z, row[2], Szy);
+#pragma unroll
+      for (int k = 1; k < L; k++) SzT[k] = fma(z, row[2 + k], SzT[k]);
+    }
+#pragma unroll
+    for (int i = 0; i < kTri<L>; i++) G[i] = sp.Gc[i];
+    G[0] = Szz;
+#pragma unroll
+    for (int k = 1; k < L; k++) G[tri<L>(0, k)] = SzT[k];
+#pragma unroll
+    for (int i = 1; i < L; i++) h[i] = sp.hc[i];
+    h[0] = Szy;
+    quad0 = sp.quad0;
+    logdet = sp.c0;
+  } else {
+    const double s2 = sp.apply_jitter ? s * s : 0.0;
+    double Syy = 0.0;
+#pragma unroll
+    for (int i = 0; i < kTri<L>; i++) G[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < L; i++) h[i] = 0.0;
+    LogProduct lp;
+    lp.init();
+    const double *row = tab;
+    for (int n = 0; n < N; n++, row += RS) {
+      const double z = rv_unit_column<false>(oc, tc, row[0], nullptr);
+      const double var = row[1] + s2;
+      const double w = 1.0 / var;
+      lp.mul(var);
+      if ((n & 3) == 3) lp.renorm();
+      const double y = row[2];
+      // column values of M for this epoch: m[0] = z, m[k] = T_k
+      double m[L];
+      m[0] = z;
+#pragma unroll
+      for (int k = 1; k < L; k++) m[k] = row[2 + k];
+      const double wy = w * y;
+      Syy = fma(wy, y, Syy);
+#pragma unroll
+      for (int i = 0; i < L; i++) {
+        const double wm = w * m[i];
+        h[i] = fma(wy, m[i], h[i]);
+#pragma unroll
+        for (int j = i; j < L; j++) G[tri<L>(i, j)] = fma(wm, m[j], G[tri<L>(i, j)]);
+      }
+    }
+    lp.renorm();
+#pragma unroll
+    for (int i = 1; i < L; i++) {
+      G[tri<L>(i, i)] += sp.inv_Lambda[i];
+      h[i] += sp.hc[i];
+    }
+    quad0 = Syy + sp.quad0;
+    logdet = sp.c0 + lp.log_value();  // -sum log w = +sum log var
+  }
+
+  // K column: prior variance and mean (pyx:461-464)
+  const double lamK = sp.K_prior_kind == 0
+                          ? lambda_K_fixed_mass(P, e, sp.sigma_K0_sq, sp.inv_P0, sp.max_K_sq, true)
+                          : sp.Lambda_K;
+  const double ilamK = 1.0 / lamK;
+  G[0] += ilamK;
+  h[0] = fma(sp.mu_K, ilamK, h[0]);
+  quad0 = fma(sp.mu_K * sp.mu_K, ilamK, quad0);
+
+  const bool ok = ldlt<L>(G);
+  double quad, detG;
+  ldlt_quad<L>(G, h, quad, detG);
+  const double ll = -0.5 * ((quad0 - quad) + (logdet + log(lamK * detG)));
+  // singular Ainv: the reference returns +inf (pyx:283-284, 381-382)
+  return ok ? ll : (double)INFINITY;
+}
+
+#if defined(__CUDACC__)
+
+constexpr int kLLThreads = 256;
+
+template <int L, bool kJit>
+__global__ void __launch_bounds__(kLLThreads, 2)
+marginal_ll_kernel(const StarParams sp, const PriorView pv, const long long n,
+                   double *__restrict__ ll_out, long long *__restrict__ llmax_key) {
+  extern __shared__ double tab[];
+  const int tab_len = sp.n_times * row_stride(L);
+  for (int i = threadIdx.x; i < tab_len; i += blockDim.x) tab[i] = sp.table[i];
+  __syncthreads();
+
+  long long kmax = ll_to_key(-INFINITY);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // all 32 lanes of a warp stay in the loop together (the solver votes warp-wide)
+  const long long n_round = ((n + 31) / 32) * 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    const bool valid = i < n;
+    const long long ii = valid ? i : n - 1;
+    double P, e, om, M0, s;
+    if (pv.aos) {
+      const double *r = pv.aos + 5 * ii;
+      P = r[0]; e = r[1]; om = r[2]; M0 = r[3]; s = r[4];
+      if (!kJit && pv.nonuniform && s != pv.s_expect) atomicOr(pv.nonuniform, 1);
+    } else {
+      P = pv.P[ii]; e = pv.e[ii]; om = pv.omega[ii]; M0 = pv.M0[ii];
+      s = (kJit && pv.s) ? pv.s[ii] : 0.0;
+    }
+    const double v = sample_ll<L, kJit>(sp, tab, P, e, om, M0, s);
+    if (valid) {
+      ll_out[i] = v;
+      const long long k = ll_to_key(v);
+      kmax = k > kmax ? k : kmax;
+    }
+  }
+
+  if (llmax_key) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const long long other = __shfl_xor_sync(0xffffffffu, kmax, o);
+      kmax = other > kmax ? other : kmax;
+    }
+    __shared__ long long wmax[kLLThreads / 32];
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = kmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      long long m = wmax[0];
+#pragma unroll
+      for (int w = 1; w < kLLThreads / 32; w++) m = wmax[w] > m ? wmax[w] : m;
+      atomicMax(llmax_key, m);
+    }
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace tjb

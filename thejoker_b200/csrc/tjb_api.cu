@@ -1,0 +1,558 @@
+// tjb_api.cu -- C ABI of libthejoker_b200.so (see include/thejoker_b200.h).
+// Host-side glue only: spec validation, the per-star constant tables (computed in
+// long double), kernel dispatch on n_linear, stream handling.  No CPU compute path.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/thejoker_b200.h"
+#include "accept.cuh"
+#include "marginal_ll.cuh"
+#include "posterior.cuh"
+#include "star_tables.hpp"
+
+using namespace tjb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(TJB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    if (cudaMalloc(&p, need) != cudaSuccess) return -1;
+    bytes = need;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+
+}  // namespace
+
+struct TjbHandle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int n_sm = 0, cc_major = 0, cc_minor = 0;
+  StarHost star;  // host copy of the spec + centring (star_tables.hpp)
+  int N = 0, L = 0, jitter_mode = 0;
+  // device tables and their parameter blocks
+  DevBuf tab_const, tab_jit;
+  StarParams sp_const, sp_jit;
+  bool const_valid = false;
+  double const_s = 0;
+  // scratch
+  DevBuf acc_mask, acc_counts, acc_offsets, acc_totals, misc;
+  DevBuf host_stage[2], host_ll[2];
+  cudaStream_t aux_stream[2] = {nullptr, nullptr};
+  cudaEvent_t aux_event[2] = {nullptr, nullptr};
+  int ll_ctas_per_sm = 0;
+};
+
+namespace {
+
+// ---- per-star constants (star_tables.hpp) + upload ------------------------------
+
+int upload_table(TjbHandle *h, DevBuf &buf, const std::vector<double> &tab, StarParams &sp) {
+  if (buf.ensure(tab.size() * sizeof(double))) return fail(TJB_E_NOMEM, "cudaMalloc table");
+  CU(cudaMemcpyAsync(buf.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice,
+                     h->stream));
+  CU(cudaStreamSynchronize(h->stream));  // tab is a caller-owned staging buffer
+  sp.table = (const double *)buf.p;
+  return TJB_OK;
+}
+
+// (re)build the constant-jitter table for the given s
+int build_const_table(TjbHandle *h, double s) {
+  std::vector<double> tab;
+  star_build_const(h->star, s, h->sp_const, tab);
+  int rc = upload_table(h, h->tab_const, tab, h->sp_const);
+  if (rc) return rc;
+  h->const_valid = true;
+  h->const_s = s;
+  return TJB_OK;
+}
+
+int build_jit_table(TjbHandle *h) {
+  std::vector<double> tab;
+  star_build_jit(h->star, h->sp_jit, tab);
+  return upload_table(h, h->tab_jit, tab, h->sp_jit);
+}
+
+// ---- kernel dispatch ---------------------------------------------------------
+
+template <int L, bool J>
+int launch_ll(TjbHandle *h, const StarParams &sp, const PriorView &pv, long long n, double *d_ll,
+              long long *d_key, cudaStream_t stream) {
+  auto kern = marginal_ll_kernel<L, J>;
+  const size_t smem = (size_t)h->N * row_stride(L) * sizeof(double);
+  if (smem > 227 * 1024)
+    return fail(TJB_E_INVALID, "epoch table does not fit in shared memory (too many epochs)");
+  if (smem > 48 * 1024)
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kLLThreads, smem));
+  if (per_sm < 1) per_sm = 1;
+  h->ll_ctas_per_sm = per_sm;
+  const long long want = (n + kLLThreads - 1) / kLLThreads;
+  const int grid = (int)std::max(1LL, std::min(want, (long long)h->n_sm * per_sm));
+  kern<<<grid, kLLThreads, smem, stream>>>(sp, pv, n, d_ll, d_key);
+  CU(cudaGetLastError());
+  return TJB_OK;
+}
+
+template <bool J>
+int dispatch_ll(TjbHandle *h, const StarParams &sp, const PriorView &pv, long long n, double *d_ll,
+                long long *d_key, cudaStream_t stream) {
+  switch (h->L) {
+    case 1: return launch_ll<1, J>(h, sp, pv, n, d_ll, d_key, stream);
+    case 2: return launch_ll<2, J>(h, sp, pv, n, d_ll, d_key, stream);
+    case 3: return launch_ll<3, J>(h, sp, pv, n, d_ll, d_key, stream);
+    case 4: return launch_ll<4, J>(h, sp, pv, n, d_ll, d_key, stream);
+    case 5: return launch_ll<5, J>(h, sp, pv, n, d_ll, d_key, stream);
+    case 6: return launch_ll<6, J>(h, sp, pv, n, d_ll, d_key, stream);
+    case 7: return launch_ll<7, J>(h, sp, pv, n, d_ll, d_key, stream);
+    case 8: return launch_ll<8, J>(h, sp, pv, n, d_ll, d_key, stream);
+  }
+  return fail(TJB_E_INVALID, "n_linear out of range");
+}
+
+// choose the kernel: a single jitter value for the whole call is folded into the
+// table (constant-jitter kernel); otherwise the per-sample-jitter kernel runs.
+int run_ll(TjbHandle *h, const PriorView &pv, bool uniform_s, double s_const, long long n,
+           double *d_ll, long long *d_key, cudaStream_t stream) {
+  if (n <= 0) return TJB_OK;
+  CU(cudaSetDevice(h->device));
+  if (h->jitter_mode == 0 || uniform_s) {
+    const double s = h->jitter_mode ? s_const : 0.0;
+    if (!h->const_valid || h->const_s != s) {
+      int rc = build_const_table(h, s);
+      if (rc) return rc;
+    }
+    return dispatch_ll<false>(h, h->sp_const, pv, n, d_ll, d_key, stream);
+  }
+  return dispatch_ll<true>(h, h->sp_jit, pv, n, d_ll, d_key, stream);
+}
+
+template <int L>
+int launch_posterior(TjbHandle *h, const double *d_rows, int k, int clamp, int n_per,
+                     const double *d_normals, double *d_ll, double *d_a, double *d_A,
+                     double *d_draws) {
+  const int grid = (k + 127) / 128;
+  posterior_kernel<L><<<grid, 128, 0, h->stream>>>(h->sp_jit, d_rows, k, clamp,
+                                                  (double)h->star.centre, h->star.centred ? 1 : -1, n_per,
+                                                  d_normals, d_ll, d_a, d_A, d_draws);
+  CU(cudaGetLastError());
+  return TJB_OK;
+}
+
+int dispatch_posterior(TjbHandle *h, const double *d_rows, int k, int clamp, int n_per,
+                       const double *d_normals, double *d_ll, double *d_a, double *d_A,
+                       double *d_draws) {
+  switch (h->L) {
+    case 1: return launch_posterior<1>(h, d_rows, k, clamp, n_per, d_normals, d_ll, d_a, d_A, d_draws);
+    case 2: return launch_posterior<2>(h, d_rows, k, clamp, n_per, d_normals, d_ll, d_a, d_A, d_draws);
+    case 3: return launch_posterior<3>(h, d_rows, k, clamp, n_per, d_normals, d_ll, d_a, d_A, d_draws);
+    case 4: return launch_posterior<4>(h, d_rows, k, clamp, n_per, d_normals, d_ll, d_a, d_A, d_draws);
+    case 5: return launch_posterior<5>(h, d_rows, k, clamp, n_per, d_normals, d_ll, d_a, d_A, d_draws);
+    case 6: return launch_posterior<6>(h, d_rows, k, clamp, n_per, d_normals, d_ll, d_a, d_A, d_draws);
+    case 7: return launch_posterior<7>(h, d_rows, k, clamp, n_per, d_normals, d_ll, d_a, d_A, d_draws);
+    case 8: return launch_posterior<8>(h, d_rows, k, clamp, n_per, d_normals, d_ll, d_a, d_A, d_draws);
+  }
+  return fail(TJB_E_INVALID, "n_linear out of range");
+}
+
+PcgParams make_pcg(const TjbPcg64 *pcg, long long offset, unsigned long long stride) {
+  PcgParams pp;
+  memset(&pp, 0, sizeof(pp));
+  if (!pcg) return pp;
+  pp.enabled = 1;
+  pp.inc = make_u128(pcg->inc_hi, pcg->inc_lo);
+  u128 st = make_u128(pcg->state_hi, pcg->state_lo);
+  if (offset > 0) {
+    const Lcg128 j = lcg_power(pp.inc, (uint64_t)offset);
+    st = j.mult * st + j.plus;
+  }
+  pp.state = st;
+  pp.stride = lcg_power(pp.inc, stride);
+  return pp;
+}
+
+}  // namespace
+
+// =============================================================================
+extern "C" {
+
+const char *tjb_last_error(void) { return g_err.c_str(); }
+int tjb_version(void) { return TJB_VERSION; }
+
+int tjb_create(const TjbSpec *spec, int device, TjbHandle **out) {
+  if (!spec || !out) return fail(TJB_E_INVALID, "null argument");
+  *out = nullptr;
+  if (spec->n_times < 1) return fail(TJB_E_INVALID, "n_times must be >= 1");
+  if (spec->n_linear < 1 || spec->n_linear > TJB_MAX_LINEAR)
+    return fail(TJB_E_INVALID, "n_linear must be in 1..8");
+  if (!spec->t || !spec->rv || !spec->ivar || (spec->n_linear > 1 && !spec->trend_M))
+    return fail(TJB_E_INVALID, "null data array");
+  if (spec->K_prior_kind != 0 && spec->K_prior_kind != 1)
+    return fail(TJB_E_INVALID, "K_prior_kind must be 0 or 1");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1)
+    return fail(TJB_E_CUDA, "no CUDA device available: libthejoker_b200 has no CPU path");
+  if (device < 0 || device >= n_dev) return fail(TJB_E_INVALID, "device index out of range");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(TJB_E_CUDA, "device is not sm_100-class; this library is built for sm_100a only");
+
+  TjbHandle *h = new TjbHandle();
+  h->device = device;
+  h->n_sm = prop.multiProcessorCount;
+  h->cc_major = prop.major;
+  h->cc_minor = prop.minor;
+  const int N = h->N = spec->n_times, L = h->L = spec->n_linear;
+  StarHost &st = h->star;
+  st.N = N;
+  st.L = L;
+  st.t_ref = spec->t_ref;
+  st.t.assign(spec->t, spec->t + N);
+  st.rv.assign(spec->rv, spec->rv + N);
+  st.ivar.assign(spec->ivar, spec->ivar + N);
+  if (L > 1) st.trend.assign(spec->trend_M, spec->trend_M + (size_t)N * (L - 1));
+  memcpy(st.mu, spec->mu, sizeof(st.mu));
+  memcpy(st.Lambda, spec->Lambda, sizeof(st.Lambda));
+  st.K_prior_kind = spec->K_prior_kind;
+  st.jitter_mode = h->jitter_mode = spec->jitter_mode ? 1 : 0;
+  st.sigma_K0 = spec->sigma_K0;
+  st.P0 = spec->P0;
+  st.max_K = spec->max_K;
+  star_prepare(st);
+
+  int rc = build_jit_table(h);
+  if (rc == TJB_OK) rc = build_const_table(h, 0.0);
+  if (rc != TJB_OK) {
+    tjb_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return TJB_OK;
+}
+
+void tjb_destroy(TjbHandle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  h->tab_const.release(); h->tab_jit.release();
+  h->acc_mask.release(); h->acc_counts.release(); h->acc_offsets.release();
+  h->acc_totals.release(); h->misc.release();
+  for (int i = 0; i < 2; i++) {
+    h->host_stage[i].release(); h->host_ll[i].release();
+    if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]);
+    if (h->aux_event[i]) cudaEventDestroy(h->aux_event[i]);
+  }
+  delete h;
+}
+
+int tjb_set_stream(TjbHandle *h, void *cuda_stream) {
+  if (!h) return fail(TJB_E_INVALID, "null handle");
+  h->stream = (cudaStream_t)cuda_stream;
+  return TJB_OK;
+}
+
+int tjb_device_info(TjbHandle *h, int *n_sm, int *ctas_per_sm, int *cc_major, int *cc_minor) {
+  if (!h) return fail(TJB_E_INVALID, "null handle");
+  if (n_sm) *n_sm = h->n_sm;
+  if (ctas_per_sm) *ctas_per_sm = h->ll_ctas_per_sm;
+  if (cc_major) *cc_major = h->cc_major;
+  if (cc_minor) *cc_minor = h->cc_minor;
+  return TJB_OK;
+}
+
+int tjb_marginal_ll_soa(TjbHandle *h, const double *d_P, const double *d_e, const double *d_omega,
+                        const double *d_M0, const double *d_s, double s_const, int64_t n,
+                        double *d_ll, int64_t *d_llmax_key) {
+  if (!h) return fail(TJB_E_INVALID, "null handle");
+  if (n < 0) return fail(TJB_E_INVALID, "negative n");
+  if (n > 0 && (!d_P || !d_e || !d_omega || !d_M0 || !d_ll))
+    return fail(TJB_E_INVALID, "null device pointer");
+  PriorView pv = {d_P, d_e, d_omega, d_M0, d_s, nullptr, 0.0, nullptr};
+  return run_ll(h, pv, d_s == nullptr, s_const, n, d_ll, (long long *)d_llmax_key, h->stream);
+}
+
+int tjb_marginal_ll_aos(TjbHandle *h, const double *d_chunk, int uniform_s, int64_t n,
+                        double *d_ll, int64_t *d_llmax_key) {
+  if (!h) return fail(TJB_E_INVALID, "null handle");
+  if (n < 0) return fail(TJB_E_INVALID, "negative n");
+  if (n == 0) return TJB_OK;
+  if (!d_chunk || !d_ll) return fail(TJB_E_INVALID, "null device pointer");
+  CU(cudaSetDevice(h->device));
+  double s0 = 0.0;
+  if (uniform_s && h->jitter_mode) {
+    CU(cudaMemcpyAsync(&s0, d_chunk + 4, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  PriorView pv = {nullptr, nullptr, nullptr, nullptr, nullptr, d_chunk, 0.0, nullptr};
+  return run_ll(h, pv, uniform_s != 0, s0, n, d_ll, (long long *)d_llmax_key, h->stream);
+}
+
+int tjb_marginal_ll_host(TjbHandle *h, const double *h_chunk, int64_t n, double *h_ll) {
+  if (!h) return fail(TJB_E_INVALID, "null handle");
+  if (n < 0) return fail(TJB_E_INVALID, "negative n");
+  if (n == 0) return TJB_OK;
+  if (!h_chunk || !h_ll) return fail(TJB_E_INVALID, "null host pointer");
+  CU(cudaSetDevice(h->device));
+  // Optimistic execution: assume every row carries the jitter of row 0 (true for
+  // the default prior, s = const) and run the constant-jitter kernel, which also
+  // checks the assumption on the rows it reads; if any row disagrees, rerun with
+  // the per-sample-jitter kernel.  No host pass over the chunk is needed.
+  const double s0 = h_chunk[4];
+  const int64_t slice = 1 << 20;
+  for (int i = 0; i < 2; i++) {
+    if (!h->aux_stream[i]) CU(cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking));
+    const int64_t m = std::min(slice, n);
+    if (h->host_stage[i].ensure((size_t)m * 5 * sizeof(double)) ||
+        h->host_ll[i].ensure((size_t)m * sizeof(double)))
+      return fail(TJB_E_NOMEM, "cudaMalloc staging");
+  }
+  if (h->acc_totals.ensure(2 * sizeof(unsigned long long))) return fail(TJB_E_NOMEM, "cudaMalloc");
+  int *d_flag = (int *)h->acc_totals.p;
+  CU(cudaStreamSynchronize(h->stream));  // order after earlier work on the handle's stream
+  CU(cudaMemset(d_flag, 0, sizeof(int)));
+  for (int pass = 0; pass < 2; pass++) {
+    const bool uniform = (pass == 0);
+    if (!uniform && h->jitter_mode == 0) break;
+    int b = 0;
+    for (int64_t lo = 0; lo < n; lo += slice, b ^= 1) {
+      const int64_t m = std::min(slice, n - lo);
+      cudaStream_t st = h->aux_stream[b];
+      double *d_in = (double *)h->host_stage[b].p, *d_out = (double *)h->host_ll[b].p;
+      CU(cudaMemcpyAsync(d_in, h_chunk + 5 * lo, (size_t)m * 5 * sizeof(double),
+                         cudaMemcpyHostToDevice, st));
+      PriorView pv = {nullptr, nullptr, nullptr, nullptr, nullptr, d_in, s0,
+                      (uniform && h->jitter_mode) ? d_flag : nullptr};
+      int rc = run_ll(h, pv, uniform, s0, m, d_out, nullptr, st);
+      if (rc) return rc;
+      CU(cudaMemcpyAsync(h_ll + lo, d_out, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(h->aux_stream[0]));
+    CU(cudaStreamSynchronize(h->aux_stream[1]));
+    int flag = 0;
+    CU(cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (!flag) break;
+  }
+  return TJB_OK;
+}
+
+// ---- accept -----------------------------------------------------------------
+
+int64_t tjb_double_to_key(double x) { return (int64_t)ll_to_key(x); }
+double tjb_key_to_double(int64_t key) { return key_to_ll((long long)key); }
+
+int tjb_llmax_reset(TjbHandle *h, int64_t *d_llmax_key) {
+  if (!h || !d_llmax_key) return fail(TJB_E_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  const long long k = ll_to_key(-INFINITY);
+  CU(cudaMemcpyAsync(d_llmax_key, &k, sizeof(k), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return TJB_OK;
+}
+
+int tjb_llmax_update(TjbHandle *h, const double *d_ll, int64_t n, int64_t *d_llmax_key) {
+  if (!h || !d_llmax_key) return fail(TJB_E_INVALID, "null argument");
+  if (n <= 0) return TJB_OK;
+  CU(cudaSetDevice(h->device));
+  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)h->n_sm * 8);
+  llmax_update_kernel<<<grid, 256, 0, h->stream>>>(d_ll, n, (long long *)d_llmax_key);
+  CU(cudaGetLastError());
+  return TJB_OK;
+}
+
+int tjb_llmax_get(TjbHandle *h, const int64_t *d_llmax_key, double *h_max) {
+  if (!h || !d_llmax_key || !h_max) return fail(TJB_E_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  long long k = 0;
+  CU(cudaMemcpyAsync(&k, d_llmax_key, sizeof(k), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  *h_max = key_to_ll(k);
+  return TJB_OK;
+}
+
+int tjb_pcg64_uniform(TjbHandle *h, const TjbPcg64 *pcg, int64_t offset, int64_t n, double *d_out) {
+  if (!h || !pcg) return fail(TJB_E_INVALID, "null argument");
+  if (n <= 0) return TJB_OK;
+  if (!d_out) return fail(TJB_E_INVALID, "null device pointer");
+  CU(cudaSetDevice(h->device));
+  const int grid = (int)std::min<long long>((n + kAccThreads - 1) / kAccThreads, (long long)h->n_sm * 8);
+  const PcgParams pp = make_pcg(pcg, offset, (unsigned long long)grid * kAccThreads);
+  pcg64_uniform_kernel<<<grid, kAccThreads, 0, h->stream>>>(pp, n, d_out);
+  CU(cudaGetLastError());
+  return TJB_OK;
+}
+
+int tjb_accept(TjbHandle *h, const double *d_ll, int64_t n, const int64_t *d_llmax_key,
+               const double *d_uniforms, const TjbPcg64 *pcg, int64_t pcg_offset,
+               int64_t index_base, int64_t max_keep, double near_tol, int64_t *d_idx,
+               int64_t *h_counts) {
+  if (!h || !h_counts) return fail(TJB_E_INVALID, "null argument");
+  h_counts[0] = h_counts[1] = h_counts[2] = 0;
+  if (n <= 0) return TJB_OK;
+  if (!d_ll || !d_llmax_key) return fail(TJB_E_INVALID, "null device pointer");
+  if ((d_uniforms == nullptr) == (pcg == nullptr))
+    return fail(TJB_E_INVALID, "exactly one of d_uniforms / pcg must be given");
+  if (max_keep < 0) return fail(TJB_E_INVALID, "negative max_keep");
+  if (max_keep > 0 && !d_idx) return fail(TJB_E_INVALID, "null index buffer");
+  CU(cudaSetDevice(h->device));
+  const long long n_words = (n + 31) / 32;
+  const int n_cta = (int)((n_words + kAccWordsPerCta - 1) / kAccWordsPerCta);
+  if (h->acc_mask.ensure((size_t)n_words * sizeof(unsigned)) ||
+      h->acc_counts.ensure((size_t)n_cta * sizeof(unsigned)) ||
+      h->acc_offsets.ensure((size_t)n_cta * sizeof(unsigned long long)) ||
+      h->acc_totals.ensure(2 * sizeof(unsigned long long)))
+    return fail(TJB_E_NOMEM, "cudaMalloc accept scratch");
+  CU(cudaMemsetAsync(h->acc_totals.p, 0, 2 * sizeof(unsigned long long), h->stream));
+  const PcgParams pp = make_pcg(pcg, pcg_offset, kAccThreads);
+  accept_flag_kernel<<<n_cta, kAccThreads, 0, h->stream>>>(
+      d_ll, n, (const long long *)d_llmax_key, d_uniforms, pp, near_tol, (unsigned *)h->acc_mask.p,
+      (unsigned *)h->acc_counts.p, (unsigned long long *)h->acc_totals.p);
+  CU(cudaGetLastError());
+  accept_scan_kernel<<<1, 1024, 0, h->stream>>>((const unsigned *)h->acc_counts.p, n_cta,
+                                               (unsigned long long *)h->acc_offsets.p);
+  CU(cudaGetLastError());
+  if (max_keep > 0) {
+    accept_scatter_kernel<<<n_cta, kAccThreads, 0, h->stream>>>(
+        (const unsigned *)h->acc_mask.p, n, (const unsigned long long *)h->acc_offsets.p,
+        index_base, max_keep, (long long *)d_idx);
+    CU(cudaGetLastError());
+  }
+  unsigned long long tot[2] = {0, 0};
+  CU(cudaMemcpyAsync(tot, h->acc_totals.p, sizeof(tot), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h_counts[0] = (int64_t)tot[0];
+  h_counts[1] = std::min<int64_t>((int64_t)tot[0], max_keep);
+  h_counts[2] = (int64_t)tot[1];
+  return TJB_OK;
+}
+
+// ---- posterior ------------------------------------------------------------------
+
+static int posterior_common(TjbHandle *h, const double *h_rows, int64_t k, int clamp_K, int n_per,
+                            const double *h_normals, double *h_ll, double *h_a, double *h_A,
+                            double *h_draws) {
+  if (!h) return fail(TJB_E_INVALID, "null handle");
+  if (k < 0 || k > (1 << 30)) return fail(TJB_E_INVALID, "bad row count");
+  if (k == 0) return TJB_OK;
+  if (!h_rows) return fail(TJB_E_INVALID, "null rows");
+  CU(cudaSetDevice(h->device));
+  const int L = h->L;
+  const size_t b_rows = (size_t)k * 5 * 8, b_ll = (size_t)k * 8, b_a = (size_t)k * L * 8,
+               b_A = (size_t)k * L * L * 8;
+  const size_t b_nrm = h_draws ? (size_t)k * n_per * L * 8 : 0;
+  const size_t b_drw = h_draws ? (size_t)k * n_per * (5 + L) * 8 : 0;
+  if (h->misc.ensure(b_rows + b_ll + b_a + b_A + b_nrm + b_drw))
+    return fail(TJB_E_NOMEM, "cudaMalloc posterior scratch");
+  char *base = (char *)h->misc.p;
+  double *d_rows = (double *)base;
+  double *d_ll = (double *)(base + b_rows);
+  double *d_a = (double *)(base + b_rows + b_ll);
+  double *d_A = (double *)(base + b_rows + b_ll + b_a);
+  double *d_nrm = (double *)(base + b_rows + b_ll + b_a + b_A);
+  double *d_drw = (double *)(base + b_rows + b_ll + b_a + b_A + b_nrm);
+  CU(cudaMemcpyAsync(d_rows, h_rows, b_rows, cudaMemcpyHostToDevice, h->stream));
+  if (h_draws) CU(cudaMemcpyAsync(d_nrm, h_normals, b_nrm, cudaMemcpyHostToDevice, h->stream));
+  int rc = dispatch_posterior(h, d_rows, (int)k, clamp_K, n_per, h_draws ? d_nrm : nullptr, d_ll,
+                              d_a, d_A, h_draws ? d_drw : nullptr);
+  if (rc) return rc;
+  if (h_ll) CU(cudaMemcpyAsync(h_ll, d_ll, b_ll, cudaMemcpyDeviceToHost, h->stream));
+  if (h_a) CU(cudaMemcpyAsync(h_a, d_a, b_a, cudaMemcpyDeviceToHost, h->stream));
+  if (h_A) CU(cudaMemcpyAsync(h_A, d_A, b_A, cudaMemcpyDeviceToHost, h->stream));
+  if (h_draws) CU(cudaMemcpyAsync(h_draws, d_drw, b_drw, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return TJB_OK;
+}
+
+int tjb_posterior_aA(TjbHandle *h, const double *h_rows, int64_t k, int clamp_K, double *h_ll,
+                     double *h_a, double *h_A) {
+  return posterior_common(h, h_rows, k, clamp_K, 0, nullptr, h_ll, h_a, h_A, nullptr);
+}
+
+int tjb_posterior_draw(TjbHandle *h, const double *h_rows, int64_t k, int n_per, int clamp_K,
+                       const double *h_normals, double *h_out, double *h_ll) {
+  if (n_per < 1) return fail(TJB_E_INVALID, "n_per must be >= 1");
+  if (k > 0 && (!h_normals || !h_out)) return fail(TJB_E_INVALID, "null normals / output");
+  return posterior_common(h, h_rows, k, clamp_K, n_per, h_normals, h_ll, nullptr, nullptr, h_out);
+}
+
+int tjb_design_column(TjbHandle *h, const double *h_row, double *h_z, int32_t *h_stats) {
+  if (!h || !h_row || !h_z) return fail(TJB_E_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  const int N = h->N;
+  if (h->misc.ensure((size_t)N * 16 + 64)) return fail(TJB_E_NOMEM, "cudaMalloc");
+  double *d_dt = (double *)h->misc.p, *d_z = d_dt + N;
+  int *d_st = (int *)(d_z + N);
+  std::vector<double> dt(N);
+  for (int n = 0; n < N; n++) dt[n] = h->star.t[n] - h->star.t_ref;
+  CU(cudaMemcpyAsync(d_dt, dt.data(), (size_t)N * 8, cudaMemcpyHostToDevice, h->stream));
+  design_column_kernel<<<1, 32, 0, h->stream>>>(d_dt, N, h_row[0], h_row[1], h_row[2], h_row[3], 0.0, d_z,
+                                              d_st);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(h_z, d_z, (size_t)N * 8, cudaMemcpyDeviceToHost, h->stream));
+  int st[3] = {0, 0, 0};
+  CU(cudaMemcpyAsync(st, d_st, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (h_stats) { h_stats[0] = st[0]; h_stats[1] = st[1]; h_stats[2] = st[2]; }
+  return TJB_OK;
+}
+
+int tjb_fp64_peak(TjbHandle *h, int iters, double *h_tflops, double *h_ms) {
+  if (!h || !h_tflops) return fail(TJB_E_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  if (h->misc.ensure(64)) return fail(TJB_E_NOMEM, "cudaMalloc");
+  const int grid = h->n_sm * 8;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  fp64_peak_kernel<<<grid, 256, 0, h->stream>>>(iters / 8 + 1, (double *)h->misc.p);  // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    CU(cudaEventRecord(e0, h->stream));
+    fp64_peak_kernel<<<grid, 256, 0, h->stream>>>(iters, (double *)h->misc.p);
+    CU(cudaEventRecord(e1, h->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double flops = 2.0 * 8.0 * (double)iters * 256.0 * (double)grid;
+  *h_tflops = flops / (best * 1e-3) / 1e12;
+  if (h_ms) *h_ms = best;
+  return TJB_OK;
+}
+
+}  // extern "C"

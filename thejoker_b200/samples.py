@@ -1,0 +1,242 @@
+"""JokerSamples: prior / posterior samples as named columns with units.
+
+Keeps the slice of thejoker/samples.py the hot path uses: column access, ``pack`` /
+``unpack`` (samples.py:404-478), ``wrap_K`` (:392-401), ``median_period`` (:378-384),
+``mean/std``, ``t_ref / poly_trend / n_offsets`` metadata, ``par_names``, ``copy``,
+indexing, ``ln_unmarginalized_likelihood`` (:611-632) and a simple ``write/read``.
+The reference wraps an astropy QTable and writes HDF5 / FITS; astropy and h5py are
+not in the target image, so storage here is a numpy ``.npz`` (one array per column =
+the SoA layout the GPU wants).  Orbit objects (twobody) are out of scope.
+"""
+from __future__ import annotations
+
+import copy as _copy
+from collections import OrderedDict
+
+import numpy as np
+
+from . import units as u
+from .prior import (get_linear_equiv_units, get_nonlinear_equiv_units,
+                    get_v0_offsets_equiv_units, validate_n_offsets, validate_poly_trend)
+
+__all__ = ["JokerSamples"]
+
+# pyx:41-45
+_nonlinear_packed_order = ["P", "e", "omega", "M0", "s"]
+_nonlinear_internal_units = {"P": u.day, "e": u.one, "omega": u.radian, "M0": u.radian}
+
+
+class JokerSamples:
+    _hdf5_path = "samples"
+
+    def __init__(self, samples=None, t_ref=None, n_offsets=None, poly_trend=None, **kwargs):
+        poly_trend = 1 if poly_trend is None else poly_trend
+        n_offsets = 0 if n_offsets is None else n_offsets
+        if isinstance(samples, JokerSamples):
+            t_ref = samples.t_ref if t_ref is None else t_ref
+            poly_trend, n_offsets = samples.poly_trend, samples.n_offsets
+            samples = samples.tbl
+        poly_trend, _ = validate_poly_trend(poly_trend)
+        n_offsets, _ = validate_n_offsets(n_offsets)
+        valid_units = {**get_nonlinear_equiv_units(), **get_linear_equiv_units(poly_trend),
+                       **get_v0_offsets_equiv_units(n_offsets)}
+        valid_units["ln_prior"] = u.one
+        valid_units["ln_likelihood"] = u.one
+        valid_units["ln_posterior"] = u.one
+        self._valid_units = valid_units
+        self.tbl = OrderedDict()
+        self.meta = {"t_ref": t_ref, "poly_trend": poly_trend, "n_offsets": n_offsets}
+        self.meta.update(kwargs)
+        self._uniform_s = False
+        if samples is not None:
+            for k in samples.keys():
+                self[k] = samples[k]
+
+    # -- dict-like ---------------------------------------------------------
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            return self.tbl[key]
+        new = self.__class__(**self.meta)
+        for k, v in self.tbl.items():
+            new.tbl[k] = u.Quantity(np.atleast_1d(v.value[key]), v.unit)
+        new._uniform_s = self._uniform_s
+        return new
+
+    def __setitem__(self, key, val):
+        if key not in self._valid_units:
+            raise ValueError(f"Invalid parameter name '{key}'. Must be one of: "
+                             f"{list(self._valid_units)}")
+        if not isinstance(val, u.Quantity):
+            val = u.Quantity(val, u.one) if self._valid_units[key] == u.one else u.Quantity(val)
+        expected = self._valid_units[key]
+        if not val.unit.is_equivalent(expected):
+            raise u.UnitsError(f"Units of '{key}' samples ({val.unit}) are not compatible with "
+                               f"expected units ({expected})")
+        val = u.Quantity(np.atleast_1d(val.value), val.unit)
+        if self.tbl and len(val) != len(self):
+            raise ValueError(f"Column '{key}' has length {len(val)}, expected {len(self)}")
+        if key == "s":
+            self._uniform_s = False
+        self.tbl[key] = val
+
+    def __len__(self):
+        for v in self.tbl.values():
+            return len(v)
+        return 0
+
+    def keys(self):
+        return self.tbl.keys()
+
+    def __contains__(self, key):
+        return key in self.tbl
+
+    def __repr__(self):
+        return f'<JokerSamples [{", ".join(self.tbl.keys())}] ({len(self)} samples)>'
+
+    @property
+    def t_ref(self):
+        return self.meta["t_ref"]
+
+    @property
+    def poly_trend(self):
+        return self.meta["poly_trend"]
+
+    @property
+    def n_offsets(self):
+        return self.meta["n_offsets"]
+
+    @property
+    def par_names(self):
+        return [k for k in self.tbl.keys() if k not in ("ln_prior", "ln_likelihood", "ln_posterior")]
+
+    def copy(self):
+        new = self.__class__(**_copy.deepcopy(self.meta))
+        for k, v in self.tbl.items():
+            new.tbl[k] = v.copy()
+        new._uniform_s = self._uniform_s
+        return new
+
+    # -- statistics --------------------------------------------------------
+    def _apply(self, func):
+        new = self.__class__(**self.meta)
+        for k, v in self.tbl.items():
+            new.tbl[k] = u.Quantity(np.atleast_1d(func(v.value)), v.unit)
+        return new
+
+    def mean(self):
+        return self._apply(np.mean)
+
+    def std(self):
+        return self._apply(np.std)
+
+    def median_period(self):
+        """The sample at the median period (samples.py:378-384)."""
+        P = self["P"].value
+        idx = np.argpartition(P, len(P) // 2)[len(P) // 2]
+        return self[idx]
+
+    def wrap_K(self):
+        """Flip negative K to positive and rotate omega by pi (samples.py:392-401)."""
+        K = self.tbl["K"].value
+        mask = K < 0
+        if np.any(mask):
+            K[mask] = np.abs(K[mask])
+            om = self.tbl["omega"]
+            f = u.rad.to(om.unit)
+            om.value[mask] = (om.value[mask] + np.pi * f) % (2 * np.pi * f)
+        return self
+
+    # -- packing -----------------------------------------------------------
+    def pack(self, units=None, names=None, nonlinear_only=True):
+        """samples.py:404-445: one float64 (n, len(names)) array, units stripped."""
+        units = {} if units is None else dict(units)
+        out_units = OrderedDict()
+        for k, v in _nonlinear_internal_units.items():
+            units.setdefault(k, v)
+        if names is None:
+            names = _nonlinear_packed_order if nonlinear_only else self.par_names
+        arrs = []
+        for name in names:
+            unit = units.get(name, self.tbl[name].unit)
+            arrs.append(self.tbl[name].to_value(unit))
+            out_units[name] = u.as_unit(unit)
+        return np.stack(arrs, axis=1), out_units
+
+    def columns(self, units=None, names=None):
+        """SoA view used by the device path: list of contiguous float64 arrays in
+        the requested units (no (n,5) packing copy)."""
+        units = {} if units is None else dict(units)
+        for k, v in _nonlinear_internal_units.items():
+            units.setdefault(k, v)
+        names = _nonlinear_packed_order if names is None else names
+        return [np.ascontiguousarray(self.tbl[n].to_value(units.get(n, self.tbl[n].unit)),
+                                     dtype=np.float64) for n in names]
+
+    @classmethod
+    def unpack(cls, packed_samples, units, **kwargs):
+        """samples.py:447-478."""
+        packed_samples = np.array(packed_samples)
+        nsamples, npars = packed_samples.shape
+        samples = cls(**kwargs)
+        for i, k in enumerate(list(units.keys())[:npars]):
+            samples[k] = u.Quantity(packed_samples[:, i], units[k])
+        return samples
+
+    # -- storage -----------------------------------------------------------
+    def write(self, output, overwrite=False, append=False):
+        import os
+
+        if append and os.path.exists(output):
+            old = self.read(output)
+            merged = self.__class__(**old.meta)
+            for k in old.tbl:
+                merged.tbl[k] = u.Quantity(
+                    np.concatenate([old.tbl[k].value, self.tbl[k].to_value(old.tbl[k].unit)]),
+                    old.tbl[k].unit)
+            return merged.write(output, overwrite=True)
+        if os.path.exists(output) and not overwrite:
+            raise OSError(f"File {output} exists: use overwrite=True")
+        payload = {f"col:{k}": v.value for k, v in self.tbl.items()}
+        payload["__units__"] = np.array([f"{k}={v.unit.scale!r}|{v.unit.dims!r}"
+                                         for k, v in self.tbl.items()])
+        payload["__meta__"] = np.array([repr(self.meta)])
+        with open(output, "wb") as f:
+            np.savez(f, **payload)
+
+    @classmethod
+    def read(cls, filename):
+        import ast
+
+        with np.load(filename, allow_pickle=False) as z:
+            meta = ast.literal_eval(str(z["__meta__"][0]))
+            new = cls(**meta)
+            for entry in z["__units__"]:
+                k, spec = str(entry).split("=", 1)
+                scale, dims = spec.split("|")
+                unit = u.Unit(ast.literal_eval(dims), float(scale))
+                new.tbl[k] = u.Quantity(z[f"col:{k}"], unit)
+        return new
+
+    # -- (unmarginalised) likelihood of posterior samples ----------------------
+    def ln_unmarginalized_likelihood(self, data):
+        """samples.py:611-632, with the orbit evaluated by a plain numpy Kepler solve
+        (host side; a handful of posterior samples)."""
+        from .likelihood_helpers import ln_normal
+        from .synthetic import rv_curve
+
+        unit = data.rv.unit
+        data_rv = data.rv.value
+        data_var = data.rv_err.to_value(unit) ** 2
+        n = len(self)
+        s_vars = self["s"].to_value(unit) ** 2 if "s" in self.tbl else np.zeros(n)
+        t_ref = self.t_ref if self.t_ref is not None else data._t_ref_bmjd
+        dt = data._t_bmjd - t_ref
+        lls = np.full(n, np.nan)
+        for i in range(n):
+            model = rv_curve(data._t_bmjd, t_ref, self["P"].to_value(u.day)[i], self["e"].value[i],
+                             self["omega"].to_value(u.rad)[i], self["M0"].to_value(u.rad)[i],
+                             self["K"].to_value(unit)[i])
+            for j in range(self.poly_trend):
+                model = model + self[f"v{j}"].to_value(unit / u.day**j)[i] * dt**j
+            lls[i] = ln_normal(model, data_rv, data_var + s_vars[i]).sum()
+        return lls

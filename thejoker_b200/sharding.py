@@ -1,0 +1,217 @@
+"""Per-GPU shards of the prior cache: the replacement for the reference's
+schwimmbad chunk pool (thejoker/multiproc_helpers.py:17-60, utils.py:22-72).
+
+The reference maps contiguous chunks of prior samples over pool workers, each of
+which re-reads its rows from a shared HDF5 file and returns a float64[n_i] array that
+the master concatenates; max / compare / where then run serially on the master
+(multiproc_helpers.py:256-258).  Here a shard is a contiguous index range resident on
+one GPU (same split rule, so concatenating shards in order reproduces the global
+index order); ll never leaves the device, the only exchange is the 8-byte max key
+(integer MAX all-reduce over NCCL when the shards live in different processes) and
+the accepted indices.
+
+Two deployments share this code:
+  * one process driving several GPUs (``DeviceEngine(devices=[0, 1, ...])``) -- keys
+    are combined on the host;
+  * one process per GPU under torchrun (``DeviceEngine(..., group=dist.group.WORLD)``)
+    -- every rank holds its own shard; keys are combined with ``dist.all_reduce(MAX)``
+    and accepted indices with ``all_gather``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+__all__ = ["batch_tasks", "shard_ranges", "DeviceEngine", "merge_accepted"]
+
+
+def batch_tasks(n_tasks, n_batches, arr=None, args=None, start_idx=0):
+    """thejoker/utils.py:22-72: equal contiguous split, the first ``n_tasks % n_batches``
+    batches get one extra task."""
+    args = [] if args is None else list(args)
+    tasks = []
+    if n_batches > 0 and n_tasks >= n_batches:
+        base, rmdr = divmod(n_tasks, n_batches)
+        i1 = start_idx
+        for i in range(n_batches):
+            i2 = i1 + base + (1 if i < rmdr else 0)
+            tasks.append([(i1, i2) if arr is None else arr[i1:i2], i1] + args)
+            i1 = i2
+    else:
+        if arr is None:
+            tasks.append([(start_idx, n_tasks + start_idx), start_idx] + args)
+        else:
+            tasks.append([arr[start_idx:n_tasks + start_idx], start_idx] + args)
+    return tasks
+
+
+def shard_ranges(n, n_shards):
+    """[(lo, hi)] per shard; always n_shards entries (empty ranges when n < n_shards)."""
+    if n >= n_shards:
+        return [t[0] for t in batch_tasks(n, n_shards)]
+    return [(min(i, n), min(i + 1, n)) for i in range(n_shards)]
+
+
+def merge_accepted(per_shard_idx, per_shard_total, max_keep):
+    """Concatenate ascending per-shard index lists in shard order and truncate to
+    max_keep -- ``good_samples_idx[:max_posterior_samples]`` (likelihood_helpers.py:109)."""
+    idx = np.concatenate([np.asarray(a, dtype=np.int64) for a in per_shard_idx]) \
+        if per_shard_idx else np.zeros(0, dtype=np.int64)
+    total = int(np.sum(per_shard_total))
+    if max_keep is not None:
+        idx = idx[:max_keep]
+    return idx, total
+
+
+class _Shard:
+    __slots__ = ("device", "helper", "lo", "hi", "cols", "s", "ll", "key")
+
+
+class DeviceEngine:
+    """The prior cache, sharded over GPUs, with the hot-path operations on it.
+
+    Parameters
+    ----------
+    make_helper : callable(device) -> CJokerHelper
+    columns : [P, e, omega, M0, s] host float64 arrays in internal units (s may be
+        None or a scalar for a constant jitter) -- the *local* part of the cache when
+        ``group`` is given, the whole cache otherwise.
+    devices : list of CUDA device indices driven by this process.
+    group : torch.distributed process group, or None.  With a group, this process's
+        columns are the shard of rank ``dist.get_rank(group)`` and ``global_offset``
+        is its first global index.
+    """
+
+    def __init__(self, make_helper, columns, devices=(0,), group=None, global_offset=0,
+                 global_size=None):
+        import torch
+
+        self.torch = torch
+        self.group = group
+        P, e, om, M0, s = columns
+        n_local = len(P)
+        self.n_local = n_local
+        self.global_offset = int(global_offset)
+        self.n_global = int(n_local if global_size is None else global_size)
+        s_is_scalar = s is None or np.ndim(s) == 0
+        self.s_const = 0.0 if s is None else (float(s) if s_is_scalar else 0.0)
+        if not s_is_scalar and n_local > 0 and np.all(s == s[0]):
+            s_is_scalar, self.s_const = True, float(s[0])
+        self.shards = []
+        for d, (lo, hi) in zip(devices, shard_ranges(n_local, len(devices))):
+            sh = _Shard()
+            sh.device, sh.lo, sh.hi = d, lo, hi
+            sh.helper = make_helper(d)
+            with torch.cuda.device(d):
+                up = lambda a: torch.from_numpy(np.ascontiguousarray(a[lo:hi], dtype=np.float64)) \
+                    .to(f"cuda:{d}", non_blocking=False)
+                sh.cols = [up(P), up(e), up(om), up(M0)]
+                sh.s = None if s_is_scalar else up(s)
+                sh.ll = torch.full((hi - lo,), float("nan"), dtype=torch.float64, device=f"cuda:{d}")
+                sh.key = sh.helper.new_llmax_key()
+            self.shards.append(sh)
+
+    # -- likelihood -----------------------------------------------------------
+    def compute_ll(self, lo=0, hi=None):
+        """ll[lo:hi) (local indices) on every shard that intersects the range; the
+        shard's running-max key is updated.  Asynchronous."""
+        hi = self.n_local if hi is None else hi
+        torch = self.torch
+        for sh in self.shards:
+            a, b = max(lo, sh.lo), min(hi, sh.hi)
+            if a >= b:
+                continue
+            with torch.cuda.device(sh.device):
+                sl = slice(a - sh.lo, b - sh.lo)
+                sh.helper.marginal_ll_soa(*[c[sl] for c in sh.cols],
+                                          s=None if sh.s is None else sh.s[sl],
+                                          s_const=self.s_const, out=sh.ll[sl], llmax_key=sh.key)
+
+    def reset_max(self):
+        for sh in self.shards:
+            with self.torch.cuda.device(sh.device):
+                sh.key = sh.helper.new_llmax_key()
+
+    def synchronize(self):
+        for sh in self.shards:
+            self.torch.cuda.synchronize(sh.device)
+
+    def global_max_key(self):
+        """Combine the shard keys: host max within the process, then an integer MAX
+        all-reduce across processes (NCCL).  Every shard's key tensor is overwritten
+        with the global key so the accept kernels read it from device memory."""
+        torch = self.torch
+        keys = [sh.key for sh in self.shards]
+        if len(keys) > 1:
+            m = max(int(k.item()) for k in keys)
+            for k in keys:
+                k.fill_(m)
+        if self.group is not None:
+            import torch.distributed as dist
+
+            k0 = keys[0]
+            if dist.get_backend(self.group) == "gloo":
+                tmp = k0.cpu()
+                dist.all_reduce(tmp, op=dist.ReduceOp.MAX, group=self.group)
+                k0.copy_(tmp)
+            else:
+                dist.all_reduce(k0, op=dist.ReduceOp.MAX, group=self.group)
+            for k in keys[1:]:
+                k.copy_(k0.to(k.device))
+        return keys[0]
+
+    def max_value(self):
+        sh = self.shards[0]
+        return sh.helper.llmax_value(sh.key)
+
+    # -- accept ---------------------------------------------------------------
+    def accept(self, rng, hi=None, max_keep=None, uniforms=None, near_tol=1e-12):
+        """Global ``where(exp(ll - max) > u)[0][:max_keep]`` over local [0, hi).
+
+        ``rng``: numpy Generator.  On PCG64 the uniforms are generated on the device
+        from the generator's state (sample with global index g uses the g-th double)
+        and the caller advances the generator by the global count afterwards; on any
+        other bit generator pass host ``uniforms`` for the local range instead.
+        Returns (global indices int64 ascending, n_accepted_total, n_near).
+        """
+        torch = self.torch
+        hi = self.n_local if hi is None else hi
+        self.global_max_key()
+        per_idx, per_tot, near = [], [], 0
+        for sh in self.shards:
+            a, b = sh.lo, min(hi, sh.hi)
+            if a >= b:
+                continue
+            with torch.cuda.device(sh.device):
+                ll = sh.ll[: b - a]
+                if uniforms is not None:
+                    u_dev = torch.from_numpy(np.ascontiguousarray(uniforms[a:b])).to(ll.device)
+                    idx, tot, nn = sh.helper.accept(ll, sh.key, uniforms=u_dev,
+                                                    index_base=self.global_offset + a,
+                                                    max_keep=max_keep, near_tol=near_tol)
+                else:
+                    idx, tot, nn = sh.helper.accept(ll, sh.key, rng=rng,
+                                                    rng_offset=self.global_offset + a,
+                                                    index_base=self.global_offset + a,
+                                                    max_keep=max_keep, near_tol=near_tol)
+                per_idx.append(idx.cpu().numpy())
+                per_tot.append(tot)
+                near += nn
+        idx, total = merge_accepted(per_idx, per_tot, max_keep)
+        if self.group is not None:
+            import torch.distributed as dist
+
+            gathered = [None] * dist.get_world_size(self.group)
+            dist.all_gather_object(gathered, (idx, total, near), group=self.group)
+            idx, total = merge_accepted([g[0] for g in gathered], [g[1] for g in gathered], max_keep)
+            near = sum(g[2] for g in gathered)
+        return idx, total, near
+
+    # -- host access ------------------------------------------------------------
+    def download_ll(self, lo=0, hi=None):
+        hi = self.n_local if hi is None else hi
+        out = np.empty(hi - lo)
+        for sh in self.shards:
+            a, b = max(lo, sh.lo), min(hi, sh.hi)
+            if a < b:
+                out[a - lo:b - lo] = sh.ll[a - sh.lo:b - sh.lo].cpu().numpy()
+        return out

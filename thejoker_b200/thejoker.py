@@ -1,0 +1,288 @@
+"""TheJoker: the orchestrator of thejoker/thejoker.py with the same public methods
+(``marginal_ln_likelihood``, ``rejection_sample``, ``iterative_rejection_sample``),
+driving device-resident shards instead of a schwimmbad pool.
+
+RNG contract: ``self.rng`` is a numpy Generator and is
+consumed exactly as the reference consumes it --
+  * in_memory=True  (likelihood_helpers.py:91-229): ``rng.uniform(size=n)`` once
+    (once per round over all accumulated lls for the iterative sampler), then the
+    linear-parameter draws from the same generator;
+  * in_memory=False (multiproc_helpers.py:185-427): optional
+    ``rng.choice(n_total, size=n, replace=False)``, ``rng.uniform(size=n)``, then
+    linear draws from per-task child generators spawned from the generator's seed
+    sequence (multiproc_helpers.py:49-54).
+On a PCG64 generator the n uniforms are produced on the GPU from the generator's
+state, bit-identical to ``rng.uniform(size=n)``, and the host generator is advanced
+by n; other bit generators fall back to drawing on the host and uploading.
+"""
+from __future__ import annotations
+
+import logging
+import os
+
+import numpy as np
+
+from . import units as u
+from .data_helpers import validate_prepare_data
+from .helper import CJokerHelper
+from .prior import JokerPrior
+from .samples import JokerSamples
+from .sharding import DeviceEngine, batch_tasks
+
+__all__ = ["TheJoker"]
+
+logger = logging.getLogger("thejoker_b200")
+
+
+def _is_pcg64(rng):
+    return type(rng.bit_generator).__name__ == "PCG64"
+
+
+class TheJoker:
+    """A custom Monte-Carlo sampler for two-body systems (thejoker.py:23-85).
+
+    Parameters
+    ----------
+    prior : JokerPrior
+    pool : optional object with ``map`` and ``close`` (accepted for signature
+        compatibility; the work is sharded over ``devices`` instead)
+    rng : numpy.random.Generator (optional)
+    tempfile_path : str (optional, unused: no temporary cache file is written)
+    devices : list of CUDA device indices (default: [LOCAL_RANK or 0])
+    jitter_mode : "apply" | "reference" -- see CJokerHelper
+    """
+
+    def __init__(self, prior, pool=None, rng=None, tempfile_path=None, devices=None,
+                 jitter_mode="apply"):
+        if pool is not None and (not hasattr(pool, "map") or not hasattr(pool, "close")):
+            raise TypeError("Input pool object must have .map() and .close() methods.")
+        self.pool = pool
+        if rng is None:
+            rng = np.random.default_rng()
+        elif not isinstance(rng, np.random.Generator):
+            raise TypeError("The input random number generator must be a "
+                            "numpy.random.Generator instance.")
+        self.rng = rng
+        if not isinstance(prior, JokerPrior):
+            raise TypeError("The input prior must be a JokerPrior instance.")
+        self.prior = prior
+        if tempfile_path is None:
+            self._tempfile_path = os.path.expanduser("~/.thejoker/")
+        else:
+            self._tempfile_path = os.path.abspath(os.path.expanduser(tempfile_path))
+        if devices is None:
+            devices = [int(os.environ.get("LOCAL_RANK", "0"))]
+        self.devices = list(devices)
+        self.jitter_mode = jitter_mode
+        self.last_stats = {}
+
+    @property
+    def tempfile_path(self):
+        os.makedirs(self._tempfile_path, exist_ok=True)
+        return self._tempfile_path
+
+    # -- helpers ----------------------------------------------------------------
+    def _make_joker_helper(self, data, device=None):
+        """thejoker.py:87-91."""
+        all_data, ids, trend_M = validate_prepare_data(data, self.prior.poly_trend,
+                                                       self.prior.n_offsets)
+        device = self.devices[0] if device is None else device
+        return CJokerHelper(all_data, self.prior, trend_M, device=device,
+                            jitter_mode=self.jitter_mode)
+
+    def _columns(self, helper, prior_samples):
+        """[P, e, omega, M0, s] host columns in internal units + optional ln_prior."""
+        if isinstance(prior_samples, str):
+            prior_samples = JokerSamples.read(prior_samples)
+        if isinstance(prior_samples, JokerSamples):
+            cols = prior_samples.columns(units=helper.internal_units, names=helper.packed_order)
+            if prior_samples._uniform_s and len(cols[4]):
+                cols[4] = float(cols[4][0])
+            ln_prior = prior_samples["ln_prior"].value if "ln_prior" in prior_samples else None
+            return cols, ln_prior
+        arr = np.asarray(prior_samples, dtype=np.float64)
+        if arr.ndim != 2 or arr.shape[1] != 5:
+            raise ValueError("packed prior samples must have shape (n, 5)")
+        return [np.ascontiguousarray(arr[:, i]) for i in range(5)], None
+
+    def _engine(self, data, cols):
+        helpers = {}
+
+        def make(d):
+            if d not in helpers:
+                helpers[d] = self._make_joker_helper(data, device=d)
+            return helpers[d]
+
+        eng = DeviceEngine(make, cols, devices=self.devices)
+        return eng, helpers[self.devices[0]]
+
+    @staticmethod
+    def _rows(cols, idx):
+        out = np.empty((len(idx), 5))
+        for j, c in enumerate(cols):
+            out[:, j] = c if np.ndim(c) == 0 else c[idx]
+        return out
+
+    def _uniform_accept(self, eng, n_accum, max_keep):
+        """One accept pass over the first n_accum samples, consuming
+        ``rng.uniform(size=n_accum)`` from self.rng."""
+        if _is_pcg64(self.rng):
+            idx, total, near = eng.accept(self.rng, hi=n_accum, max_keep=max_keep)
+            self.rng.bit_generator.advance(int(n_accum))
+        else:
+            uu = self.rng.uniform(size=n_accum)
+            idx, total, near = eng.accept(self.rng, hi=n_accum, max_keep=max_keep, uniforms=uu)
+        self.last_stats.update(n_accepted=total, n_near_threshold=near, ll_max=eng.max_value())
+        return idx, total
+
+    def _full_samples(self, helper, rows, rng, n_linear_samples, in_memory, n_batches):
+        """make_full_samples_inmem (likelihood_helpers.py:69-88) / make_full_samples
+        (multiproc_helpers.py:150-182, with per-task child generators)."""
+        if in_memory:
+            raw, _ = helper.batch_get_posterior_samples(rows, n_linear_samples, rng)
+        else:
+            n_batches = 1 if n_batches is None else n_batches  # max(1, SerialPool.size)
+            tasks = batch_tasks(len(rows), n_batches, arr=rows)
+            sg = rng.bit_generator._seed_seq.spawn(len(tasks))
+            parts = []
+            for task, seq in zip(tasks, sg):
+                child = np.random.Generator(np.random.PCG64(seq))
+                parts.append(helper.batch_get_posterior_samples(task[0], n_linear_samples, child)[0])
+            raw = np.concatenate(parts) if parts else np.zeros((0, 5 + helper.n_linear))
+        return JokerSamples.unpack(raw, helper.internal_units, t_ref=helper.data.t_ref,
+                                   poly_trend=self.prior.poly_trend, n_offsets=self.prior.n_offsets)
+
+    # -- public API -------------------------------------------------------------
+    def marginal_ln_likelihood(self, data, prior_samples, n_batches=None, in_memory=False):
+        """Marginal log-likelihood at each prior sample (thejoker.py:93-138).  Returns
+        a numpy array; the computation runs on the configured GPUs."""
+        helper0 = self._make_joker_helper(data)
+        cols, _ = self._columns(helper0, prior_samples)
+        eng, _ = self._engine(data, cols)
+        eng.compute_ll()
+        return eng.download_ll()
+
+    def rejection_sample(self, data, prior_samples, n_prior_samples=None,
+                         max_posterior_samples=None, n_linear_samples=1, return_logprobs=False,
+                         return_all_logprobs=False, n_batches=None, randomize_prior_order=False,
+                         in_memory=False):
+        """Rejection sampling (thejoker.py:140-257)."""
+        helper0 = self._make_joker_helper(data)
+        if isinstance(prior_samples, (int, np.integer)):
+            prior_samples = self.prior.sample(size=int(prior_samples),
+                                              return_logprobs=return_logprobs, rng=self.rng)
+        cols, ln_prior = self._columns(helper0, prior_samples)
+        n_total = len(cols[0])
+        if return_logprobs and ln_prior is None:
+            raise RuntimeError("return_logprobs=True but ln_prior values not found in prior "
+                               "samples: generate them with prior.sample(..., "
+                               "return_logprobs=True)")
+        sel = None
+        if in_memory:
+            n_use = n_total  # likelihood_helpers.py:91-127 uses every row it is given
+        else:
+            if n_prior_samples is None:
+                n_use = n_total
+            elif n_prior_samples > n_total:
+                raise ValueError("Number of prior samples to use is greater than the number of "
+                                 f"prior samples passed. n_prior_samples={n_prior_samples} vs. "
+                                 f"n_total_samples={n_total}")
+            else:
+                n_use = int(n_prior_samples)
+            if randomize_prior_order:  # multiproc_helpers.py:245-248
+                sel = self.rng.choice(n_total, size=n_use, replace=False)
+                cols = [c if np.ndim(c) == 0 else c[sel] for c in cols]
+            elif n_use < n_total:
+                cols = [c if np.ndim(c) == 0 else c[:n_use] for c in cols]
+        if max_posterior_samples is None:
+            max_posterior_samples = n_use
+
+        eng, helper = self._engine(data, cols)
+        eng.compute_ll()
+        good, _ = self._uniform_accept(eng, n_use, max_posterior_samples)
+        full_idx = good if sel is None else sel[good]
+
+        samples = self._full_samples(helper, self._rows(cols, good), self.rng, n_linear_samples,
+                                     in_memory, n_batches)
+        lls = None
+        if return_logprobs or return_all_logprobs:
+            lls = eng.download_ll()
+        if return_logprobs:
+            samples["ln_prior"] = np.repeat(ln_prior[full_idx], n_linear_samples)
+            samples["ln_likelihood"] = np.repeat(lls[good], n_linear_samples)
+        if return_all_logprobs:
+            return samples, lls
+        return samples
+
+    def iterative_rejection_sample(self, data, prior_samples, n_requested_samples,
+                                   max_prior_samples=None, n_linear_samples=1,
+                                   return_logprobs=False, n_batches=None,
+                                   randomize_prior_order=False, init_batch_size=None,
+                                   growth_factor=128, in_memory=False):
+        """Adaptive rejection sampling (thejoker.py:259-370;
+        likelihood_helpers.py:130-229; multiproc_helpers.py:289-427)."""
+        helper0 = self._make_joker_helper(data)
+        cols, ln_prior = self._columns(helper0, prior_samples)
+        n_total = len(cols[0])
+        if return_logprobs and ln_prior is None:
+            raise RuntimeError("return_logprobs=True but ln_prior values not found in prior "
+                               "samples")
+        maxiter = 128
+        if in_memory:
+            safety_factor, n_max = 1, n_total            # likelihood_helpers.py:144-145
+        else:
+            safety_factor = 4                            # multiproc_helpers.py:333-334
+            n_max = n_total if max_prior_samples is None else int(max_prior_samples)
+        n_process = growth_factor * n_requested_samples if init_batch_size is None \
+            else init_batch_size
+        if n_process > n_max:
+            raise ValueError("Prior sample library not big enough! For iterative sampling, you "
+                             "have to have at least growth_factor * n_requested_samples = "
+                             f"{growth_factor * n_requested_samples} samples in the prior samples "
+                             f"cache file. You have, or have limited to, {n_max} samples.")
+        if not in_memory and randomize_prior_order:      # multiproc_helpers.py:350-354
+            all_idx = self.rng.choice(n_total, size=n_max, replace=False)
+            cols = [c if np.ndim(c) == 0 else c[all_idx] for c in cols]
+        else:
+            all_idx = np.arange(0, n_max, 1)
+            if n_max < n_total:
+                cols = [c if np.ndim(c) == 0 else c[:n_max] for c in cols]
+
+        eng, helper = self._engine(data, cols)
+        start_idx = 0
+        n_accum = 0
+        good = np.zeros(0, dtype=np.int64)
+        for i in range(maxiter):
+            logger.log(1, f"iteration {i}, computing {n_process} likelihoods")
+            eng.compute_ll(start_idx, start_idx + n_process)
+            n_accum = start_idx + n_process
+            good, n_good = self._uniform_accept(eng, n_accum, None)
+            ll_max = self.last_stats["ll_max"]
+            if in_memory and not np.isfinite(ll_max):
+                # likelihood_helpers.py:173-176 *returns* this error object
+                return RuntimeError(f"There are NaN or Inf likelihood values in iteration step {i}!")
+            if n_good == 0:
+                raise RuntimeError("Failed to find any good samples!")
+            logger.log(1, f"{n_good} good samples after rejection sampling")
+            if n_good >= n_requested_samples:
+                break
+            start_idx += n_process
+            n_need = n_requested_samples - n_good
+            n_process = int(safety_factor * n_need / n_good * n_accum)
+            if start_idx + n_process > n_max:
+                n_process = n_max - start_idx
+            if n_process <= 0:
+                break
+        else:
+            raise RuntimeError("Hit maximum number of iterations!")
+
+        good = good[:n_requested_samples]
+        full_idx = all_idx[good]
+        samples = self._full_samples(helper, self._rows(cols, good), self.rng, n_linear_samples,
+                                     in_memory, n_batches)
+        if return_logprobs:
+            lls = eng.download_ll(0, n_accum)
+            samples["ln_prior"] = np.repeat(ln_prior[full_idx], n_linear_samples)
+            samples["ln_likelihood"] = np.repeat(lls[good], n_linear_samples)
+        self.last_stats["n_ll_evaluated"] = n_accum
+        return samples
