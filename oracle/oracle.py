@@ -75,6 +75,25 @@ def _lapack_pointers():
     return out
 
 
+_blas_limited = False
+
+
+def _limit_blas_threads():
+    """The oracle parallelises over prior samples (OpenMP); the L x L / N x N LAPACK
+    calls inside each thread must stay single-threaded (scipy's OpenBLAS is a pthreads
+    build and warns / oversubscribes when entered from an OpenMP region)."""
+    global _blas_limited
+    if _blas_limited:
+        return
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=1, user_api="blas")
+    except Exception:
+        pass
+    _blas_limited = True
+
+
 def load(use_lapack: bool = True):
     global _lib
     if _lib is None:
@@ -96,6 +115,7 @@ def load(use_lapack: bool = True):
         lib.orc_truth_posterior_aA.argtypes = [ctypes.POINTER(OrcSpec), _dp, ctypes.c_int, _dp, _dp]
         _lib = lib
     if use_lapack:
+        _limit_blas_threads()
         _lib.orc_set_lapack(*_lapack_pointers())
     else:
         _lib.orc_set_lapack(None, None, None)

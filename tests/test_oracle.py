@@ -1,0 +1,155 @@
+"""The CPU oracle against itself: the C restatement (LAPACK-bound, as the reference's
+Cython) vs the numpy restatement of the reference's pure-Python test oracle, vs the
+quad-precision truth, vs the committed golden vectors.  Mirrors the structure of the
+reference's own cross-implementation tests
+(thejoker/src/tests/test_fast_likelihood.py:20-135), which compare two
+implementations at np.allclose tolerance on 3-epoch data."""
+import glob
+import os
+
+import numpy as np
+import pytest
+from helpers import prior_chunk, rel_err, star_spec
+
+from oracle import py_oracle
+from oracle.oracle import (OracleHelper, batch_tasks_ranges, iterative_rejection_indices,
+                           near_threshold_count, rejection_accept)
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def _spec_from_npz(z):
+    keys = ("t", "rv", "ivar", "t0", "trend_M", "mu", "Lambda", "K_prior_kind", "sigma_K0", "P0",
+            "max_K", "jitter_mode")
+    spec = {k: (z[k] if z[k].ndim else z[k].item()) for k in keys}
+    spec["n_times"], spec["n_linear"] = len(spec["t"]), 1 + np.atleast_2d(spec["trend_M"]).shape[1]
+    return spec
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_oracle_reproduces_golden(path):
+    z = np.load(path)
+    spec = _spec_from_npz(z)
+    orc = OracleHelper.from_spec(spec)
+    ll = orc.batch_marginal_ln_likelihood(z["chunk"])
+    # same machine class, same LAPACK: tight, but not bit-exact across OpenBLAS kernels
+    assert np.max(rel_err(ll, z["ll"])) < 1e-11
+    good = rejection_accept(ll, z["uniforms"])
+    near = near_threshold_count(ll, z["uniforms"])
+    assert near > 0 or np.array_equal(good, z["good"])
+    lls, a, Ainv = orc.posterior_aAinv(z["chunk"][:16])
+    assert np.allclose(a, z["post_a"], rtol=1e-9, atol=1e-12)
+    assert np.allclose(np.linalg.inv(Ainv), z["post_A"], rtol=1e-8)
+
+
+def test_against_py():
+    """test_fast_likelihood.py::test_against_py: custom Normal K prior, 3 epochs."""
+    spec, _, _ = star_spec(3, 1, normal_K=10.0)
+    chunk = prior_chunk(512)
+    ll_c = OracleHelper.from_spec(spec).batch_marginal_ln_likelihood(chunk)
+    ll_py = py_oracle.marginal_ln_likelihood(chunk, spec)
+    assert np.allclose(ll_c, ll_py)
+    assert np.max(rel_err(ll_c, ll_py)) < 1e-9
+
+
+def test_scale_varK_against_py():
+    """test_fast_likelihood.py::test_scale_varK_against_py: FixedCompanionMass K."""
+    spec, _, _ = star_spec(3, 1)
+    chunk = prior_chunk(512)
+    ll_c = OracleHelper.from_spec(spec).batch_marginal_ln_likelihood(chunk)
+    ll_py = py_oracle.marginal_ln_likelihood(chunk, spec)
+    assert np.allclose(ll_c, ll_py)
+    assert np.max(rel_err(ll_c, ll_py)) < 1e-9
+
+
+def test_likelihood_helpers():
+    """test_fast_likelihood.py::test_likelihood_helpers: a, A, b, B per sample."""
+    spec, _, _ = star_spec(3, 1, normal_K=1.0)
+    chunk = prior_chunk(16)
+    orc = OracleHelper.from_spec(spec)
+    for row in chunk:
+        ll = orc.test_likelihood_worker(row)
+        assert np.abs(ll) < 1e8
+        M = py_oracle.design_matrix(row, spec["t"], spec["t0"], spec["trend_M"])
+        _, b, B, a, A = py_oracle.likelihood_worker(spec["rv"], spec["ivar"], M, spec["mu"],
+                                                    spec["Lambda"], make_aA=True)
+        assert np.allclose(orc.a, a) and np.allclose(orc.A, A)
+        assert np.allclose(orc.b, b) and np.allclose(orc.B, B)
+
+
+@pytest.mark.parametrize("N,pt,sl", [(16, 1, None), (64, 1, None), (64, 2, (-2.0, 1.0)), (12, 3, None)])
+def test_oracle_vs_quad_truth(N, pt, sl):
+    spec, _, _ = star_spec(N, pt)
+    chunk = prior_chunk(1024, s_lognormal=sl)
+    orc = OracleHelper.from_spec(spec)
+    ll = orc.batch_marginal_ln_likelihood(chunk, n_threads=0)
+    truth, kappa = orc.truth_ll(chunk)
+    # generic prior draws: the reference algorithm is good to ~1e-9 relative at worst
+    assert np.max(rel_err(ll, truth)) < 5e-9
+    assert np.median(rel_err(ll, truth)) < 1e-13
+
+
+def test_builtin_lu_matches_lapack():
+    spec, _, _ = star_spec(16, 2)
+    chunk = prior_chunk(256)
+    a = OracleHelper.from_spec(spec, use_lapack=True).batch_marginal_ln_likelihood(chunk)
+    b = OracleHelper.from_spec(spec, use_lapack=False).batch_marginal_ln_likelihood(chunk)
+    OracleHelper.from_spec(spec, use_lapack=True)  # restore the binding for later tests
+    assert np.max(rel_err(a, b)) < 1e-10
+
+
+def test_jitter_reference_bug_switch():
+    """jitter_mode=0 reproduces the reference as written: s has no effect
+    (fast_likelihood.pyx:458 writes s_ivar, nothing reads it)."""
+    spec, _, _ = star_spec(16, 1, jitter_mode="reference")
+    chunk = prior_chunk(128, s_lognormal=(0.0, 1.0))
+    chunk0 = chunk.copy()
+    chunk0[:, 4] = 0.0
+    orc = OracleHelper.from_spec(spec)
+    assert np.array_equal(orc.batch_marginal_ln_likelihood(chunk),
+                          orc.batch_marginal_ln_likelihood(chunk0))
+    spec1 = dict(spec, jitter_mode=1)
+    ll1 = OracleHelper.from_spec(spec1).batch_marginal_ln_likelihood(chunk)
+    assert not np.allclose(ll1, orc.batch_marginal_ln_likelihood(chunk0))
+    assert np.max(rel_err(ll1, py_oracle.marginal_ln_likelihood(chunk, spec1))) < 1e-9
+
+
+def test_kepler_variant_sensitivity():
+    """The two plausible readings of twobody's Newton loop (update-then-test vs
+    test-then-update, both with tol 1e-10) agree on ll far below the 1e-10 gate for
+    generic samples; the residual spread is what 'parity unpinned' can cost."""
+    spec, _, _ = star_spec(64, 1)
+    chunk = prior_chunk(2048)
+    a = OracleHelper.from_spec(spec, kepler_variant=0).batch_marginal_ln_likelihood(chunk, 0)
+    b = OracleHelper.from_spec(spec, kepler_variant=1).batch_marginal_ln_likelihood(chunk, 0)
+    r = rel_err(a, b)
+    print('kepler variant spread: median %.2e max %.2e' % (np.median(r), np.max(r)))
+    assert np.median(r) < 1e-12
+    assert np.max(r) < 1e-7  # rare samples: residual ~1e-10 amplified by d ll / d z
+
+
+def test_kepler_solver_residual():
+    from oracle.oracle import load
+
+    lib = load()
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        e, M = rng.beta(0.867, 3.03), rng.uniform(-50, 50)
+        E = lib.orc_eccentric_anomaly(M, e, 1e-10, 128, 0)
+        assert abs(E - e * np.sin(E) - M) < 1e-13 * max(1, abs(M))
+
+
+def test_accept_rule_and_iterative_logic():
+    rng = np.random.default_rng(3)
+    lls = rng.normal(-50, 3, size=5000)
+    uu = rng.uniform(size=5000)
+    good = rejection_accept(lls, uu, 7)
+    assert np.all(np.diff(good) > 0) and len(good) <= 7
+    assert np.all(np.exp(lls[good] - lls.max()) > uu[good])
+    r = batch_tasks_ranges(10, 3)
+    assert r == [(0, 4), (4, 7), (7, 10)]
+    idx, all_lls = iterative_rejection_indices(lambda a, b: lls[a:b], len(lls),
+                                               np.random.default_rng(1), 4, growth_factor=16)
+    assert len(idx) <= 4 and len(all_lls) <= len(lls)
+    with pytest.raises(ValueError):
+        iterative_rejection_indices(lambda a, b: lls[a:b], 100, rng, 4, growth_factor=128)
