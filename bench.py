@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- prior samples / second through the marginal log-likelihood.
+
+Metric (BASELINE.json): prior samples/sec through marginal ll (N=64 epochs, 2^28-sample
+default prior, L=2, s=0) at 1/2/4/8 B200.  A "step" is one pass of the hot kernel over
+the whole prior cache; under torchrun the 2^28 samples are sharded over the ranks with
+the reference's batch_tasks rule (strong scaling, no data-path collective: the shards
+are independent; the 8-byte max-key all-reduce of the accept step runs once after the
+timed region as a cross-rank check).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on
+                                                             # the host cores (CPU oracle)
+
+One JSON line on stdout (rank 0).  `value`: device-resident SoA prior, CUDA-event time,
+max over ranks.  `e2e`: the reference-facing call CJokerHelper.batch_marginal_ln_likelihood
+on a pinned HOST chunk (n, 5), host->device and device->host copies inside the timed
+region.  `roofline`: algorithmic FP64 work / kernel time against the
+FP64 FMA-chain peak measured in this run.  `cpu_baseline`: the CPU oracle (restatement of
+the reference's Cython, same LAPACK) on this box's cores, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_EPOCHS = 64
+LOG2_PRIOR = 28
+METRIC = "prior samples/sec through marginal ll (N=64, 2^28 prior)"
+UNIT = "samples/s"
+
+# BASELINE.md section 3 / SURVEY.md section 8(d): reference-algorithm work model
+W_EPOCH_L2 = 292.0   # flop per (sample, epoch): Newton k=3 Kepler solve + RV column + Gram sums
+W_TAIL = 300.0       # flop per sample: Lambda_K, L x L factorisation, log det, combine
+FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 37.2
+
+
+def w_sample(n_epochs):
+    return n_epochs * W_EPOCH_L2 + W_TAIL
+
+
+def make_star():
+    """the reference's test fixture with noise, default prior."""
+    import thejoker_b200 as tj
+    from thejoker_b200 import units as u
+    from thejoker_b200.data_helpers import validate_prepare_data
+    from thejoker_b200.synthetic import make_noisy_data
+
+    data, _ = make_noisy_data(n_times=N_EPOCHS, seed=42)
+    prior = tj.JokerPrior.default(P_min=2 * u.day, P_max=1024 * u.day, sigma_K0=30 * u.km / u.s,
+                                  sigma_v=100 * u.km / u.s)
+    all_data, ids, trend_M = validate_prepare_data(data, prior.poly_trend, prior.n_offsets)
+    return all_data, prior, trend_M
+
+
+def shard_of(n_total, rank, world):
+    from thejoker_b200.sharding import shard_ranges
+
+    return shard_ranges(n_total, world)[rank]
+
+
+# ---------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.gpu)], stdout=open(self.path, "w"),
+                stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            load = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] or sm
+            out.update(sm_mhz=float(np.median(load)), sm_max_mhz=float(max(smax)),
+                       reasons=sorted(reasons), samples=len(sm), power_w_max=float(max(power)))
+        return out
+
+
+# ---------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import thejoker_b200 as tj
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+
+    n_total = 1 << args.log2_prior
+    lo, hi = shard_of(n_total, rank, world)
+    n = hi - lo
+    all_data, prior, trend_M = make_star()
+    helper = tj.CJokerHelper(all_data, prior, trend_M, device=local)
+
+    # synthetic default prior, generated on the device in SoA float64 (seed 123 + rank)
+    g = torch.Generator(device="cuda").manual_seed(123 + rank)
+    P = torch.exp(torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
+                  * (np.log(1024.0) - np.log(2.0)) + np.log(2.0))
+    # Beta(0.867, 3.03) through two gammas (torch's CUDA gamma sampler)
+    torch.manual_seed(123 + rank)
+    ga = torch._standard_gamma(torch.full((n,), 0.867, dtype=torch.float64, device="cuda"))
+    gb = torch._standard_gamma(torch.full((n,), 3.03, dtype=torch.float64, device="cuda"))
+    e = (ga / (ga + gb)).clamp_(0.0, 1.0 - 1e-12)
+    del ga, gb
+    om = (torch.rand(n, dtype=torch.float64, device="cuda", generator=g) * 2 - 1) * np.pi
+    M0 = (torch.rand(n, dtype=torch.float64, device="cuda", generator=g) * 2 - 1) * np.pi
+    ll = torch.empty(n, dtype=torch.float64, device="cuda")
+    key = helper.new_llmax_key()
+
+    def step():
+        helper.marginal_ll_soa(P, e, om, M0, s=None, s_const=0.0, out=ll, llmax_key=key)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_total = ev[0].elapsed_time(ev[-1])
+    per_launch = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total_max = float(t.item())
+    ms_per_step = ms_total_max / args.steps
+    value = n_total / (ms_per_step * 1e-3)
+
+    # cross-rank check (untimed): the accept step's integer MAX all-reduce of the max key
+    kk = key.clone()
+    if world > 1:
+        dist.all_reduce(kk, op=dist.ReduceOp.MAX)
+    ll_max = helper.llmax_value(kk)
+    assert np.isfinite(ll_max) and ll_max >= ll.max().item()
+
+    # ---- e2e: the reference-facing call on a pinned host chunk ----------------------
+    n_e2e = min(n, 1 << args.log2_e2e)
+    host = torch.empty((n_e2e, 5), dtype=torch.float64).pin_memory()
+    host[:, 0].copy_(P[:n_e2e]); host[:, 1].copy_(e[:n_e2e]); host[:, 2].copy_(om[:n_e2e])
+    host[:, 3].copy_(M0[:n_e2e]); host[:, 4].zero_()
+    host_ll = torch.empty(n_e2e, dtype=torch.float64).pin_memory()
+    chunk_np, ll_np = host.numpy(), host_ll.numpy()
+    import ctypes
+
+    from thejoker_b200 import _lib
+
+    def e2e_step():
+        _lib.check(helper._lib.tjb_marginal_ll_host(helper._h, ctypes.c_void_p(chunk_np.ctypes.data),
+                                                    n_e2e, ctypes.c_void_p(ll_np.ctypes.data)))
+
+    e2e_step()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()  # synchronous: returns when ll is back in host memory
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = n_e2e * world * e2e_steps / float(dt.item())
+    assert np.array_equal(ll_np[:1024], ll[:1024].cpu().numpy())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline -----------------------------------------------------------------------
+    peak_tf, _ = helper.fp64_peak(40000)
+    kernel_ms = float(np.mean(per_launch))
+    achieved_tf = (n * w_sample(N_EPOCHS)) / (kernel_ms * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_bytes = n * 40.0  # 4 prior columns read + ll written
+    hbm_gbs = hbm_bytes / (kernel_ms * 1e-3) / 1e9
+    prof = {}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "kernel_counts.json")))
+    except Exception:
+        pass
+    roofline = {
+        "bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+        "frac": achieved_tf / peak_tf,
+        "peak_source": "FP64 FMA-chain microbenchmark (tjb_fp64_peak) measured in this run; "
+                       f"nominal {FP64_NOMINAL_TFLOPS:.1f}",
+        "frac_of_nominal": achieved_tf / FP64_NOMINAL_TFLOPS,
+        "work_model_flop_per_sample": w_sample(N_EPOCHS),
+        "kernel": "marginal_ll_kernel<2,false>", "kernel_ms": kernel_ms,
+        "executed_fp64_flop_per_sample": prof.get("executed_fp64_flop_per_sample"),
+        "executed_frac": (None if not prof.get("executed_fp64_flop_per_sample") else
+                          n * prof["executed_fp64_flop_per_sample"] / (kernel_ms * 1e-3) / 1e12 / peak_tf),
+        "traffic": prof.get("dram_bytes_per_launch_at_2p28"),
+        "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
+                "algorithmic_bytes_per_sample": 40,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"},
+    }
+
+    cpu = cpu_baseline(args.cpu_seconds) if world == 1 and not args.no_cpu_baseline else None
+
+    rec = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"N={N_EPOCHS} epochs, L=2 (K, v0), s=0, 2^{args.log2_prior} default-prior "
+                               "samples sharded over the ranks (configs[1]/metric config)",
+                   "l2": "inputs (32 B/sample x 2^28/ranks) are larger than L2",
+                   "n_prior": n_total, "n_epochs": N_EPOCHS, "sharding": f"contiguous x{world}"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_e2e * 40),
+                "d2h_bytes_per_step": int(n_e2e * 8), "n_per_rank": int(n_e2e), "steps": e2e_steps,
+                "call": "CJokerHelper.batch_marginal_ln_likelihood -> tjb_marginal_ll_host, pinned "
+                        "host chunk (n,5) in, host ll out"},
+        "gpu_launches": args.steps,
+        "clocks": clocks,
+        "roofline": roofline,
+        "ll_max": ll_max,
+    }
+    if cpu is not None:
+        rec["cpu_baseline"] = cpu
+    print(json.dumps(rec))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------
+def _oracle_and_chunk(n):
+    from oracle.oracle import OracleHelper
+    from thejoker_b200.helper import extract_spec
+    from thejoker_b200.synthetic import default_prior_columns
+
+    all_data, prior, trend_M = make_star()
+    spec = extract_spec(all_data, prior, trend_M)
+    chunk = np.ascontiguousarray(np.stack(default_prior_columns(n, seed=123), axis=1))
+    return OracleHelper.from_spec(spec), chunk
+
+
+def cpu_baseline(seconds=12.0):
+    """The CPU oracle (oracle/joker_oracle.c: restatement of the reference's Cython +
+    scipy LAPACK, OpenMP over samples like the reference's pool.map over chunks) on a
+    bounded sample of the same workload."""
+    from oracle.oracle import load
+
+    lib = load()
+    cores = lib.orc_max_threads()
+    orc, chunk = _oracle_and_chunk(1 << 12)
+    orc.batch_marginal_ln_likelihood(chunk[:256], n_threads=0)
+    done, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        orc.batch_marginal_ln_likelihood(chunk, n_threads=0)
+        done += len(chunk)
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": UNIT, "cores": int(cores), "kind": "port",
+            "sample": f"{done} default-prior samples at N={N_EPOCHS} in {dt:.1f} s "
+                      "(restatement of fast_likelihood.pyx, Cython safety checks off, "
+                      "scipy LAPACK; the reference binary cannot run in this image)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm on the host cores (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle.oracle import load
+
+    lib = load()
+    cores = lib.orc_max_threads()
+    n_step = 1 << args.log2_ref_step
+    orc, chunk = _oracle_and_chunk(n_step)
+    for _ in range(max(1, min(args.warmup, 2))):
+        orc.batch_marginal_ln_likelihood(chunk[: n_step // 4], n_threads=0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.batch_marginal_ln_likelihood(chunk, n_threads=0)
+    dt = time.perf_counter() - t0
+    value = n_step * args.steps / dt
+    sample = (f"each step = {n_step} samples of the same workload (2^{LOG2_PRIOR} would take "
+              f"~{(1 << LOG2_PRIOR) / value / 3600:.1f} h)")
+    rec = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"N={N_EPOCHS} epochs, L=2 (K, v0), s=0, default prior; {sample}",
+                   "n_prior": 1 << LOG2_PRIOR, "n_epochs": N_EPOCHS},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": int(cores), "kind": "port",
+                         "sample": sample + "; oracle/joker_oracle.c (restatement of "
+                                            "fast_likelihood.pyx + scipy LAPACK, OpenMP over samples)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(rec))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2-prior", dest="log2_prior", type=int, default=LOG2_PRIOR)
+    ap.add_argument("--log2-e2e", dest="log2_e2e", type=int, default=28,
+                    help="per-rank samples of the pinned host chunk for the e2e measurement")
+    ap.add_argument("--log2-ref-step", dest="log2_ref_step", type=int, default=15)
+    ap.add_argument("--cpu-seconds", dest="cpu_seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

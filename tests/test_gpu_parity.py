@@ -1,0 +1,420 @@
+"""Parity of the CUDA path with the CPU oracle, through the C ABI
+(libthejoker_b200.so via ctypes).  Everything here needs a B200.
+
+Gates (BASELINE.json north_star): ll within 1e-10 relative of the reference algorithm
+on identical inputs -- where the reference algorithm itself is further than that from
+the exact value (ill-conditioned B), the CUDA result must be at least as close to the
+quad-precision truth; accepted index sets bit-exact except samples within 1e-12 of the
+threshold, which are counted."""
+import glob
+import os
+
+import numpy as np
+import pytest
+from helpers import prior_chunk, rel_err, star_spec
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def make_helper(spec_args, device=0, **kw):
+    import thejoker_b200 as tj
+    from thejoker_b200.data_helpers import validate_prepare_data
+
+    N, pt = spec_args[:2]
+    spec, data, prior = star_spec(N, pt, **kw)
+    jm = kw.get("jitter_mode", "apply")
+    all_data, ids, trend_M = validate_prepare_data(data, prior.poly_trend, prior.n_offsets)
+    return tj.CJokerHelper(all_data, prior, trend_M, device=device, jitter_mode=jm), spec, data, prior
+
+
+def parity_ok(got, ref, truth):
+    r_ref, r_truth, ref_truth = rel_err(got, ref), rel_err(got, truth), rel_err(ref, truth)
+    ok = (r_ref <= 1e-10) | (r_truth <= ref_truth)
+    return ok, r_ref, r_truth, ref_truth
+
+
+SPEC_KEYS = ("t", "rv", "ivar", "t0", "trend_M", "mu", "Lambda", "K_prior_kind", "sigma_K0", "P0",
+             "max_K", "jitter_mode")
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_vectors(torch_cuda, path):
+    """The committed fixtures (inputs + oracle outputs) travel without the oracle."""
+    import thejoker_b200 as tj
+
+    z = np.load(path)
+    spec = {k: (z[k] if z[k].ndim else z[k].item()) for k in SPEC_KEYS}
+    helper = tj.CJokerHelper.from_spec(spec, device=0)
+    ll = helper.batch_marginal_ln_likelihood(np.ascontiguousarray(z["chunk"]))
+    ok, r_ref, r_truth, ref_truth = parity_ok(ll, z["ll"], z["ll_truth"])
+    assert ok.all(), (r_ref.max(), r_truth.max(), ref_truth.max())
+    assert r_truth.max() < 1e-10
+    lls, a, A = helper.posterior_aA(z["chunk"][:16])
+    assert np.allclose(a, z["post_a"], rtol=1e-8, atol=1e-10)
+    assert np.allclose(A, z["post_A"], rtol=1e-7, atol=1e-14)
+    # accept on the fixture's own uniforms
+    import torch
+
+    ll_dev = torch.from_numpy(ll).cuda()
+    key = helper.new_llmax_key()
+    helper.llmax_update(ll_dev, key)
+    idx, tot, near = helper.accept(ll_dev, key, uniforms=torch.from_numpy(z["uniforms"]).cuda())
+    if near == 0 and np.max(r_ref) < 1e-12:
+        assert np.array_equal(idx.cpu().numpy(), z["good"])
+
+
+CASES = [
+    ((16, 1), None, {}),
+    ((64, 1), None, {}),
+    ((64, 2), (-2.0, 1.0), {}),
+    ((256, 1), None, {}),
+    ((3, 1), None, {"normal_K": 10.0}),
+    ((20, 1), None, {"n_surveys": 2}),
+    ((24, 2), None, {"n_surveys": 3}),
+    ((12, 3), None, {}),
+    ((64, 1), None, {"K": 1e-4}),
+    ((64, 1), None, {"sigma": 0.01}),
+]
+
+
+@pytest.mark.parametrize("args,sl,kw", CASES)
+def test_ll_parity_host_path(torch_cuda, oracle_lib, args, sl, kw):
+    """batch_marginal_ln_likelihood (host chunk in, host ll out) vs oracle + truth."""
+    helper, spec, _, _ = make_helper(args, **kw)
+    n = 1 << 14 if args[0] <= 64 else 1 << 12
+    chunk = prior_chunk(n, s_lognormal=sl)
+    orc = oracle_lib.OracleHelper.from_spec(spec)
+    ref = orc.batch_marginal_ln_likelihood(chunk, n_threads=0)
+    truth, kappa = orc.truth_ll(chunk)
+    ll = helper.batch_marginal_ln_likelihood(chunk)
+    ok, r_ref, r_truth, ref_truth = parity_ok(ll, ref, truth)
+    print(f"\n{args} {kw}: max rel vs oracle {r_ref.max():.2e} (frac>1e-10: "
+          f"{np.mean(r_ref > 1e-10):.1e}), vs truth {r_truth.max():.2e}, oracle vs truth "
+          f"{ref_truth.max():.2e}")
+    assert ok.all()
+    assert r_truth.max() < 1e-10
+    # ragged / tiny / empty inputs
+    for m in (0, 1, 31, 33, 257):
+        part = helper.batch_marginal_ln_likelihood(np.ascontiguousarray(chunk[:m]))
+        assert part.shape == (m,) and np.array_equal(part, ll[:m])
+    with pytest.raises(ValueError):
+        helper.batch_marginal_ln_likelihood(chunk.astype(np.float32))
+    with pytest.raises(ValueError):
+        helper.batch_marginal_ln_likelihood(chunk[:, :4])
+
+
+def test_ll_device_paths_agree(torch_cuda, oracle_lib):
+    """SoA / AoS device entry points and the host entry point give identical bits, for
+    both kernels (constant jitter folded into the table vs per-sample jitter)."""
+    torch = torch_cuda
+    helper, spec, _, _ = make_helper((64, 2))
+    n = 50_000
+    for sl, s_const in ((None, None), (None, 0.3), ((-2.0, 1.0), None)):
+        chunk = prior_chunk(n, s_lognormal=sl, s_const=s_const)
+        host = helper.batch_marginal_ln_likelihood(chunk)
+        dev = torch.from_numpy(chunk).cuda()
+        cols = [dev[:, i].contiguous() for i in range(5)]
+        key = helper.new_llmax_key()
+        if sl is None:
+            soa = helper.marginal_ll_soa(*cols[:4], s=None, s_const=s_const or 0.0, llmax_key=key)
+            aos = helper.marginal_ll_aos(dev, uniform_s=True)
+            soa_j = helper.marginal_ll_soa(*cols[:4], s=cols[4])
+            assert np.max(rel_err(soa_j.cpu().numpy(), host)) < 1e-12
+        else:
+            soa = helper.marginal_ll_soa(*cols[:4], s=cols[4], llmax_key=key)
+            aos = helper.marginal_ll_aos(dev, uniform_s=False)
+        assert np.array_equal(soa.cpu().numpy(), host)
+        assert np.array_equal(aos.cpu().numpy(), host)
+        assert helper.llmax_value(key) == host.max()
+        ref = oracle_lib.OracleHelper.from_spec(spec).batch_marginal_ln_likelihood(chunk[:4096], 0)
+        assert np.max(rel_err(host[:4096], ref)) < 1e-9
+
+
+def test_jitter_modes(torch_cuda, oracle_lib):
+    """jitter_mode='reference' ignores s like the reference's Cython does
+    (fast_likelihood.pyx:458); 'apply' matches the intended semantics
+    (src/tests/py_likelihood.py:17-29)."""
+    chunk = prior_chunk(4096, s_lognormal=(0.0, 1.0))
+    chunk0 = chunk.copy()
+    chunk0[:, 4] = 0
+    h_ref, spec_ref, _, _ = make_helper((32, 1), jitter_mode="reference")
+    assert np.array_equal(h_ref.batch_marginal_ln_likelihood(chunk),
+                          h_ref.batch_marginal_ln_likelihood(chunk0))
+    o = oracle_lib.OracleHelper.from_spec(spec_ref).batch_marginal_ln_likelihood(chunk, 0)
+    assert np.max(rel_err(h_ref.batch_marginal_ln_likelihood(chunk), o)) < 1e-10
+    h_app, spec_app, _, _ = make_helper((32, 1), jitter_mode="apply")
+    o = oracle_lib.OracleHelper.from_spec(spec_app).batch_marginal_ln_likelihood(chunk, 0)
+    assert np.max(rel_err(h_app.batch_marginal_ln_likelihood(chunk), o)) < 1e-10
+
+
+def test_design_column_and_solver_tail(torch_cuda, oracle_lib):
+    """z = cos(f+omega) + e cos(omega) per epoch vs the Newton restatement, including
+    e up to 0.999; the fixed-work solver must report no non-converged epochs."""
+    helper, spec, _, _ = make_helper((64, 1))
+    orc = oracle_lib.OracleHelper.from_spec(spec)
+    rng = np.random.default_rng(5)
+    chunk = prior_chunk(400)
+    chunk[:150, 1] = rng.uniform(0.8, 0.999, 150)
+    chunk[150:160, 1] = 0.0
+    extra = 0
+    for row in chunk:
+        z, st = helper.design_column(row, return_stats=True)
+        zo = orc.design_column(row)
+        assert st[2] == 0
+        extra += st[1]
+        assert np.max(np.abs(z - zo)) < 3e-12 / (1 - row[1]) ** 2
+    print(f"\nextra FP64 Householder passes over {len(chunk) * 64} epochs: {extra}")
+
+
+def test_posterior_aA_and_draws(torch_cuda, oracle_lib):
+    """(a, A) vs oracle (dsysv / inverse of Ainv) as in
+    test_fast_likelihood.py::test_likelihood_helpers; draws: same RNG consumption as
+    rng.multivariate_normal, right mean / covariance."""
+    for args, kw in (((3, 1), {"normal_K": 1.0}), ((64, 2), {}), ((20, 1), {"n_surveys": 2})):
+        helper, spec, _, _ = make_helper(args, **kw)
+        orc = oracle_lib.OracleHelper.from_spec(spec)
+        chunk = prior_chunk(16)
+        for row in chunk:
+            ll = helper.test_likelihood_worker(row)
+            ll_o = orc.test_likelihood_worker(row)
+            assert np.abs(ll) < 1e8
+            assert np.isclose(ll, ll_o, rtol=1e-9)
+            assert np.allclose(helper.a, orc.a, rtol=1e-8, atol=1e-10)
+            assert np.allclose(helper.A, orc.A, rtol=1e-7, atol=1e-14)
+            assert np.allclose(helper.b, orc.b)
+            a_t, A_t = orc.truth_aA(row)
+            assert np.allclose(helper.a, a_t, rtol=1e-9, atol=1e-11)
+        # reference-identical draws through numpy
+        r1, r2 = np.random.default_rng(3), np.random.default_rng(3)
+        s_np, _ = helper.batch_get_posterior_samples(chunk, 2, r1, draw="numpy")
+        s_or, _ = orc.batch_get_posterior_samples(chunk, 2, r2)
+        assert np.allclose(s_np, s_or, rtol=1e-6, atol=1e-9)
+        # device draws: stream consumption equals multivariate_normal's
+        r3 = np.random.default_rng(3)
+        s_dev, lls = helper.batch_get_posterior_samples(chunk, 2, r3)
+        assert np.array_equal(r1.standard_normal(3), r3.standard_normal(3))
+        assert s_dev.shape == s_np.shape and np.array_equal(s_dev[:, :5], s_np[:, :5])
+    # distribution check on one row
+    helper, spec, _, _ = make_helper((16, 1))
+    row = prior_chunk(1)
+    _, a, A = helper.posterior_aA(row)
+    draws, _ = helper.batch_get_posterior_samples(row, 200_000, np.random.default_rng(0))
+    x = draws[:, 5:]
+    assert np.allclose(x.mean(0), a[0], atol=5 * np.sqrt(np.diag(A[0]) / len(x)))
+    assert np.allclose(np.cov(x.T), A[0], rtol=0.02)
+
+
+def test_pcg64_uniforms_bit_exact(torch_cuda):
+    helper, _, _, _ = make_helper((8, 1))
+    for seed, n, off in ((42, 100_000, 0), (7, 65_537, 12_345), (1, 1, 0), (5, 3_000_000, 999_999)):
+        rng = np.random.default_rng(seed)
+        dev = helper.pcg64_uniform(rng, n, offset=off).cpu().numpy()
+        want = np.random.default_rng(seed).random(n + off)[off:]
+        assert np.array_equal(dev, want)
+
+
+@pytest.mark.parametrize("flat", [False, True])
+def test_accept_bit_exact(torch_cuda, oracle_lib, flat):
+    """where(exp(ll - max) > u)[0][:max_keep]: bit-exact index set vs numpy on the same
+    ll and the same uniforms (host-supplied and device PCG64)."""
+    torch = torch_cuda
+    helper, spec, _, _ = make_helper((16, 1), K=1e-4 if flat else None)
+    n = 300_000
+    chunk = prior_chunk(n)
+    ll = helper.batch_marginal_ln_likelihood(chunk)
+    ll_dev = torch.from_numpy(ll).cuda()
+    key = helper.new_llmax_key()
+    helper.llmax_update(ll_dev, key)
+    assert helper.llmax_value(key) == ll.max()
+    rng = np.random.default_rng(7)
+    uu = np.random.default_rng(7).uniform(size=n)
+    for max_keep in (None, 1, 5, 100):
+        want = oracle_lib.rejection_accept(ll, uu, max_keep)
+        near = oracle_lib.near_threshold_count(ll, uu)
+        idx, tot, n_near = helper.accept(ll_dev, key, uniforms=torch.from_numpy(uu).cuda(),
+                                         max_keep=max_keep)
+        idx2, tot2, _ = helper.accept(ll_dev, key, rng=rng, max_keep=max_keep)
+        assert n_near == near
+        if near == 0:
+            assert np.array_equal(idx.cpu().numpy(), want)
+            assert np.array_equal(idx2.cpu().numpy(), want)
+            assert tot == tot2 == len(oracle_lib.rejection_accept(ll, uu))
+    if flat:
+        assert tot > 10  # test_sampler.py:156: uninformative data keeps many samples
+    # offsets: shard [lo, hi) of a larger stream reports global indices
+    lo = 100_003
+    idx, tot, _ = helper.accept(ll_dev[lo:], key, rng=rng, rng_offset=lo, index_base=lo)
+    want = oracle_lib.rejection_accept(ll, uu)
+    assert np.array_equal(idx.cpu().numpy(), want[want >= lo])
+    # NaN / +inf propagate through the max like numpy.max (appendix B)
+    bad = ll.copy()
+    bad[17] = np.nan
+    k2 = helper.new_llmax_key()
+    helper.llmax_update(torch.from_numpy(bad).cuda(), k2)
+    assert np.isnan(helper.llmax_value(k2))
+    idx, tot, _ = helper.accept(torch.from_numpy(bad).cuda(), k2, rng=rng)
+    assert tot == 0 and idx.numel() == 0
+
+
+def test_rejection_sample_api(torch_cuda, oracle_lib):
+    """TheJoker.rejection_sample end to end (thejoker/tests/test_sampler.py:128-173):
+    count bounds, logprobs, determinism, and index-set identity with the oracle fed the
+    same prior samples and the same generator."""
+    import thejoker_b200 as tj
+    from helpers import default_prior
+    from thejoker_b200.synthetic import make_data
+
+    for poly_trend in (1, 2):
+        prior = default_prior(poly_trend, sigma_K0=25.0, P_min=5.0, P_max=500.0)
+        data, _ = make_data(8, rng=np.random.default_rng(11))
+        flat_data, _ = make_data(8, rng=np.random.default_rng(11), K=1e-4)
+        prior_samples = prior.sample(size=16384, return_logprobs=True, rng=np.random.default_rng(1))
+        joker = tj.TheJoker(prior, rng=np.random.default_rng(42))
+        for in_memory in (True, False):
+            samples = joker.rejection_sample(data, prior_samples, in_memory=in_memory)
+            assert 0 < len(samples) < 10
+            samples = joker.rejection_sample(data, prior_samples, return_logprobs=True,
+                                             in_memory=in_memory)
+            assert len(samples) > 0 and "ln_likelihood" in samples and "ln_prior" in samples
+            samples = joker.rejection_sample(flat_data, prior_samples, in_memory=in_memory)
+            assert len(samples) > 10
+            assert np.isfinite(samples.ln_unmarginalized_likelihood(flat_data)).all()
+        samples, lls = joker.rejection_sample(flat_data, prior_samples, return_all_logprobs=True)
+        assert len(lls) == len(prior_samples)
+        all_Ps, all_Ks = [], []
+        for i in range(4):
+            joker = tj.TheJoker(prior, rng=np.random.default_rng(42))
+            s = joker.rejection_sample(flat_data, prior_samples)
+            all_Ps.append(s["P"].value)
+            all_Ks.append(s["K"].value)
+        for i in range(1, 4):
+            assert np.array_equal(all_Ps[0], all_Ps[i]) and np.array_equal(all_Ks[0], all_Ks[i])
+        # identity with the reference algorithm on identical inputs
+        joker = tj.TheJoker(prior, rng=np.random.default_rng(42))
+        helper = joker._make_joker_helper(flat_data)
+        chunk, _ = prior_samples.pack(units=helper.internal_units, names=helper.packed_order)
+        got = joker.rejection_sample(flat_data, prior_samples, in_memory=True, max_posterior_samples=64)
+        orc = oracle_lib.OracleHelper.from_spec(helper.spec)
+        ref_ll = orc.batch_marginal_ln_likelihood(chunk, 0)
+        uu = np.random.default_rng(42).uniform(size=len(chunk))
+        good = oracle_lib.rejection_accept(ref_ll, uu, 64)
+        if oracle_lib.near_threshold_count(ref_ll, uu) == 0:
+            assert np.array_equal(got["P"].value, chunk[good, 0])
+        assert joker.last_stats["n_near_threshold"] == oracle_lib.near_threshold_count(ref_ll, uu)
+        with pytest.raises(ValueError):
+            joker.rejection_sample(data, prior_samples, n_prior_samples=10**6)
+        s_int = tj.TheJoker(prior, rng=np.random.default_rng(3)).rejection_sample(flat_data, 4096)
+        assert len(s_int) > 0
+
+
+def test_iterative_rejection_sample_api(torch_cuda, oracle_lib):
+    """thejoker/tests/test_sampler.py:176-211 plus identity with the restated driver."""
+    import thejoker_b200 as tj
+    from helpers import default_prior
+    from thejoker_b200.synthetic import make_data
+
+    prior = default_prior(1, sigma_K0=25.0, P_min=5.0, P_max=500.0)
+    data, _ = make_data(3, rng=np.random.default_rng(2))
+    prior_samples = prior.sample(size=10_000, return_logprobs=True, rng=np.random.default_rng(1))
+    for in_memory in (True, False):
+        joker = tj.TheJoker(prior, rng=np.random.default_rng(42))
+        s = joker.iterative_rejection_sample(data, prior_samples, n_requested_samples=4,
+                                             in_memory=in_memory)
+        assert len(s) > 1
+        s = joker.iterative_rejection_sample(data, prior_samples, n_requested_samples=4,
+                                             return_logprobs=True, in_memory=in_memory)
+        assert len(s) > 1 and "ln_prior" in s
+    runs = []
+    for i in range(3):
+        joker = tj.TheJoker(prior, rng=np.random.default_rng(42))
+        s = joker.iterative_rejection_sample(data, prior_samples, n_requested_samples=4,
+                                             randomize_prior_order=True)
+        runs.append((s["P"].value, s["K"].value))
+    assert all(np.array_equal(runs[0][0], r[0]) and np.array_equal(runs[0][1], r[1]) for r in runs)
+    # identity of the accepted set with the restated in-memory driver
+    joker = tj.TheJoker(prior, rng=np.random.default_rng(9))
+    helper = joker._make_joker_helper(data)
+    chunk, _ = prior_samples.pack(units=helper.internal_units, names=helper.packed_order)
+    got = joker.iterative_rejection_sample(data, prior_samples, n_requested_samples=16,
+                                           in_memory=True, growth_factor=8)
+    orc = oracle_lib.OracleHelper.from_spec(helper.spec)
+    idx, all_lls = oracle_lib.iterative_rejection_indices(
+        lambda a, b: orc.batch_marginal_ln_likelihood(chunk[a:b], 0), len(chunk),
+        np.random.default_rng(9), 16, growth_factor=8, safety_factor=1)
+    assert np.array_equal(got["P"].value, chunk[idx, 0])
+    assert joker.last_stats["n_ll_evaluated"] == len(all_lls)
+    with pytest.raises(ValueError):
+        joker.iterative_rejection_sample(data, prior_samples, n_requested_samples=1000)
+
+
+def test_marginal_ln_likelihood_api(torch_cuda, oracle_lib):
+    """thejoker/tests/test_sampler.py:81-108: JokerSamples / file / packed array in,
+    len(ll) == len(prior_samples); values equal the helper's."""
+    import thejoker_b200 as tj
+    from helpers import default_prior
+    from thejoker_b200.synthetic import make_data
+
+    prior = default_prior(2, sigma_K0=25.0, P_min=1.0, P_max=365.0)
+    data, _ = make_data(8, rng=np.random.default_rng(0))
+    ps = prior.sample(size=100, rng=np.random.default_rng(0))
+    joker = tj.TheJoker(prior)
+    ll = joker.marginal_ln_likelihood(data, ps)
+    assert len(ll) == len(ps)
+    helper = joker._make_joker_helper(data)
+    chunk, _ = ps.pack(units=helper.internal_units, names=helper.packed_order)
+    assert np.array_equal(ll, helper.batch_marginal_ln_likelihood(np.ascontiguousarray(chunk)))
+    assert np.array_equal(ll, joker.marginal_ln_likelihood(data, ps, in_memory=True))
+
+
+def test_multi_survey_offsets(torch_cuda, oracle_lib):
+    """v0_offsets: list of RVData with an indicator column per extra survey."""
+    import thejoker_b200 as tj
+
+    spec, data, prior = star_spec(24, 1, n_surveys=3)
+    joker = tj.TheJoker(prior, rng=np.random.default_rng(0))
+    helper = joker._make_joker_helper(data)
+    assert helper.n_linear == 4
+    chunk = prior_chunk(8192)
+    ll = helper.batch_marginal_ln_likelihood(chunk)
+    ref = oracle_lib.OracleHelper.from_spec(helper.spec).batch_marginal_ln_likelihood(chunk, 0)
+    assert np.max(rel_err(ll, ref)) < 1e-10
+    s = joker.rejection_sample(data, chunk, in_memory=True)
+    assert list(s.keys())[:8] == ["P", "e", "omega", "M0", "s", "K", "v0", "dv0_1"]
+
+
+def test_large_n_properties(torch_cuda):
+    """Size-independent checks at BASELINE scale (2^24 samples, N=64): the fused max
+    equals the max of the written ll, permutation equivariance, finite everywhere."""
+    torch = torch_cuda
+    helper, spec, _, _ = make_helper((64, 1))
+    n = 1 << 24
+    g = torch.Generator(device="cuda").manual_seed(123)
+    U = torch.rand(4, n, dtype=torch.float64, device="cuda", generator=g)
+    P = torch.exp(U[0] * np.log(512.0) + np.log(2.0))
+    e = torch.distributions.Beta(torch.tensor(0.867, dtype=torch.float64, device="cuda"),
+                                 torch.tensor(3.03, dtype=torch.float64, device="cuda")).sample((n,))
+    om, M0 = (U[2] * 2 - 1) * np.pi, (U[3] * 2 - 1) * np.pi
+    key = helper.new_llmax_key()
+    ll = helper.marginal_ll_soa(P, e, om, M0, llmax_key=key)
+    assert torch.isfinite(ll).all()
+    assert helper.llmax_value(key) == ll.max().item()
+    perm = torch.randperm(n, device="cuda")[: 1 << 20]
+    ll2 = helper.marginal_ll_soa(P[perm].contiguous(), e[perm].contiguous(),
+                                 om[perm].contiguous(), M0[perm].contiguous())
+    assert torch.equal(ll2, ll[perm])
+    # omega -> omega + 2 pi and M0 -> M0 + 2 pi leave the model unchanged
+    ll3 = helper.marginal_ll_soa(P[: 1 << 20].contiguous(), e[: 1 << 20].contiguous(),
+                                 (om[: 1 << 20] + 2 * np.pi).contiguous(),
+                                 (M0[: 1 << 20] - 2 * np.pi).contiguous())
+    rel = ((ll3 - ll[: 1 << 20]).abs() / ll[: 1 << 20].abs()).max().item()
+    assert rel < 1e-9

@@ -125,6 +125,10 @@ def _pcg_struct(rng):
     return _lib.TjbPcg64(st["state"] >> 64, st["state"] & m, st["inc"] >> 64, st["inc"] & m)
 
 
+def _rebuild_from_spec(spec, device):
+    return CJokerHelper.from_spec(spec, device)
+
+
 class CJokerHelper:
     """GPU-backed stand-in for thejoker.src.fast_likelihood.CJokerHelper.
 
@@ -145,11 +149,41 @@ class CJokerHelper:
         self.data = data
         self._trend_M = np.ascontiguousarray(trend_M, dtype=np.float64)
         self._jitter_mode = jitter_mode
-        self.spec = extract_spec(data, prior, self._trend_M, jitter_mode)
+        self._init_from_spec(extract_spec(data, prior, self._trend_M, jitter_mode), device)
+
+    @classmethod
+    def from_spec(cls, spec, device=None):
+        """Build directly from the plain arrays ``extract_spec`` returns (keys t, rv,
+        ivar, t0, trend_M, mu, Lambda, K_prior_kind, sigma_K0, P0, max_K, jitter_mode),
+        without RVData / JokerPrior objects -- the entry point for callers that already
+        hold a star table (tests, the multi-star driver)."""
+        self = cls.__new__(cls)
+        self.prior = self.data = None
+        spec = dict(spec)
+        spec["t"], spec["rv"], spec["ivar"] = (np.ascontiguousarray(spec[k], dtype="f8")
+                                               for k in ("t", "rv", "ivar"))
+        n = len(spec["t"])
+        spec["trend_M"] = np.ascontiguousarray(spec["trend_M"], dtype="f8").reshape(n, -1)
+        spec["mu"] = np.ascontiguousarray(spec["mu"], dtype="f8")
+        spec["Lambda"] = np.ascontiguousarray(spec["Lambda"], dtype="f8")
+        spec.setdefault("n_times", n)
+        spec.setdefault("n_linear", 1 + spec["trend_M"].shape[1])
+        spec.setdefault("n_pars", 5 + spec["n_linear"])
+        spec.setdefault("internal_units", OrderedDict())
+        spec["jitter_mode"] = JITTER_MODES[spec.get("jitter_mode", 1)]
+        self._trend_M = spec["trend_M"]
+        self._jitter_mode = spec["jitter_mode"]
+        self._init_from_spec(spec, device)
+        return self
+
+    def _init_from_spec(self, spec, device):
+        self.spec = spec
         self.internal_units = self.spec["internal_units"]
         self.packed_order = list(_nonlinear_packed_order)
         self.n_times, self.n_linear = self.spec["n_times"], self.spec["n_linear"]
         self.n_pars = self.spec["n_pars"]
+        if self.n_linear > _lib.TJB_MAX_LINEAR or len(spec["mu"]) < self.n_linear:
+            raise ValueError("bad n_linear / mu length")
         self.a = self.A = self.b = None
         if device is None:
             import os
@@ -159,15 +193,15 @@ class CJokerHelper:
         lib = self._lib = _lib.load()
         sp = self.spec
         cs = _lib.TjbSpec()
-        cs.n_times, cs.n_linear, cs.t_ref = sp["n_times"], sp["n_linear"], sp["t0"]
+        cs.n_times, cs.n_linear, cs.t_ref = sp["n_times"], sp["n_linear"], float(sp["t0"])
         dp = ctypes.POINTER(ctypes.c_double)
         cs.t, cs.rv, cs.ivar = (sp[k].ctypes.data_as(dp) for k in ("t", "rv", "ivar"))
         cs.trend_M = sp["trend_M"].ctypes.data_as(dp)
         for i in range(sp["n_linear"]):
             cs.mu[i], cs.Lambda[i] = sp["mu"][i], sp["Lambda"][i]
-        cs.K_prior_kind = sp["K_prior_kind"]
-        cs.sigma_K0, cs.P0 = sp["sigma_K0"], sp["P0"]
-        cs.max_K = sp["max_K"] if np.isfinite(sp["max_K"]) else 1e300
+        cs.K_prior_kind = int(sp["K_prior_kind"])
+        cs.sigma_K0, cs.P0 = float(sp["sigma_K0"]), float(sp["P0"])
+        cs.max_K = float(sp["max_K"]) if np.isfinite(sp["max_K"]) else 1e300
         cs.jitter_mode = sp["jitter_mode"]
         h = ctypes.c_void_p()
         _lib.check(lib.tjb_create(ctypes.byref(cs), self.device, ctypes.byref(h)))
@@ -183,6 +217,8 @@ class CJokerHelper:
             self._h = None
 
     def __reduce__(self):  # pyx:122-123
+        if self.data is None:
+            return (_rebuild_from_spec, (self.spec, self.device))
         return (CJokerHelper, (self.data, self.prior, np.array(self._trend_M), self.device,
                                self._jitter_mode))
 
