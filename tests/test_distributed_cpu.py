@@ -1,0 +1,70 @@
+"""The N>1 path on CPU: two gloo ranks each own a contiguous shard of the prior
+(batch_tasks rule), compute ll for it (CPU oracle standing in for the kernel), combine
+the max through the integer-key all-reduce and the accepted indices through the
+rank-ordered gather -- and must reproduce the single-process accept exactly
+(thejoker/multiproc_helpers.py:256-263)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, max_keep, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from helpers import prior_chunk, star_spec
+
+    from oracle.oracle import OracleHelper
+    from thejoker_b200 import _lib
+    from thejoker_b200.sharding import allreduce_max_key, gather_accepted, shard_ranges
+
+    spec, _, _ = star_spec(16, 1, K=1e-4)
+    chunk = prior_chunk(n)
+    lo, hi = shard_ranges(n, world)[rank]
+    ll = OracleHelper.from_spec(spec).batch_marginal_ln_likelihood(chunk[lo:hi])
+    if rank == 1:
+        ll[3] = ll.max() + 1.0  # the global max lives on rank 1
+    lib = _lib.load()
+    key = torch.tensor([lib.tjb_double_to_key(float(ll.max()))], dtype=torch.int64)
+    allreduce_max_key(key)
+    gmax = lib.tjb_key_to_double(int(key.item()))
+    uu = np.random.default_rng(7).uniform(size=n)[lo:hi]  # sample g uses the g-th uniform
+    good = np.where(np.exp(ll - gmax) > uu)[0] + lo
+    if max_keep is not None:
+        good = good[:max_keep]
+    idx, total, near = gather_accepted(good, len(np.where(np.exp(ll - gmax) > uu)[0]), 0, max_keep)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), idx=idx, total=total, gmax=gmax, ll=ll, lo=lo)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("max_keep", [None, 5])
+def test_two_rank_accept_matches_single_process(tmp_path, max_keep):
+    n, world = 6001, 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n, max_keep, str(tmp_path)), nprocs=world, join=True)
+    r = [np.load(tmp_path / f"r{k}.npz") for k in range(world)]
+    ll = np.concatenate([r[0]["ll"], r[1]["ll"]])
+    assert len(ll) == n and r[1]["lo"] == 3001  # first shard gets the remainder
+    uu = np.random.default_rng(7).uniform(size=n)
+    want = np.where(np.exp(ll - ll.max()) > uu)[0]
+    assert r[0]["gmax"] == r[1]["gmax"] == ll.max()
+    for k in range(world):
+        assert r[k]["total"] == len(want)
+        assert np.array_equal(r[k]["idx"], want if max_keep is None else want[:max_keep])

@@ -21,7 +21,8 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["batch_tasks", "shard_ranges", "DeviceEngine", "merge_accepted"]
+__all__ = ["batch_tasks", "shard_ranges", "DeviceEngine", "merge_accepted", "allreduce_max_key",
+           "gather_accepted"]
 
 
 def batch_tasks(n_tasks, n_batches, arr=None, args=None, start_idx=0):
@@ -60,6 +61,34 @@ def merge_accepted(per_shard_idx, per_shard_total, max_keep):
     if max_keep is not None:
         idx = idx[:max_keep]
     return idx, total
+
+
+def allreduce_max_key(key, group=None):
+    """In-place integer MAX all-reduce of an int64 max-key tensor (the one collective
+    of the accept step: multiproc_helpers.py:256-258 does ``lls.max()`` on the master
+    after gathering every ll; here only 8 bytes per rank move).  NCCL for CUDA
+    tensors; gloo (CPU tests) goes through a host copy when the tensor is on a GPU."""
+    import torch.distributed as dist
+
+    if dist.get_backend(group) == "gloo" and key.is_cuda:
+        tmp = key.cpu()
+        dist.all_reduce(tmp, op=dist.ReduceOp.MAX, group=group)
+        key.copy_(tmp)
+    else:
+        dist.all_reduce(key, op=dist.ReduceOp.MAX, group=group)
+    return key
+
+
+def gather_accepted(idx, total, near, max_keep, group=None):
+    """All ranks get the rank-ordered concatenation of the per-rank ascending index
+    lists, truncated to max_keep, plus the global counts."""
+    import torch.distributed as dist
+
+    gathered = [None] * dist.get_world_size(group)
+    dist.all_gather_object(gathered, (np.asarray(idx, dtype=np.int64), int(total), int(near)),
+                           group=group)
+    idx, total = merge_accepted([g[0] for g in gathered], [g[1] for g in gathered], max_keep)
+    return idx, total, sum(g[2] for g in gathered)
 
 
 class _Shard:
@@ -146,17 +175,9 @@ class DeviceEngine:
             for k in keys:
                 k.fill_(m)
         if self.group is not None:
-            import torch.distributed as dist
-
-            k0 = keys[0]
-            if dist.get_backend(self.group) == "gloo":
-                tmp = k0.cpu()
-                dist.all_reduce(tmp, op=dist.ReduceOp.MAX, group=self.group)
-                k0.copy_(tmp)
-            else:
-                dist.all_reduce(k0, op=dist.ReduceOp.MAX, group=self.group)
+            allreduce_max_key(keys[0], self.group)
             for k in keys[1:]:
-                k.copy_(k0.to(k.device))
+                k.copy_(keys[0].to(k.device))
         return keys[0]
 
     def max_value(self):
@@ -198,12 +219,7 @@ class DeviceEngine:
                 near += nn
         idx, total = merge_accepted(per_idx, per_tot, max_keep)
         if self.group is not None:
-            import torch.distributed as dist
-
-            gathered = [None] * dist.get_world_size(self.group)
-            dist.all_gather_object(gathered, (idx, total, near), group=self.group)
-            idx, total = merge_accepted([g[0] for g in gathered], [g[1] for g in gathered], max_keep)
-            near = sum(g[2] for g in gathered)
+            idx, total, near = gather_accepted(idx, total, near, max_keep, self.group)
         return idx, total, near
 
     # -- host access ------------------------------------------------------------
