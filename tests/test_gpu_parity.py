@@ -405,6 +405,7 @@ def test_large_n_properties(torch_cuda):
     P = torch.exp(U[0] * np.log(512.0) + np.log(2.0))
     e = torch.distributions.Beta(torch.tensor(0.867, dtype=torch.float64, device="cuda"),
                                  torch.tensor(3.03, dtype=torch.float64, device="cuda")).sample((n,))
+    e = e.contiguous()
     om, M0 = (U[2] * 2 - 1) * np.pi, (U[3] * 2 - 1) * np.pi
     key = helper.new_llmax_key()
     ll = helper.marginal_ll_soa(P, e, om, M0, llmax_key=key)

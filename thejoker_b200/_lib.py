@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libthejoker_b200.so")
+LIB_PATH = os.environ.get("TJB_LIB_PATH", os.path.join(_HERE, "libthejoker_b200.so"))  # override: tuning builds
 _SRC = [os.path.join(_HERE, "csrc", f) for f in
         ("tjb_api.cu", "kepler.cuh", "linalg.cuh", "marginal_ll.cuh", "accept.cuh", "posterior.cuh")]
 _HDR = os.path.join(os.path.dirname(_HERE), "include", "thejoker_b200.h")

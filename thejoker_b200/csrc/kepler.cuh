@@ -206,79 +206,110 @@ struct SolveStats {
 // the warp moved by more than 1e-4 (tc.m[2]).
 constexpr int kF64MaxIter = 16;
 
-// One epoch.  dt = t_n - t_ref [day].  Returns z_n; all lanes of a warp must call together.
-template <bool kCountStats>
-TJB_HD double rv_unit_column(const OrbitConsts &oc, const TrigCoef &tc, double dt, SolveStats *st) {
-  // mean anomaly in quarter-revolutions (unreduced)
-  const double x4 = fma(dt, oc.nu4, -oc.ph4);
+// K epochs of one sample at once (K independent dependency chains interleaved by
+// the compiler: the per-epoch chain is ~600 cycles of latency for ~120 issue slots, so
+// with 4-5 resident warps per scheduler a single chain per thread leaves the FP64 pipe
+// half idle).  dt[k] = t_n - t_ref [day]; z[k] receives z_n.  All lanes of a warp must
+// call together.
+template <int K, bool kCountStats>
+TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const double *dt, double *z,
+                            SolveStats *st) {
+  double x4[K], D[K], sE[K], cE[K];
+  float Df[K];
 
   // ---- FP32: reduce, starter D0 = e sinM / sqrt(1 - 2 e cosM + e^2), one
   //      third-order Householder step.  Errors of this stage (including the
   //      ~1e-5 from rounding x4 to float) only move the FP64 starting point.
   const float ef = oc.ef;
-  const float x4f = (float)x4;
-  const float r4 = (x4f * 0.25f + kMagicF) - kMagicF;      // nearest whole revolution
-  const float Mf = fmaf(r4, -4.0f, x4f) * 1.57079632679f;  // M in [-pi, pi]
-  float Df;
-  {
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    x4[k] = fma(dt[k], oc.nu4, -oc.ph4);  // mean anomaly in quarter-revolutions (unreduced)
+    const float x4f = (float)x4[k];
+    const float r4 = (x4f * 0.25f + kMagicF) - kMagicF;      // nearest whole revolution
+    const float Mf = fmaf(r4, -4.0f, x4f) * 1.57079632679f;  // M in [-pi, pi]
     const float sM = fsin_approx(Mf), cM = fcos_approx(Mf);
-    Df = ef * sM * frsqrt_approx(fmaf(-2.0f * ef, cM, oc.g0f));
-    const float Ef = Mf + Df;
+    const float D0 = ef * sM * frsqrt_approx(fmaf(-2.0f * ef, cM, oc.g0f));
+    const float Ef = Mf + D0;
     const float es = ef * fsin_approx(Ef), ec = ef * fcos_approx(Ef);
     const float r = frcp_approx(1.0f - ec);
-    const float t = es * r;           // f''/f'
-    const float u = fmaf(-Df, r, t);  // -f/f'
+    const float t = es * r;           // f2/f1
+    const float u = fmaf(-D0, r, t);  // -f/f1
     const float q = fmaf(0.5f * t, t, ec * r * (-1.0f / 6.0f));
     const float del = u * fmaf(u, fmaf(u, q, -0.5f * t), 1.0f);
-    Df = fminf(fmaxf(Df + del, -ef), ef);  // |E - M| <= e holds for the root
+    Df[k] = fminf(fmaxf(D0 + del, -ef), ef);  // |E - M| <= e holds for the root
   }
 
   // ---- FP64: exact reduction of E0 = M + D0 and one full sincos -----------
-  const double d4 = (double)(Df * 0.63661977236f);  // D0 in quarter-revolutions
-  const double v = x4 + d4;
-  const double tv = v + kMagic;
-  const double w = v - (tv - kMagic);  // in [-0.5, 0.5]
-  double sE, cE;
-  sincos_quarter(tc, w, lo32(tv), sE, cE);
-  double D = d4 * tc.m[4];  // E0 - M [rad]
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const double d4 = (double)(Df[k] * 0.63661977236f);  // D0 in quarter-revolutions
+    const double v = x4[k] + d4;
+    const double tv = v + kMagic;
+    const double w = v - (tv - kMagic);  // in [-0.5, 0.5]
+    sincos_quarter(tc, w, lo32(tv), sE[k], cE[k]);
+    D[k] = d4 * tc.m[4];  // E0 - M [rad]
+  }
 
   // ---- third-order Householder step with angle-addition update -------------
-  // Normal case: one pass.  If any lane of the warp moved by more than 1e-4,
-  // (sinE, cosE) are re-evaluated in full at the updated E and the pass repeats
-  // (warp-uniform branch; rare: e >~ 0.8 near pericentre).
+  // Normal case: one pass.  If any lane of the warp moved by more than 1e-4 in any of
+  // its K epochs, (sinE, cosE) are re-evaluated in full at the updated E and the pass
+  // repeats (warp-uniform branch; rare: e >~ 0.8 near pericentre).
+  // With f = D - e sinE, f1 = 1 - e cosE, f2 = e sinE, f3 = e cosE:
+  //   u = -f/f1, t = f2/f1, b6 = f3/(6 f1), delta = u (1 + u (-t/2 + u (t^2/2 - b6)))
   for (int it = 0;; ++it) {
-    const double es = oc.e * sE;
-    const double r = rcp_pos(fma(-oc.e, cE, 1.0));
-    const double t = es * r;             // f''/f'
-    const double u = fma(-D, r, t);      // Newton step -f/f' = (e sinE - D)/f'
-    const double b6 = (oc.e6 * cE) * r;  // f'''/(6 f')
-    const double th = 0.5 * t;
-    // delta = u (1 + u (-t/2 + u (t^2/2 - b6)))
-    const double q = fma(th, t, -b6);
-    const double del = u * fma(u, fma(u, q, -th), 1.0);
-    D += del;
-    const bool big = !(fabs(del) <= tc.m[2]);
+    double del[K];
+    bool big = false;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const double es = oc.e * sE[k];
+      const double r = rcp_pos(fma(-oc.e, cE[k], 1.0));
+      const double t = es * r;
+      const double u = fma(-D[k], r, t);
+      const double b6 = (oc.e6 * cE[k]) * r;
+      const double th = 0.5 * t;
+      const double q = fma(th, t, -b6);
+      del[k] = u * fma(u, fma(u, q, -th), 1.0);
+      D[k] += del[k];
+      big = big || !(fabs(del[k]) <= tc.m[2]);
+    }
     if (!any_lane(big) || it + 1 >= kF64MaxIter) {
       if (kCountStats && big) st->not_converged++;
-      // rotate (sinE, cosE) by delta, |delta| <= 1e-4: truncation error < 1e-21
-      const double d2 = del * del;
-      const double sd = del * fma(d2, -tc.m[0], 1.0);
-      const double cd = fma(d2, fma(d2, tc.m[1], -0.5), 1.0);
-      const double sN = fma(cE, sd, sE * cd);
-      cE = fma(-sE, sd, cE * cd);
-      sE = sN;
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        // rotate (sinE, cosE) by delta, |delta| <= 1e-4: truncation error < 1e-21
+        const double d2 = del[k] * del[k];
+        const double sd = del[k] * fma(d2, -tc.m[0], 1.0);
+        const double cd = fma(d2, fma(d2, tc.m[1], -0.5), 1.0);
+        const double sN = fma(cE[k], sd, sE[k] * cd);
+        cE[k] = fma(-sE[k], sd, cE[k] * cd);
+        sE[k] = sN;
+      }
       break;
     }
     if (kCountStats) st->extra_f64++;
-    const double v2 = fma(D, tc.m[3], x4);
-    const double tv2 = v2 + kMagic;
-    sincos_quarter(tc, v2 - (tv2 - kMagic), lo32(tv2), sE, cE);
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const double v2 = fma(D[k], tc.m[3], x4[k]);
+      const double tv2 = v2 + kMagic;
+      sincos_quarter(tc, v2 - (tv2 - kMagic), lo32(tv2), sE[k], cE[k]);
+    }
   }
 
   // ---- z = [a (cosE - e) + b sinE] / (1 - e cosE) + e a ---------------------
-  const double r = rcp_pos(fma(-oc.e, cE, 1.0));
-  const double num = fma(oc.b, sE, fma(oc.a, cE, -oc.ea));
-  return fma(num, r, oc.ea);
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const double r = rcp_pos(fma(-oc.e, cE[k], 1.0));
+    const double num = fma(oc.b, sE[k], fma(oc.a, cE[k], -oc.ea));
+    z[k] = fma(num, r, oc.ea);
+  }
+}
+
+// One epoch.
+template <bool kCountStats>
+TJB_HD double rv_unit_column(const OrbitConsts &oc, const TrigCoef &tc, double dt, SolveStats *st) {
+  double z;
+  rv_unit_columns<1, kCountStats>(oc, tc, &dt, &z, st);
+  return z;
 }
 
 }  // namespace tjb

@@ -35,6 +35,12 @@ struct PriorView {
 // in chi2.
 TJB_HD constexpr int row_stride(int L) { return (L + 2 + 1) & ~1; }
 
+// epochs processed per loop iteration of the constant-jitter kernel
+#ifndef TJB_EPOCHS_PER_ITER
+#define TJB_EPOCHS_PER_ITER 2
+#endif
+constexpr int kEpochsPerIter = TJB_EPOCHS_PER_ITER;
+
 struct StarParams {
   int n_times;
   const double *table;              // device, [N, row_stride(L)]
@@ -110,7 +116,23 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab, do
 #pragma unroll
     for (int k = 1; k < L; k++) SzT[k] = 0.0;
     const double *row = tab;
-    for (int n = 0; n < N; n++, row += RS) {
+    int n = 0;
+    // kEpochsPerIter epochs per iteration: independent Kepler chains for ILP
+    for (; n + kEpochsPerIter <= N; n += kEpochsPerIter, row += kEpochsPerIter * RS) {
+      double dt[kEpochsPerIter], z[kEpochsPerIter];
+#pragma unroll
+      for (int j = 0; j < kEpochsPerIter; j++) dt[j] = row[j * RS];
+      rv_unit_columns<kEpochsPerIter, false>(oc, tc, dt, z, nullptr);
+#pragma unroll
+      for (int j = 0; j < kEpochsPerIter; j++) {
+        const double *rj = row + j * RS;
+        Szz = fma(z[j] * z[j], rj[1], Szz);
+        Szy = fma(z[j], rj[2], Szy);
+#pragma unroll
+        for (int k = 1; k < L; k++) SzT[k] = fma(z[j], rj[2 + k], SzT[k]);
+      }
+    }
+    for (; n < N; n++, row += RS) {
       const double z = rv_unit_column<false>(oc, tc, row[0], nullptr);
       Szz = fma(z * z, row[1], Szz);
       Szy = fma(z, row[2], Szy);
@@ -188,10 +210,16 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab, do
 
 #if defined(__CUDACC__)
 
-constexpr int kLLThreads = 256;
+#ifndef TJB_LL_THREADS
+#define TJB_LL_THREADS 256
+#endif
+#ifndef TJB_LL_MIN_CTAS
+#define TJB_LL_MIN_CTAS 2
+#endif
+constexpr int kLLThreads = TJB_LL_THREADS;
 
 template <int L, bool kJit>
-__global__ void __launch_bounds__(kLLThreads, 2)
+__global__ void __launch_bounds__(kLLThreads, TJB_LL_MIN_CTAS)
 marginal_ll_kernel(const StarParams sp, const PriorView pv, const long long n,
                    double *__restrict__ ll_out, long long *__restrict__ llmax_key) {
   extern __shared__ double tab[];

@@ -1,0 +1,59 @@
+"""Time every build/variants/*.so (kernel tuning builds) on the GPU box.
+Each variant runs in its own process (the library path is fixed at import)."""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CHILD = r'''
+import json, os, sys
+import numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+import thejoker_b200 as tj
+from helpers import star_spec
+from thejoker_b200.data_helpers import validate_prepare_data
+out = {"lib": os.path.basename(os.environ["TJB_LIB_PATH"])}
+n = 1 << 24
+g = torch.Generator(device="cuda").manual_seed(1)
+P = torch.exp(torch.rand(n, dtype=torch.float64, device="cuda", generator=g) * np.log(512.0) + np.log(2.0))
+torch.manual_seed(1)
+ga = torch._standard_gamma(torch.full((n,), 0.867, dtype=torch.float64, device="cuda"))
+gb = torch._standard_gamma(torch.full((n,), 3.03, dtype=torch.float64, device="cuda"))
+e = (ga / (ga + gb)).contiguous()
+om = (torch.rand(n, dtype=torch.float64, device="cuda", generator=g) * 2 - 1) * np.pi
+M0 = (torch.rand(n, dtype=torch.float64, device="cuda", generator=g) * 2 - 1) * np.pi
+s = torch.exp(torch.randn(n, dtype=torch.float64, device="cuda", generator=g) - 2)
+ll = torch.empty(n, dtype=torch.float64, device="cuda")
+for N, pt, jit in ((64, 1, False), (64, 2, True), (256, 1, False), (16, 1, False)):
+    spec, data, prior = star_spec(N, pt)
+    all_data, ids, trend_M = validate_prepare_data(data, prior.poly_trend, prior.n_offsets)
+    h = tj.CJokerHelper(all_data, prior, trend_M, device=0)
+    m = n if N <= 64 else n // 4
+    args = [t[:m] for t in (P, e, om, M0)]
+    for _ in range(2):
+        h.marginal_ll_soa(*args, s=s[:m] if jit else None, out=ll[:m])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        h.marginal_ll_soa(*args, s=s[:m] if jit else None, out=ll[:m])
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    out[f"N{N}_L{1+pt}_{'jit' if jit else 'const'}"] = round(m / ms * 1e3 / 1e9, 4)
+    out["ctas_per_sm"] = h.device_info()["ctas_per_sm"]
+    out[f"chk{N}{jit}"] = float(ll[:1000].sum().item())
+print(json.dumps(out))
+''' % (ROOT, ROOT)
+
+results = []
+for lib in sorted(glob.glob(os.path.join(ROOT, "build", "variants", "*.so"))):
+    env = dict(os.environ, TJB_LIB_PATH=lib)
+    r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
+    line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-400:]
+    print(line, flush=True)
+    results.append(line)
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+open(os.path.join(ROOT, "gpurun_out", "tune.jsonl"), "w").write("\n".join(results) + "\n")
