@@ -87,17 +87,15 @@ TJB_D float frcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-// reciprocal of a positive, normal double: MUFU.RCP64H seed + 2 Newton steps.
-// The argument here is always 1 - e cosE in (1-e, 1+e], so none of the
-// denormal / overflow handling of a general division is needed.
+// reciprocal of a positive, normal double: MUFU.RCP64H seed (20 bits, measured:
+// tools/microbench3.cu) + one third-order step r (1 + t + t^2), t = 1 - x r: relative
+// error <= 2.2e-16 with 3 FMAs.  The argument here is always 1 - e cosE in (1-e, 1+e],
+// so none of the denormal / overflow handling of a general division is needed.
 TJB_D double rcp_pos(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double t = fma(-x, r, 1.0);
-  r = fma(r, t, r);
-  t = fma(-x, r, 1.0);
-  r = fma(r, t, r);
-  return r;
+  const double t = fma(-x, r, 1.0);
+  return fma(r, fma(t, t, t), r);
 }
 #else
 inline int lo32(double x) { int64_t b; memcpy(&b, &x, 8); return (int)(uint32_t)(b & 0xffffffff); }
@@ -112,6 +110,43 @@ inline float frcp_approx(float x) { return 1.0f / x; }
 inline double rcp_pos(double x) { return 1.0 / x; }
 #endif
 
+// How the loop gets its FP64 constants (measured on B200):
+//   0  pinned in registers (coefficient + run-time zero)
+//   1  __constant__ arrays read in the loop (ptxas emits LDC / LDCU per use)
+//   2  literals (ptxas materialises them with MOVs / immediates)
+#ifndef TJB_COEF_MODE
+#define TJB_COEF_MODE 0
+#endif
+TJB_HD constexpr double sin_lit(int i) {
+  return i == 0 ? 1.570796326794896619231322 : i == 1 ? -0.6459640975062449269023451
+       : i == 2 ? 0.07969262624606334392301012 : i == 3 ? -0.004681754132625933413797963
+       : i == 4 ? 0.0001604411526673809583408432 : i == 5 ? -0.000003598649570240691901625632
+       : 5.634704113884750951753422e-8;
+}
+TJB_HD constexpr double cos_lit(int i) {
+  return i == 0 ? 1.0 : i == 1 ? -1.233700550136169827354311 : i == 2 ? 0.2536695079010476193552061
+       : i == 3 ? -0.02086348076333075982186824 : i == 4 ? 0.000919260274390553378473447
+       : i == 5 ? -0.00002520203791691774237050555 : i == 6 ? 0.0000004710641505803501879438872
+       : -6.324746678866069891109223e-9;
+}
+TJB_HD constexpr double misc_lit(int i) {
+  return i == 0 ? 1.0 / 6.0 : i == 1 ? 1.0 / 24.0 : i == 2 ? 1.0e-4 : i == 3 ? 0.63661977236758134308
+       : 1.57079632679489661923;
+}
+#if TJB_COEF_MODE == 0 || !defined(__CUDA_ARCH__)
+#define TJB_SC(i) tc.s[i]
+#define TJB_CC(i) tc.c[i]
+#define TJB_MC(i) tc.m[i]
+#elif TJB_COEF_MODE == 1
+#define TJB_SC(i) kSinC[i]
+#define TJB_CC(i) kCosC[i]
+#define TJB_MC(i) kMisc[i]
+#else
+#define TJB_SC(i) sin_lit(i)
+#define TJB_CC(i) cos_lit(i)
+#define TJB_MC(i) misc_lit(i)
+#endif
+
 // The polynomial coefficients, pinned in registers for the whole epoch loop.
 // ptxas otherwise re-loads each of them from the constant bank on every epoch
 // (17 LDC per iteration), which makes the loop issue-bound instead of FP64-bound.
@@ -120,6 +155,10 @@ struct TrigCoef {
   // `zero` must be a run-time 0.0 (a kernel parameter): coefficient + zero is an
   // FP64 result ptxas will not rematerialise, so the values stay in registers.
   TJB_HD void load(double zero) {
+#if TJB_COEF_MODE != 0 && defined(__CUDA_ARCH__)
+    (void)zero;
+    return;
+#endif
 #pragma unroll
     for (int i = 0; i < 7; i++) s[i] = kSinC[i] + zero;
 #pragma unroll
@@ -132,18 +171,18 @@ struct TrigCoef {
 // sin and cos of (k + w) * pi/2 for |w| <= 0.5 and integer quadrant k (any int).
 TJB_HD void sincos_quarter(const TrigCoef &tc, double w, int k, double &s, double &c) {
   const double w2 = w * w;
-  double ps = fma(tc.s[6], w2, tc.s[5]);
-  double pc = fma(tc.c[7], w2, tc.c[6]);
-  ps = fma(ps, w2, tc.s[4]);
-  pc = fma(pc, w2, tc.c[5]);
-  ps = fma(ps, w2, tc.s[3]);
-  pc = fma(pc, w2, tc.c[4]);
-  ps = fma(ps, w2, tc.s[2]);
-  pc = fma(pc, w2, tc.c[3]);
-  ps = fma(ps, w2, tc.s[1]);
-  pc = fma(pc, w2, tc.c[2]);
-  ps = fma(ps, w2, tc.s[0]);
-  pc = fma(pc, w2, tc.c[1]);
+  double ps = fma(TJB_SC(6), w2, TJB_SC(5));
+  double pc = fma(TJB_CC(7), w2, TJB_CC(6));
+  ps = fma(ps, w2, TJB_SC(4));
+  pc = fma(pc, w2, TJB_CC(5));
+  ps = fma(ps, w2, TJB_SC(3));
+  pc = fma(pc, w2, TJB_CC(4));
+  ps = fma(ps, w2, TJB_SC(2));
+  pc = fma(pc, w2, TJB_CC(3));
+  ps = fma(ps, w2, TJB_SC(1));
+  pc = fma(pc, w2, TJB_CC(2));
+  ps = fma(ps, w2, TJB_SC(0));
+  pc = fma(pc, w2, TJB_CC(1));
   const double sx = ps * w;
   const double cx = fma(pc, w2, 1.0);
   // quadrant rotation: k=0 (s,c) k=1 (c,-s) k=2 (-s,-c) k=3 (-c,s)
@@ -203,7 +242,7 @@ struct SolveStats {
 
 // A third-order Householder step maps an error eps to ~C eps^4 with C = O(1) for
 // e <~ 0.95 (tools/kepler_solver_study.py): the pass is repeated while any lane of
-// the warp moved by more than 1e-4 (tc.m[2]).
+// the warp moved by more than 1e-4 (TJB_MC(2)).
 constexpr int kF64MaxIter = 16;
 
 // K epochs of one sample at once (K independent dependency chains interleaved by
@@ -247,7 +286,7 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
     const double tv = v + kMagic;
     const double w = v - (tv - kMagic);  // in [-0.5, 0.5]
     sincos_quarter(tc, w, lo32(tv), sE[k], cE[k]);
-    D[k] = d4 * tc.m[4];  // E0 - M [rad]
+    D[k] = d4 * TJB_MC(4);  // E0 - M [rad]
   }
 
   // ---- third-order Householder step with angle-addition update -------------
@@ -270,16 +309,17 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
       const double q = fma(th, t, -b6);
       del[k] = u * fma(u, fma(u, q, -th), 1.0);
       D[k] += del[k];
-      big = big || !(fabs(del[k]) <= tc.m[2]);
+      big = big || !(fabs(del[k]) <= TJB_MC(2));
     }
     if (!any_lane(big) || it + 1 >= kF64MaxIter) {
       if (kCountStats && big) st->not_converged++;
 #pragma unroll
       for (int k = 0; k < K; k++) {
-        // rotate (sinE, cosE) by delta, |delta| <= 1e-4: truncation error < 1e-21
+        // rotate (sinE, cosE) by delta, |delta| <= 1e-4: sin d = d (1 - d^2/6) + O(1e-22),
+        // cos d = 1 - d^2/2 + O(4e-18)
         const double d2 = del[k] * del[k];
-        const double sd = del[k] * fma(d2, -tc.m[0], 1.0);
-        const double cd = fma(d2, fma(d2, tc.m[1], -0.5), 1.0);
+        const double sd = del[k] * fma(d2, -TJB_MC(0), 1.0);
+        const double cd = fma(d2, -0.5, 1.0);
         const double sN = fma(cE[k], sd, sE[k] * cd);
         cE[k] = fma(-sE[k], sd, cE[k] * cd);
         sE[k] = sN;
@@ -289,7 +329,7 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
     if (kCountStats) st->extra_f64++;
 #pragma unroll
     for (int k = 0; k < K; k++) {
-      const double v2 = fma(D[k], tc.m[3], x4[k]);
+      const double v2 = fma(D[k], TJB_MC(3), x4[k]);
       const double tv2 = v2 + kMagic;
       sincos_quarter(tc, v2 - (tv2 - kMagic), lo32(tv2), sE[k], cE[k]);
     }

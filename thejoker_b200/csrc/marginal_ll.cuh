@@ -159,18 +159,18 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab, do
     LogProduct lp;
     lp.init();
     const double *row = tab;
-    for (int n = 0; n < N; n++, row += RS) {
-      const double z = rv_unit_column<false>(oc, tc, row[0], nullptr);
-      const double var = row[1] + s2;
-      const double w = 1.0 / var;
+    int n = 0;
+    auto accumulate = [&](const double *rj, double z) {
+      const double var = rj[1] + s2;
+      // positive and normal unless ivar == 0 (var = inf): then the epoch has zero weight
+      const double w = var < 1.0e300 ? rcp_pos(var) : 0.0;
       lp.mul(var);
-      if ((n & 3) == 3) lp.renorm();
-      const double y = row[2];
+      const double y = rj[2];
       // column values of M for this epoch: m[0] = z, m[k] = T_k
       double m[L];
       m[0] = z;
 #pragma unroll
-      for (int k = 1; k < L; k++) m[k] = row[2 + k];
+      for (int k = 1; k < L; k++) m[k] = rj[2 + k];
       const double wy = w * y;
       Syy = fma(wy, y, Syy);
 #pragma unroll
@@ -180,6 +180,19 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab, do
 #pragma unroll
         for (int j = i; j < L; j++) G[tri<L>(i, j)] = fma(wm, m[j], G[tri<L>(i, j)]);
       }
+    };
+    for (; n + kEpochsPerIter <= N; n += kEpochsPerIter, row += kEpochsPerIter * RS) {
+      double dt[kEpochsPerIter], z[kEpochsPerIter];
+#pragma unroll
+      for (int j = 0; j < kEpochsPerIter; j++) dt[j] = row[j * RS];
+      rv_unit_columns<kEpochsPerIter, false>(oc, tc, dt, z, nullptr);
+#pragma unroll
+      for (int j = 0; j < kEpochsPerIter; j++) accumulate(row + j * RS, z[j]);
+      lp.renorm();  // at most kEpochsPerIter factors between renormalisations
+    }
+    for (; n < N; n++, row += RS) {
+      accumulate(row, rv_unit_column<false>(oc, tc, row[0], nullptr));
+      lp.renorm();
     }
     lp.renorm();
 #pragma unroll
