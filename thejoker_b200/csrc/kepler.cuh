@@ -241,15 +241,39 @@ struct SolveStats {
 };
 
 // A third-order Householder step maps an error eps to ~C eps^4 with C = O(1) for
-// e <~ 0.95 (tools/kepler_solver_study.py): the pass is repeated while any lane of
-// the warp moved by more than 1e-4 (TJB_MC(2)).
+// e <~ 0.95 (tools/kepler_solver_study.py): a lane repeats the pass while it moved by
+// more than 1e-4 (kMisc[2]), at most kF64MaxIter times.
 constexpr int kF64MaxIter = 16;
 
+// One third-order Householder step from (D, sE, cE): returns delta.
+//   f = D - e sinE, f1 = 1 - e cosE, f2 = e sinE, f3 = e cosE
+//   u = -f/f1, t = f2/f1, b6 = f3/(6 f1), delta = u (1 + u (-t/2 + u (t^2/2 - b6)))
+TJB_HD double householder3(const OrbitConsts &oc, double D, double sE, double cE) {
+  const double es = oc.e * sE;
+  const double r = rcp_pos(fma(-oc.e, cE, 1.0));
+  const double t = es * r;
+  const double u = fma(-D, r, t);
+  const double b6 = (oc.e6 * cE) * r;
+  const double th = 0.5 * t;
+  const double q = fma(th, t, -b6);
+  return u * fma(u, fma(u, q, -th), 1.0);
+}
+
+// rotate (sinE, cosE) by delta, |delta| <= 1e-4: sin d = d (1 - d^2/6) + O(1e-22),
+// cos d = 1 - d^2/2 + O(4e-18)
+TJB_HD void rotate_small(const TrigCoef &tc, double del, double &sE, double &cE) {
+  const double d2 = del * del;
+  const double sd = del * fma(d2, -TJB_MC(0), 1.0);
+  const double cd = fma(d2, -0.5, 1.0);
+  const double sN = fma(cE, sd, sE * cd);
+  cE = fma(-sE, sd, cE * cd);
+  sE = sN;
+}
+
 // K epochs of one sample at once (K independent dependency chains interleaved by
-// the compiler: the per-epoch chain is ~600 cycles of latency for ~120 issue slots, so
-// with 4-5 resident warps per scheduler a single chain per thread leaves the FP64 pipe
-// half idle).  dt[k] = t_n - t_ref [day]; z[k] receives z_n.  All lanes of a warp must
-// call together.
+// the compiler).  dt[k] = t_n - t_ref [day]; z[k] receives z_n.  All lanes of a warp
+// must call together.  The result of a lane depends only on that lane's inputs (not
+// on its warp-mates): lanes that need extra passes iterate under a per-lane flag.
 template <int K, bool kCountStats>
 TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const double *dt, double *z,
                             SolveStats *st) {
@@ -278,7 +302,10 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
     Df[k] = fminf(fmaxf(D0 + del, -ef), ef);  // |E - M| <= e holds for the root
   }
 
-  // ---- FP64: exact reduction of E0 = M + D0 and one full sincos -----------
+  // ---- FP64: exact reduction of E0 = M + D0, one full sincos, one Householder step
+  double del[K];
+  bool need[K];
+  bool any_need = false;
 #pragma unroll
   for (int k = 0; k < K; k++) {
     const double d4 = (double)(Df[k] * 0.63661977236f);  // D0 in quarter-revolutions
@@ -287,51 +314,52 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
     const double w = v - (tv - kMagic);  // in [-0.5, 0.5]
     sincos_quarter(tc, w, lo32(tv), sE[k], cE[k]);
     D[k] = d4 * TJB_MC(4);  // E0 - M [rad]
+    del[k] = householder3(oc, D[k], sE[k], cE[k]);
+    D[k] += del[k];
+    // error map of the step: eps -> ~C eps^4 (tools/kepler_solver_study.py); a lane
+    // that moved by more than 1e-4 takes further passes
+    need[k] = !(fabs(del[k]) <= TJB_MC(2));
+    any_need = any_need || need[k];
   }
-
-  // ---- third-order Householder step with angle-addition update -------------
-  // Normal case: one pass.  If any lane of the warp moved by more than 1e-4 in any of
-  // its K epochs, (sinE, cosE) are re-evaluated in full at the updated E and the pass
-  // repeats (warp-uniform branch; rare: e >~ 0.8 near pericentre).
-  // With f = D - e sinE, f1 = 1 - e cosE, f2 = e sinE, f3 = e cosE:
-  //   u = -f/f1, t = f2/f1, b6 = f3/(6 f1), delta = u (1 + u (-t/2 + u (t^2/2 - b6)))
-  for (int it = 0;; ++it) {
-    double del[K];
-    bool big = false;
+  if (!any_lane(any_need)) {
+    // the normal case: every lane of the warp converged in one pass
+#pragma unroll
+    for (int k = 0; k < K; k++) rotate_small(tc, del[k], sE[k], cE[k]);
+  } else {
+    // rare (e >~ 0.8 near pericentre, or |x4| beyond float range): lanes that need it
+    // re-evaluate sincos in full at the updated E and repeat the step; converged lanes
+    // are frozen at exactly the values the normal case gives them.
 #pragma unroll
     for (int k = 0; k < K; k++) {
-      const double es = oc.e * sE[k];
-      const double r = rcp_pos(fma(-oc.e, cE[k], 1.0));
-      const double t = es * r;
-      const double u = fma(-D[k], r, t);
-      const double b6 = (oc.e6 * cE[k]) * r;
-      const double th = 0.5 * t;
-      const double q = fma(th, t, -b6);
-      del[k] = u * fma(u, fma(u, q, -th), 1.0);
-      D[k] += del[k];
-      big = big || !(fabs(del[k]) <= TJB_MC(2));
-    }
-    if (!any_lane(big) || it + 1 >= kF64MaxIter) {
-      if (kCountStats && big) st->not_converged++;
-#pragma unroll
-      for (int k = 0; k < K; k++) {
-        // rotate (sinE, cosE) by delta, |delta| <= 1e-4: sin d = d (1 - d^2/6) + O(1e-22),
-        // cos d = 1 - d^2/2 + O(4e-18)
-        const double d2 = del[k] * del[k];
-        const double sd = del[k] * fma(d2, -TJB_MC(0), 1.0);
-        const double cd = fma(d2, -0.5, 1.0);
-        const double sN = fma(cE[k], sd, sE[k] * cd);
-        cE[k] = fma(-sE[k], sd, cE[k] * cd);
-        sE[k] = sN;
+      double sR = sE[k], cR = cE[k];
+      rotate_small(tc, del[k], sR, cR);
+      bool nd = need[k];
+      double Dk = D[k];
+      for (int it = 1; it < kF64MaxIter && any_lane(nd); ++it) {
+        const double v2 = fma(Dk, TJB_MC(3), x4[k]);
+        const double tv2 = v2 + kMagic;
+        double s2, c2;
+        sincos_quarter(tc, v2 - (tv2 - kMagic), lo32(tv2), s2, c2);
+        const double d2 = householder3(oc, Dk, s2, c2);
+        if (nd) {
+          if (kCountStats) st->extra_f64++;
+          Dk += d2;
+          if (fabs(d2) <= TJB_MC(2)) {
+            rotate_small(tc, d2, s2, c2);
+            sR = s2;
+            cR = c2;
+            nd = false;
+          }
+        }
       }
-      break;
-    }
-    if (kCountStats) st->extra_f64++;
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-      const double v2 = fma(D[k], TJB_MC(3), x4[k]);
-      const double tv2 = v2 + kMagic;
-      sincos_quarter(tc, v2 - (tv2 - kMagic), lo32(tv2), sE[k], cE[k]);
+      if (nd) {  // did not converge within kF64MaxIter passes: best estimate, counted
+        if (kCountStats) st->not_converged++;
+        const double v2 = fma(Dk, TJB_MC(3), x4[k]);
+        const double tv2 = v2 + kMagic;
+        sincos_quarter(tc, v2 - (tv2 - kMagic), lo32(tv2), sR, cR);
+      }
+      sE[k] = sR;
+      cE[k] = cR;
     }
   }
 
