@@ -307,19 +307,25 @@ def _oracle_and_chunk(n):
     return OracleHelper.from_spec(spec), chunk
 
 
+def host_cores():
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1,
+    which must not cap the CPU arm)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(seconds=12.0):
     """The CPU oracle (oracle/joker_oracle.c: restatement of the reference's Cython +
     scipy LAPACK, OpenMP over samples like the reference's pool.map over chunks) on a
     bounded sample of the same workload."""
-    from oracle.oracle import load
-
-    lib = load()
-    cores = lib.orc_max_threads()
+    cores = host_cores()
     orc, chunk = _oracle_and_chunk(1 << 12)
-    orc.batch_marginal_ln_likelihood(chunk[:256], n_threads=0)
+    orc.batch_marginal_ln_likelihood(chunk[:256], n_threads=cores)
     done, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < seconds:
-        orc.batch_marginal_ln_likelihood(chunk, n_threads=0)
+        orc.batch_marginal_ln_likelihood(chunk, n_threads=cores)
         done += len(chunk)
     dt = time.perf_counter() - t0
     return {"value": done / dt, "unit": UNIT, "cores": int(cores), "kind": "port",
@@ -332,17 +338,14 @@ def run_reference(args):
     """--impl reference: the reference algorithm on the host cores (rank 0 only)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    from oracle.oracle import load
-
-    lib = load()
-    cores = lib.orc_max_threads()
+    cores = host_cores()
     n_step = 1 << args.log2_ref_step
     orc, chunk = _oracle_and_chunk(n_step)
     for _ in range(max(1, min(args.warmup, 2))):
-        orc.batch_marginal_ln_likelihood(chunk[: n_step // 4], n_threads=0)
+        orc.batch_marginal_ln_likelihood(chunk[: n_step // 4], n_threads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.batch_marginal_ln_likelihood(chunk, n_threads=0)
+        orc.batch_marginal_ln_likelihood(chunk, n_threads=cores)
     dt = time.perf_counter() - t0
     value = n_step * args.steps / dt
     sample = (f"each step = {n_step} samples of the same workload (2^{LOG2_PRIOR} would take "

@@ -1,0 +1,88 @@
+"""Multi-GPU paths (skipped on a single-GPU box): one process driving two GPUs, and
+two NCCL ranks (one per GPU) in SPMD mode, must both reproduce the single-GPU result
+bit for bit -- same ll, same accepted indices, same posterior samples."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _n_gpus():
+    import torch
+
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def _setup():
+    import thejoker_b200 as tj
+    from helpers import default_prior
+    from thejoker_b200.synthetic import make_data
+
+    prior = default_prior(2, sigma_K0=25.0, P_min=5.0, P_max=500.0)
+    flat, _ = make_data(12, rng=np.random.default_rng(11), K=1e-4)
+    ps = prior.sample(size=100_003, return_logprobs=True, rng=np.random.default_rng(1))
+    return tj, prior, flat, ps
+
+
+def _run(joker, flat, ps):
+    out = {}
+    out["ll"] = joker.marginal_ln_likelihood(flat, ps)
+    s = joker.rejection_sample(flat, ps, max_posterior_samples=200, return_logprobs=True,
+                               in_memory=True)
+    out["rej_P"], out["rej_K"] = s["P"].value, s["K"].value
+    out["rej_ll"] = s["ln_likelihood"].value
+    s = joker.iterative_rejection_sample(flat, ps, n_requested_samples=64, in_memory=True)
+    out["it_P"], out["it_K"] = s["P"].value, s["K"].value
+    out["n_eval"] = joker.last_stats["n_ll_evaluated"]
+    return out
+
+
+def test_one_process_two_gpus():
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    tj, prior, flat, ps = _setup()
+    a = _run(tj.TheJoker(prior, rng=np.random.default_rng(42), devices=[0]), flat, ps)
+    b = _run(tj.TheJoker(prior, rng=np.random.default_rng(42), devices=[0, 1]), flat, ps)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+
+
+def _worker(rank, world, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world,
+                            device_id=torch.device(f"cuda:{rank}"))
+    tj, prior, flat, ps = _setup()
+    joker = tj.TheJoker(prior, rng=np.random.default_rng(42), devices=[rank],
+                        group=dist.group.WORLD)
+    out = _run(joker, flat, ps)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **out)
+    dist.destroy_process_group()
+
+
+def test_two_nccl_ranks_spmd(tmp_path):
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    tj, prior, flat, ps = _setup()
+    want = _run(tj.TheJoker(prior, rng=np.random.default_rng(42), devices=[0]), flat, ps)
+    for rank in range(2):
+        got = np.load(tmp_path / f"rank{rank}.npz")
+        for k in want:
+            assert np.array_equal(want[k], got[k]), (rank, k)

@@ -155,6 +155,13 @@ class DeviceEngine:
                                           s=None if sh.s is None else sh.s[sl],
                                           s_const=self.s_const, out=sh.ll[sl], llmax_key=sh.key)
 
+    def compute_ll_global(self, glo, ghi):
+        """ll for the part of the GLOBAL index range [glo, ghi) this process owns."""
+        lo = max(glo, self.global_offset) - self.global_offset
+        hi = min(ghi, self.global_offset + self.n_local) - self.global_offset
+        if lo < hi:
+            self.compute_ll(lo, hi)
+
     def reset_max(self):
         for sh in self.shards:
             with self.torch.cuda.device(sh.device):
@@ -195,7 +202,8 @@ class DeviceEngine:
         Returns (global indices int64 ascending, n_accepted_total, n_near).
         """
         torch = self.torch
-        hi = self.n_local if hi is None else hi
+        # hi is a GLOBAL count of accumulated samples; this process owns part of it
+        hi = self.n_local if hi is None else max(0, min(hi - self.global_offset, self.n_local))
         self.global_max_key()
         per_idx, per_tot, near = [], [], 0
         for sh in self.shards:
@@ -205,7 +213,8 @@ class DeviceEngine:
             with torch.cuda.device(sh.device):
                 ll = sh.ll[: b - a]
                 if uniforms is not None:
-                    u_dev = torch.from_numpy(np.ascontiguousarray(uniforms[a:b])).to(ll.device)
+                    g0 = self.global_offset
+                    u_dev = torch.from_numpy(np.ascontiguousarray(uniforms[g0 + a:g0 + b])).to(ll.device)
                     idx, tot, nn = sh.helper.accept(ll, sh.key, uniforms=u_dev,
                                                     index_base=self.global_offset + a,
                                                     max_keep=max_keep, near_tol=near_tol)
@@ -221,6 +230,21 @@ class DeviceEngine:
         if self.group is not None:
             idx, total, near = gather_accepted(idx, total, near, max_keep, self.group)
         return idx, total, near
+
+    def gather_ll(self, glo=0, ghi=None):
+        """ll over the GLOBAL range [glo, ghi) on every rank (rank-ordered concatenation,
+        multiproc_helpers.py:120 ``np.concatenate(results)``)."""
+        ghi = self.n_global if ghi is None else ghi
+        lo = max(glo, self.global_offset) - self.global_offset
+        hi = min(ghi, self.global_offset + self.n_local) - self.global_offset
+        mine = self.download_ll(lo, hi) if lo < hi else np.zeros(0)
+        if self.group is None:
+            return mine
+        import torch.distributed as dist
+
+        parts = [None] * dist.get_world_size(self.group)
+        dist.all_gather_object(parts, mine, group=self.group)
+        return np.concatenate(parts)
 
     # -- host access ------------------------------------------------------------
     def download_ll(self, lo=0, hi=None):

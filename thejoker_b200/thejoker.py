@@ -50,10 +50,15 @@ class TheJoker:
     tempfile_path : str (optional, unused: no temporary cache file is written)
     devices : list of CUDA device indices (default: [LOCAL_RANK or 0])
     jitter_mode : "apply" | "reference" -- see CJokerHelper
+    group : torch.distributed process group (optional).  SPMD use under torchrun: every
+        rank constructs the same TheJoker (same prior samples, same rng seed) and calls
+        the same method; each rank evaluates only its contiguous shard of the prior
+        cache on its GPU, the max is combined with an integer MAX all-reduce (NCCL) and
+        the accepted indices are gathered, so every rank returns identical samples.
     """
 
     def __init__(self, prior, pool=None, rng=None, tempfile_path=None, devices=None,
-                 jitter_mode="apply"):
+                 jitter_mode="apply", group=None):
         if pool is not None and (not hasattr(pool, "map") or not hasattr(pool, "close")):
             raise TypeError("Input pool object must have .map() and .close() methods.")
         self.pool = pool
@@ -74,6 +79,7 @@ class TheJoker:
             devices = [int(os.environ.get("LOCAL_RANK", "0"))]
         self.devices = list(devices)
         self.jitter_mode = jitter_mode
+        self.group = group
         self.last_stats = {}
 
     @property
@@ -113,8 +119,20 @@ class TheJoker:
                 helpers[d] = self._make_joker_helper(data, device=d)
             return helpers[d]
 
-        eng = DeviceEngine(make, cols, devices=self.devices)
-        return eng, helpers[self.devices[0]]
+        if self.group is None:
+            eng = DeviceEngine(make, cols, devices=self.devices)
+        else:
+            import torch.distributed as dist
+
+            from .sharding import shard_ranges
+
+            n = len(cols[0])
+            rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
+            lo, hi = shard_ranges(n, world)[rank]
+            local = [c if np.ndim(c) == 0 else c[lo:hi] for c in cols]
+            eng = DeviceEngine(make, local, devices=self.devices[:1], group=self.group,
+                               global_offset=lo, global_size=n)
+        return eng, make(self.devices[0])
 
     @staticmethod
     def _rows(cols, idx):
@@ -160,7 +178,7 @@ class TheJoker:
         cols, _ = self._columns(helper0, prior_samples)
         eng, _ = self._engine(data, cols)
         eng.compute_ll()
-        return eng.download_ll()
+        return eng.gather_ll()
 
     def rejection_sample(self, data, prior_samples, n_prior_samples=None,
                          max_posterior_samples=None, n_linear_samples=1, return_logprobs=False,
@@ -206,7 +224,7 @@ class TheJoker:
                                      in_memory, n_batches)
         lls = None
         if return_logprobs or return_all_logprobs:
-            lls = eng.download_ll()
+            lls = eng.gather_ll()
         if return_logprobs:
             samples["ln_prior"] = np.repeat(ln_prior[full_idx], n_linear_samples)
             samples["ln_likelihood"] = np.repeat(lls[good], n_linear_samples)
@@ -254,7 +272,7 @@ class TheJoker:
         good = np.zeros(0, dtype=np.int64)
         for i in range(maxiter):
             logger.log(1, f"iteration {i}, computing {n_process} likelihoods")
-            eng.compute_ll(start_idx, start_idx + n_process)
+            eng.compute_ll_global(start_idx, start_idx + n_process)
             n_accum = start_idx + n_process
             good, n_good = self._uniform_accept(eng, n_accum, None)
             ll_max = self.last_stats["ll_max"]
@@ -281,7 +299,7 @@ class TheJoker:
         samples = self._full_samples(helper, self._rows(cols, good), self.rng, n_linear_samples,
                                      in_memory, n_batches)
         if return_logprobs:
-            lls = eng.download_ll(0, n_accum)
+            lls = eng.gather_ll(0, n_accum)
             samples["ln_prior"] = np.repeat(ln_prior[full_idx], n_linear_samples)
             samples["ln_likelihood"] = np.repeat(lls[good], n_linear_samples)
         self.last_stats["n_ll_evaluated"] = n_accum
