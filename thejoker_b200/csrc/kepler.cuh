@@ -114,6 +114,7 @@ inline double rcp_pos(double x) { return 1.0 / x; }
 //   0  pinned in registers (coefficient + run-time zero)
 //   1  __constant__ arrays read in the loop (ptxas emits LDC / LDCU per use)
 //   2  literals (ptxas materialises them with MOVs / immediates)
+//   3  kernel-parameter constants (StarParams::trig, constant bank 0 / uniform registers)
 #ifndef TJB_COEF_MODE
 #define TJB_COEF_MODE 0
 #endif
@@ -133,7 +134,7 @@ TJB_HD constexpr double misc_lit(int i) {
   return i == 0 ? 1.0 / 6.0 : i == 1 ? 1.0 / 24.0 : i == 2 ? 1.0e-4 : i == 3 ? 0.63661977236758134308
        : 1.57079632679489661923;
 }
-#if TJB_COEF_MODE == 0 || !defined(__CUDA_ARCH__)
+#if TJB_COEF_MODE == 0 || TJB_COEF_MODE == 3 || !defined(__CUDA_ARCH__)
 #define TJB_SC(i) tc.s[i]
 #define TJB_CC(i) tc.c[i]
 #define TJB_MC(i) tc.m[i]
@@ -155,7 +156,7 @@ struct TrigCoef {
   // `zero` must be a run-time 0.0 (a kernel parameter): coefficient + zero is an
   // FP64 result ptxas will not rematerialise, so the values stay in registers.
   TJB_HD void load(double zero) {
-#if TJB_COEF_MODE != 0 && defined(__CUDA_ARCH__)
+#if (TJB_COEF_MODE == 1 || TJB_COEF_MODE == 2) && defined(__CUDA_ARCH__)
     (void)zero;
     return;
 #endif

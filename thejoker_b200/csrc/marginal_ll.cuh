@@ -55,6 +55,7 @@ struct StarParams {
   double sigma_K0_sq, inv_P0, max_K_sq;
   int apply_jitter;                 // kJit kernels: 0 -> treat s as 0 (reference behaviour)
   double zero;                      // run-time 0.0, see TrigCoef::load
+  TrigCoef trig;                    // polynomial coefficients as kernel-parameter constants
 };
 
 // order-preserving int64 key of a double: key(a) < key(b) <=> a < b, NaN above +inf
@@ -101,8 +102,12 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab, do
                         double omega, double M0, double s) {
   constexpr int RS = row_stride(L);
   const OrbitConsts oc = make_orbit_consts(P, e, omega, M0);
+#if TJB_COEF_MODE == 3 && defined(__CUDA_ARCH__)
+  const TrigCoef &tc = sp.trig;  // constant-bank (kernel parameter) operands
+#else
   TrigCoef tc;
   tc.load(sp.zero);
+#endif
   const int N = sp.n_times;
 
   double G[kTri<L>];
@@ -233,7 +238,7 @@ constexpr int kLLThreads = TJB_LL_THREADS;
 
 template <int L, bool kJit>
 __global__ void __launch_bounds__(kLLThreads, TJB_LL_MIN_CTAS)
-marginal_ll_kernel(const StarParams sp, const PriorView pv, const long long n,
+marginal_ll_kernel(const __grid_constant__ StarParams sp, const PriorView pv, const long long n,
                    double *__restrict__ ll_out, long long *__restrict__ llmax_key) {
   extern __shared__ double tab[];
   const int tab_len = sp.n_times * row_stride(L);

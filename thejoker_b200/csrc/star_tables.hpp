@@ -59,6 +59,7 @@ inline void star_fill_common(const StarHost &st, StarParams &sp) {
   sp.max_K_sq = st.max_K * st.max_K;
   sp.apply_jitter = st.jitter_mode;
   sp.zero = 0.0;
+  sp.trig.load(0.0);  // host copy of the polynomial coefficients (TJB_COEF_MODE 3)
   for (int i = 1; i < st.L; i++) sp.inv_Lambda[i] = (double)(1.0L / (long double)st.Lambda[i]);
 }
 
