@@ -65,6 +65,10 @@ typedef struct TjbHandle TjbHandle;
 /* ---- lifecycle -------------------------------------------------------- */
 /* replaces CJokerHelper.__init__ (pyx:125-253) */
 int tjb_create(const TjbSpec *spec, int device, TjbHandle **out);
+/* Replace the star (data + linear prior) of an existing handle; device buffers are
+ * reused.  For drivers that run many stars against one shared prior cache (the
+ * reference re-creates a CJokerHelper per star, thejoker.py:87-91). */
+int tjb_update_star(TjbHandle *h, const TjbSpec *spec);
 void tjb_destroy(TjbHandle *h);
 int tjb_set_stream(TjbHandle *h, void *cuda_stream);
 const char *tjb_last_error(void);

@@ -421,3 +421,83 @@ def test_large_n_properties(torch_cuda):
                                  (M0[: 1 << 20] - 2 * np.pi).contiguous())
     rel = ((ll3 - ll[: 1 << 20]).abs() / ll[: 1 << 20].abs()).max().item()
     assert rel < 1e-9
+
+
+def test_device_prior_sampling(torch_cuda):
+    """rejection_sample(data, prior_samples=<int>): the prior is drawn on the GPU
+    (SURVEY.md section 8 f2).  Distribution checks against the host sampler, determinism,
+    logprobs, and a jitter prior that is not constant."""
+    import thejoker_b200 as tj
+    from helpers import default_prior
+    from thejoker_b200 import units as u
+    from thejoker_b200.prior import LogNormal
+    from thejoker_b200.synthetic import make_data
+
+    prior = default_prior(1, sigma_K0=25.0, P_min=5.0, P_max=500.0)
+    cols, s, lp = prior.sample_device(400_000, "cuda:0", 1234, u.km / u.s, return_logprobs=True)
+    host = prior.sample(size=400_000, rng=np.random.default_rng(0), return_logprobs=True)
+    P, e = cols[0].cpu().numpy(), cols[1].cpu().numpy()
+    assert s == 0.0 and P.min() >= 5 and P.max() <= 500 and e.min() > 0 and e.max() < 1
+    for dev, hst in ((np.log(P), np.log(host["P"].value)), (e, host["e"].value),
+                     (cols[2].cpu().numpy(), host["omega"].value)):
+        q = [0.01, 0.1, 0.25, 0.5, 0.75, 0.9, 0.99]
+        assert np.allclose(np.quantile(dev, q), np.quantile(hst, q), rtol=0.03, atol=0.02)
+    # ln_prior on the device equals the host formula at the same points
+    dev_samples = tj.JokerSamples()
+    lp_host = (prior.pars["P"].logp(P) + prior.pars["e"].logp(e)
+               + prior.pars["omega"].logp(cols[2].cpu().numpy())
+               + prior.pars["M0"].logp(cols[3].cpu().numpy()))
+    assert np.allclose(lp.cpu().numpy(), lp_host, rtol=1e-12, atol=1e-12)
+
+    flat, _ = make_data(8, rng=np.random.default_rng(11), K=1e-4)
+    runs = []
+    for _ in range(2):
+        joker = tj.TheJoker(prior, rng=np.random.default_rng(5))
+        smp = joker.rejection_sample(flat, 1 << 18, max_posterior_samples=128,
+                                     return_logprobs=True)
+        runs.append(smp)
+        assert 10 < len(smp) <= 128 and np.isfinite(smp["ln_prior"].value).all()
+    assert np.array_equal(runs[0]["P"].value, runs[1]["P"].value)
+    assert np.array_equal(runs[0]["K"].value, runs[1]["K"].value)
+    # non-constant jitter prior, in m/s, through the per-sample-jitter kernel
+    prior_s = default_prior(1, sigma_K0=25.0, P_min=5.0, P_max=500.0,
+                            s=LogNormal("s", np.log(200.0), 0.5, u.m / u.s))
+    smp = tj.TheJoker(prior_s, rng=np.random.default_rng(5)).rejection_sample(flat, 1 << 16)
+    sv = smp["s"].to_value(u.km / u.s)
+    assert len(smp) > 10 and 0.02 < np.median(sv) < 2.0
+
+
+def test_multistar_driver_matches_per_star(torch_cuda):
+    """MultiStarJoker (BASELINE configs[4] in miniature): many
+    stars, ragged epoch counts, two surveys per star, one shared prior cache.  Each star
+    must reproduce TheJoker.rejection_sample run on it alone with the same child RNG."""
+    import thejoker_b200 as tj
+    from helpers import default_prior
+    from thejoker_b200 import units as u
+    from thejoker_b200.prior import Normal
+    from thejoker_b200.synthetic import make_noisy_data
+
+    rng = np.random.default_rng(3)
+    prior = default_prior(1, sigma_K0=25.0, P_min=2.0, P_max=1024.0,
+                          v0_offsets=[Normal("dv0_1", 0.0, 5.0, u.km / u.s)])
+    ps = prior.sample(size=1 << 16, rng=np.random.default_rng(1))
+    stars = []
+    for i in range(6):
+        n = int(np.clip(rng.poisson(20), 8, 40))
+        full, _ = make_noisy_data(n, seed=100 + i, K=[None, 1e-4][i % 2])
+        cut = int(rng.integers(3, n - 3))
+        stars.append([tj.RVData(full._t_bmjd[:cut], full.rv[:cut], full.rv_err[:cut]),
+                      tj.RVData(full._t_bmjd[cut:], (full.rv.value[cut:] + 3.0) * u.km / u.s,
+                                full.rv_err[cut:])])
+    ms = tj.MultiStarJoker(prior, ps, rng=np.random.default_rng(77), devices=[0])
+    out = ms.rejection_sample(stars, max_posterior_samples=64)
+    assert len(out) == 6
+    seqs = np.random.default_rng(77).bit_generator._seed_seq.spawn(6)
+    for i, star in enumerate(stars):
+        child = np.random.Generator(np.random.PCG64(seqs[i]))
+        ref = tj.TheJoker(prior, rng=child).rejection_sample(star, ps, in_memory=True,
+                                                             max_posterior_samples=64)
+        assert len(ref) == len(out[i]) > 0
+        for k in ("P", "e", "K", "v0", "dv0_1"):
+            assert np.array_equal(ref[k].value, out[i][k].value), (i, k)
+        assert ms.last_stats[i]["n_accepted"] >= len(out[i])

@@ -11,9 +11,11 @@ streams and torch.distributed only.  There is no CPU fallback.
 from . import units  # noqa: F401
 from .data import RVData  # noqa: F401
 from .helper import CJokerHelper, extract_spec  # noqa: F401
+from .multistar import MultiStarJoker  # noqa: F401
 from .prior import JokerPrior  # noqa: F401
 from .samples import JokerSamples  # noqa: F401
 from .thejoker import TheJoker  # noqa: F401
 
 __version__ = "0.1.0"
-__all__ = ["TheJoker", "RVData", "JokerPrior", "JokerSamples", "CJokerHelper", "units"]
+__all__ = ["TheJoker", "RVData", "JokerPrior", "JokerSamples", "CJokerHelper", "MultiStarJoker",
+           "units"]

@@ -53,6 +53,7 @@ _vp = ctypes.c_void_p
 _H = ctypes.c_void_p  # TjbHandle*
 SYMBOLS = {
     "tjb_create": (ctypes.c_int, [ctypes.POINTER(TjbSpec), ctypes.c_int, ctypes.POINTER(_H)]),
+    "tjb_update_star": (ctypes.c_int, [_H, ctypes.POINTER(TjbSpec)]),
     "tjb_destroy": (None, [_H]),
     "tjb_set_stream": (ctypes.c_int, [_H, _vp]),
     "tjb_last_error": (ctypes.c_char_p, []),

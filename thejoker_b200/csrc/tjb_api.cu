@@ -211,9 +211,8 @@ extern "C" {
 const char *tjb_last_error(void) { return g_err.c_str(); }
 int tjb_version(void) { return TJB_VERSION; }
 
-int tjb_create(const TjbSpec *spec, int device, TjbHandle **out) {
-  if (!spec || !out) return fail(TJB_E_INVALID, "null argument");
-  *out = nullptr;
+static int validate_spec(const TjbSpec *spec) {
+  if (!spec) return fail(TJB_E_INVALID, "null spec");
   if (spec->n_times < 1) return fail(TJB_E_INVALID, "n_times must be >= 1");
   if (spec->n_linear < 1 || spec->n_linear > TJB_MAX_LINEAR)
     return fail(TJB_E_INVALID, "n_linear must be in 1..8");
@@ -221,6 +220,39 @@ int tjb_create(const TjbSpec *spec, int device, TjbHandle **out) {
     return fail(TJB_E_INVALID, "null data array");
   if (spec->K_prior_kind != 0 && spec->K_prior_kind != 1)
     return fail(TJB_E_INVALID, "K_prior_kind must be 0 or 1");
+  return TJB_OK;
+}
+
+static int load_star(TjbHandle *h, const TjbSpec *spec) {
+  const int N = h->N = spec->n_times, L = h->L = spec->n_linear;
+  StarHost &st = h->star;
+  st.N = N;
+  st.L = L;
+  st.t_ref = spec->t_ref;
+  st.t.assign(spec->t, spec->t + N);
+  st.rv.assign(spec->rv, spec->rv + N);
+  st.ivar.assign(spec->ivar, spec->ivar + N);
+  st.trend.clear();
+  if (L > 1) st.trend.assign(spec->trend_M, spec->trend_M + (size_t)N * (L - 1));
+  memcpy(st.mu, spec->mu, sizeof(st.mu));
+  memcpy(st.Lambda, spec->Lambda, sizeof(st.Lambda));
+  st.K_prior_kind = spec->K_prior_kind;
+  st.jitter_mode = h->jitter_mode = spec->jitter_mode ? 1 : 0;
+  st.sigma_K0 = spec->sigma_K0;
+  st.P0 = spec->P0;
+  st.max_K = spec->max_K;
+  star_prepare(st);
+  h->const_valid = false;
+  int rc = build_jit_table(h);
+  if (rc == TJB_OK) rc = build_const_table(h, 0.0);
+  return rc;
+}
+
+int tjb_create(const TjbSpec *spec, int device, TjbHandle **out) {
+  if (!out) return fail(TJB_E_INVALID, "null argument");
+  *out = nullptr;
+  int rc = validate_spec(spec);
+  if (rc) return rc;
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1)
     return fail(TJB_E_CUDA, "no CUDA device available: libthejoker_b200 has no CPU path");
@@ -236,32 +268,22 @@ int tjb_create(const TjbSpec *spec, int device, TjbHandle **out) {
   h->n_sm = prop.multiProcessorCount;
   h->cc_major = prop.major;
   h->cc_minor = prop.minor;
-  const int N = h->N = spec->n_times, L = h->L = spec->n_linear;
-  StarHost &st = h->star;
-  st.N = N;
-  st.L = L;
-  st.t_ref = spec->t_ref;
-  st.t.assign(spec->t, spec->t + N);
-  st.rv.assign(spec->rv, spec->rv + N);
-  st.ivar.assign(spec->ivar, spec->ivar + N);
-  if (L > 1) st.trend.assign(spec->trend_M, spec->trend_M + (size_t)N * (L - 1));
-  memcpy(st.mu, spec->mu, sizeof(st.mu));
-  memcpy(st.Lambda, spec->Lambda, sizeof(st.Lambda));
-  st.K_prior_kind = spec->K_prior_kind;
-  st.jitter_mode = h->jitter_mode = spec->jitter_mode ? 1 : 0;
-  st.sigma_K0 = spec->sigma_K0;
-  st.P0 = spec->P0;
-  st.max_K = spec->max_K;
-  star_prepare(st);
-
-  int rc = build_jit_table(h);
-  if (rc == TJB_OK) rc = build_const_table(h, 0.0);
+  rc = load_star(h, spec);
   if (rc != TJB_OK) {
     tjb_destroy(h);
     return rc;
   }
   *out = h;
   return TJB_OK;
+}
+
+int tjb_update_star(TjbHandle *h, const TjbSpec *spec) {
+  if (!h) return fail(TJB_E_INVALID, "null handle");
+  int rc = validate_spec(spec);
+  if (rc) return rc;
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));  // kernels in flight still read the old tables
+  return load_star(h, spec);
 }
 
 void tjb_destroy(TjbHandle *h) {

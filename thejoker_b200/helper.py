@@ -191,7 +191,12 @@ class CJokerHelper:
         self.device = int(device)
 
         lib = self._lib = _lib.load()
-        sp = self.spec
+        h = ctypes.c_void_p()
+        _lib.check(lib.tjb_create(ctypes.byref(self._c_spec(self.spec)), self.device, ctypes.byref(h)))
+        self._h = h
+
+    @staticmethod
+    def _c_spec(sp):
         cs = _lib.TjbSpec()
         cs.n_times, cs.n_linear, cs.t_ref = sp["n_times"], sp["n_linear"], float(sp["t0"])
         dp = ctypes.POINTER(ctypes.c_double)
@@ -203,9 +208,19 @@ class CJokerHelper:
         cs.sigma_K0, cs.P0 = float(sp["sigma_K0"]), float(sp["P0"])
         cs.max_K = float(sp["max_K"]) if np.isfinite(sp["max_K"]) else 1e300
         cs.jitter_mode = sp["jitter_mode"]
-        h = ctypes.c_void_p()
-        _lib.check(lib.tjb_create(ctypes.byref(cs), self.device, ctypes.byref(h)))
-        self._h = h
+        return cs
+
+    def update_star(self, data, prior, trend_M):
+        """Point this helper (and its device buffers) at another star: the multi-star
+        replacement for constructing a new CJokerHelper per star (thejoker.py:87-91)."""
+        self.prior, self.data = prior, data
+        self._trend_M = np.ascontiguousarray(trend_M, dtype=np.float64)
+        spec = extract_spec(data, prior, self._trend_M, self._jitter_mode)
+        self.spec = spec
+        self.internal_units = spec["internal_units"]
+        self.n_times, self.n_linear, self.n_pars = spec["n_times"], spec["n_linear"], spec["n_pars"]
+        self.a = self.A = self.b = None
+        _lib.check(self._lib.tjb_update_star(self._h, ctypes.byref(self._c_spec(spec))))
 
     def __del__(self):
         h = getattr(self, "_h", None)

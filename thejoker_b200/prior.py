@@ -37,6 +37,13 @@ class Distribution:
     def logp(self, value, **ctx):
         raise NotImplementedError
 
+    # device-side counterparts (torch CUDA generator); None -> not supported on device
+    def draw_device(self, gen, size, device):
+        return None
+
+    def logp_device(self, value):
+        return None
+
 
 class Normal(Distribution):
     """Independent Normal prior (the only kind allowed on linear parameters,
@@ -105,6 +112,18 @@ class UniformLog(Distribution):
         fac = np.log(self.b) - np.log(self.a)
         return np.exp(rng.uniform(size=size) * fac + np.log(self.a))  # distributions.py:25-28
 
+    def draw_device(self, gen, size, device):
+        import torch
+
+        fac = np.log(self.b) - np.log(self.a)
+        uu = torch.rand(size, dtype=torch.float64, device=device, generator=gen)
+        return torch.exp(uu * fac + np.log(self.a))
+
+    def logp_device(self, value):
+        import torch
+
+        return -torch.log(value) - np.log(np.log(self.b) - np.log(self.a))
+
     def logp(self, value, **ctx):
         # normalised density of 1/x on (a,b).  (distributions.py:44-46 writes
         # ``-value - log(fac)``, missing the log; the density form is used here.)
@@ -118,6 +137,17 @@ class Uniform(Distribution):
 
     def draw(self, rng, size, **ctx):
         return rng.uniform(self.lower, self.upper, size=size)
+
+    def draw_device(self, gen, size, device):
+        import torch
+
+        uu = torch.rand(size, dtype=torch.float64, device=device, generator=gen)
+        return uu * (self.upper - self.lower) + self.lower
+
+    def logp_device(self, value):
+        import torch
+
+        return torch.full_like(value, -np.log(self.upper - self.lower))
 
     def logp(self, value, **ctx):
         return np.full(np.shape(value), -np.log(self.upper - self.lower))
@@ -138,6 +168,25 @@ class Beta(Distribution):
 
     def draw(self, rng, size, **ctx):
         return rng.beta(self.alpha, self.beta, size=size)
+
+    def draw_device(self, gen, size, device):
+        import torch
+
+        # Beta(a, b) = Ga / (Ga + Gb); torch's CUDA gamma sampler has no generator
+        # argument, so it is driven by a seed drawn from `gen`
+        seed = int(torch.randint(0, 2**62, (1,), device=device, generator=gen).item())
+        with torch.random.fork_rng(devices=[torch.device(device)]):
+            torch.manual_seed(seed)
+            ga = torch._standard_gamma(torch.full((size,), self.alpha, dtype=torch.float64, device=device))
+            gb = torch._standard_gamma(torch.full((size,), self.beta, dtype=torch.float64, device=device))
+        return (ga / (ga + gb)).clamp_(1e-300, 1.0 - 1e-16)
+
+    def logp_device(self, value):
+        import torch
+        from math import lgamma
+
+        lB = lgamma(self.alpha) + lgamma(self.beta) - lgamma(self.alpha + self.beta)
+        return (self.alpha - 1) * torch.log(value) + (self.beta - 1) * torch.log1p(-value) - lB
 
     def logp(self, value, **ctx):
         from math import lgamma
@@ -170,6 +219,12 @@ class Constant(Distribution):
     def draw(self, rng, size, **ctx):
         return np.full(size, self.value)
 
+    def draw_device(self, gen, size, device):
+        return self.value  # a scalar: the engine folds a constant jitter into the epoch table
+
+    def logp_device(self, value):
+        return 0.0
+
     def logp(self, value, **ctx):
         return np.zeros(np.shape(value))
 
@@ -183,6 +238,18 @@ class LogNormal(Distribution):
 
     def draw(self, rng, size, **ctx):
         return np.exp(rng.normal(self.mu, self.sigma, size=size))
+
+    def draw_device(self, gen, size, device):
+        import torch
+
+        z = torch.randn(size, dtype=torch.float64, device=device, generator=gen)
+        return torch.exp(z * self.sigma + self.mu)
+
+    def logp_device(self, value):
+        import torch
+
+        lv = torch.log(value)
+        return -lv - 0.5 * (np.log(2 * np.pi * self.sigma**2) + ((lv - self.mu) / self.sigma) ** 2)
 
     def logp(self, value, **ctx):
         lv = np.log(value)
@@ -383,6 +450,35 @@ class JokerPrior:
 
     def __str__(self):
         return ", ".join(self.par_names)
+
+    def sample_device(self, size, device, seed, rv_unit, return_logprobs=False):
+        """Draw the nonlinear parameters on a GPU: returns
+        ``([P, e, omega, M0] float64 CUDA tensors in [day, -, rad, rad], s, ln_prior)``
+        where ``s`` is a tensor in ``rv_unit`` or a python float for a constant jitter and
+        ``ln_prior`` is a tensor or None.  Returns None if a distribution has no device
+        sampler (the caller then samples on the host).  Streams come from torch's Philox
+        generator seeded with ``seed``; like the reference's pm.draw path this is not
+        stream-compatible with numpy, the distributions are the same."""
+        import torch
+
+        gen = torch.Generator(device=device).manual_seed(int(seed))
+        out, logp = {}, None
+        for name in ("P", "e", "omega", "M0", "s"):
+            p = self.pars[name]
+            v = p.draw_device(gen, int(size), device)
+            if v is None:
+                return None
+            if return_logprobs:
+                lp = p.logp_device(v)
+                if lp is None:
+                    return None
+                logp = lp if logp is None else logp + lp
+            to = {"P": u.day, "e": u.one, "omega": u.rad, "M0": u.rad, "s": rv_unit}[name]
+            f = float(p.unit.to(to))
+            out[name] = v * f if f != 1.0 else v
+        if return_logprobs and not hasattr(logp, "shape"):
+            logp = torch.full((int(size),), float(logp), dtype=torch.float64, device=device)
+        return [out["P"], out["e"], out["omega"], out["M0"]], out["s"], logp
 
     def sample(self, size=1, generate_linear=False, return_logprobs=False, rng=None, dtype=None,
                **kwargs):

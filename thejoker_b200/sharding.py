@@ -127,17 +127,60 @@ class DeviceEngine:
             s_is_scalar, self.s_const = True, float(s[0])
         self.shards = []
         for d, (lo, hi) in zip(devices, shard_ranges(n_local, len(devices))):
-            sh = _Shard()
-            sh.device, sh.lo, sh.hi = d, lo, hi
-            sh.helper = make_helper(d)
             with torch.cuda.device(d):
                 up = lambda a: torch.from_numpy(np.ascontiguousarray(a[lo:hi], dtype=np.float64)) \
                     .to(f"cuda:{d}", non_blocking=False)
-                sh.cols = [up(P), up(e), up(om), up(M0)]
-                sh.s = None if s_is_scalar else up(s)
-                sh.ll = torch.full((hi - lo,), float("nan"), dtype=torch.float64, device=f"cuda:{d}")
-                sh.key = sh.helper.new_llmax_key()
-            self.shards.append(sh)
+                cols = [up(P), up(e), up(om), up(M0)]
+                s_dev = None if s_is_scalar else up(s)
+            self._add_shard(make_helper, d, lo, hi, cols, s_dev)
+
+    def _add_shard(self, make_helper, d, lo, hi, cols, s_dev):
+        torch = self.torch
+        sh = _Shard()
+        sh.device, sh.lo, sh.hi = d, lo, hi
+        sh.helper = make_helper(d)
+        sh.cols, sh.s = cols, s_dev
+        with torch.cuda.device(d):
+            sh.ll = torch.full((hi - lo,), float("nan"), dtype=torch.float64, device=f"cuda:{d}")
+            sh.key = sh.helper.new_llmax_key()
+        self.shards.append(sh)
+
+    @classmethod
+    def from_device_columns(cls, make_helper, shards, s_const=0.0, group=None, global_offset=0,
+                            global_size=None):
+        """Engine over prior columns that already live on the GPUs.  ``shards`` is a list
+        of ``(device, [P, e, omega, M0] float64 CUDA tensors, s tensor or None)`` in
+        index order; nothing is copied."""
+        import torch
+
+        self = cls.__new__(cls)
+        self.torch, self.group = torch, group
+        self.s_const = float(s_const)
+        self.shards = []
+        lo = 0
+        for d, cols, s_dev in shards:
+            hi = lo + cols[0].numel()
+            self._add_shard(make_helper, d, lo, hi, [c.contiguous() for c in cols], s_dev)
+            lo = hi
+        self.n_local = lo
+        self.global_offset = int(global_offset)
+        self.n_global = int(lo if global_size is None else global_size)
+        return self
+
+    def rows(self, local_idx):
+        """Packed (k, 5) host rows [P, e, omega, M0, s] for local sample indices."""
+        torch = self.torch
+        local_idx = np.asarray(local_idx, dtype=np.int64)
+        out = np.empty((len(local_idx), 5))
+        for sh in self.shards:
+            m = (local_idx >= sh.lo) & (local_idx < sh.hi)
+            if not m.any():
+                continue
+            ii = torch.from_numpy(local_idx[m] - sh.lo).to(sh.cols[0].device)
+            for j, c in enumerate(sh.cols):
+                out[m, j] = c.index_select(0, ii).cpu().numpy()
+            out[m, 4] = self.s_const if sh.s is None else sh.s.index_select(0, ii).cpu().numpy()
+        return out
 
     # -- likelihood -----------------------------------------------------------
     def compute_ll(self, lo=0, hi=None):
