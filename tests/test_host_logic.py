@@ -311,3 +311,60 @@ def test_ll_key_order():
     ks = [lib.emu_ll_to_key(x) for x in xs]
     assert ks == sorted(ks) and all(lib.emu_key_to_ll(k) == x for k, x in zip(ks, xs))
     assert lib.emu_ll_to_key(np.nan) > lib.emu_ll_to_key(np.inf)
+
+
+def test_samples_analysis():
+    """thejoker/tests/test_samples_analysis.py in miniature."""
+    from thejoker_b200 import samples_analysis as sa
+
+    data, _ = make_data(30, rng=np.random.default_rng(0))
+    s = tj.JokerSamples()
+    s["P"] = np.array([51.8, 51.81, 51.79]) * u.day
+    s["ln_prior"] = np.array([0.0, 0.0, 0.0])
+    s["ln_likelihood"] = np.array([-3.0, -1.0, -2.0])
+    best, idx = sa.MAP_sample(s, return_index=True)
+    assert idx == 1 and best["P"].value[0] == 51.81
+    assert sa.is_P_unimodal(s, data)
+    wide = tj.JokerSamples()
+    wide["P"] = np.array([20.0, 51.8, 300.0]) * u.day
+    assert not sa.is_P_unimodal(wide, data)
+    two = tj.JokerSamples()
+    two["P"] = np.concatenate([np.full(5, 51.8) + 1e-3 * np.arange(5),
+                               np.full(4, 103.6) + 1e-3 * np.arange(4)]) * u.day
+    ok, reps, counts = sa.is_P_Kmodal(two, data, n_clusters=2)
+    assert ok and sorted(counts) == [4, 5] and np.allclose(sorted(reps.value), [51.8, 103.6], atol=0.1)
+    one = s[0]
+    assert 0 < sa.max_phase_gap(one, data) < 1 and 0 < sa.phase_coverage(one, data) <= 1
+    assert np.isclose(sa.periods_spanned(one, data), np.ptp(data._t_bmjd) / 51.8)
+    assert sa.phase_coverage_per_period(one, data) >= 1
+    with pytest.raises(ValueError):
+        sa.MAP_sample(wide)
+
+
+def test_prior_cache_roundtrip(tmp_path):
+    """Native SoA prior cache (section 8 f1): units converted once, constant jitter stored
+    as a scalar, memory-mapped shards."""
+    from thejoker_b200.cache import PriorCache, read_reference_hdf5, write_prior_cache
+
+    prior = default_prior(1)
+    s = prior.sample(size=1000, rng=np.random.default_rng(0), return_logprobs=True)
+    path = write_prior_cache(s, str(tmp_path / "cache"))
+    c = PriorCache(path)
+    assert len(c) == 1000 and c.s_const == 0.0 and c.has_ln_prior
+    cols = c.columns(lo=100, hi=200)
+    assert np.array_equal(cols[0], s["P"].to_value(u.day)[100:200]) and cols[4] == 0.0
+    back = c.to_samples()
+    assert np.array_equal(back["e"].value, s["e"].value) and back._uniform_s
+    from thejoker_b200.prior import LogNormal
+    prior_s = default_prior(1, s=LogNormal("s", 0.0, 1.0, u.m / u.s))
+    s2 = prior_s.sample(size=50, rng=np.random.default_rng(0))
+    c2 = PriorCache(write_prior_cache(s2, str(tmp_path / "cache2"), rv_unit=u.km / u.s))
+    assert c2.s_const is None
+    assert np.allclose(c2.columns(rv_unit=u.m / u.s)[4], s2["s"].to_value(u.m / u.s))
+    with pytest.raises(OSError):
+        write_prior_cache(s, path)
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            read_reference_hdf5("nope.hdf5")

@@ -1,0 +1,142 @@
+"""Prior-cache storage.
+
+The reference keeps the prior cache in an HDF5 file written by ``JokerSamples.write``
+(dataset ``samples`` of compound rows = AoS, units in a YAML header;
+thejoker/samples.py:480-545, samples_helpers.py:35-272) and every pool worker re-reads
+its slice with PyTables, converts units column by column and packs an (n, 5) array
+(thejoker/utils.py:106-198) -- at 2^28 samples that path is I/O bound.
+
+Native format here: a directory with one little-endian float64 ``.npy`` file per column
+(SoA, exactly the layout the GPU kernel reads) already converted to the internal units
+[day, -, rad, rad, rv-unit], plus ``meta.json``.  Columns are memory-mapped, so a shard
+``[lo, hi)`` is read straight from the page cache / disk into the device upload without
+touching the rest of the file, and a constant jitter column is stored as a scalar.
+
+``read_reference_hdf5`` reads the reference's own HDF5 layout when ``h5py`` is
+importable (it is not in the build image, so that function is import-gated).
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+
+from . import units as u
+from .samples import JokerSamples
+
+__all__ = ["write_prior_cache", "PriorCache", "read_reference_hdf5"]
+
+_COLS = ("P", "e", "omega", "M0", "s")
+_INTERNAL = {"P": u.day, "e": u.one, "omega": u.rad, "M0": u.rad}
+
+
+def write_prior_cache(samples: JokerSamples, path: str, rv_unit=None, overwrite=False):
+    """Store prior samples as a native SoA cache directory."""
+    rv_unit = u.as_unit(u.km / u.s if rv_unit is None else rv_unit)
+    if os.path.exists(path):
+        if not overwrite:
+            raise OSError(f"{path} exists: use overwrite=True")
+    os.makedirs(path, exist_ok=True)
+    n = len(samples)
+    meta = {"n": n, "rv_unit_scale": rv_unit.scale, "rv_unit_dims": list(rv_unit.dims),
+            "poly_trend": samples.poly_trend, "n_offsets": samples.n_offsets, "columns": [],
+            "s_const": None}
+    for name in _COLS:
+        unit = _INTERNAL.get(name, rv_unit)
+        col = np.ascontiguousarray(samples[name].to_value(unit), dtype="<f8")
+        if name == "s" and n and np.all(col == col[0]):
+            meta["s_const"] = float(col[0])
+            continue
+        np.save(os.path.join(path, f"{name}.npy"), col)
+        meta["columns"].append(name)
+    if "ln_prior" in samples:
+        np.save(os.path.join(path, "ln_prior.npy"),
+                np.ascontiguousarray(samples["ln_prior"].value, dtype="<f8"))
+        meta["columns"].append("ln_prior")
+    with open(os.path.join(path, "meta.json"), "w") as f:
+        json.dump(meta, f)
+    return path
+
+
+class PriorCache:
+    """Memory-mapped view of a native prior cache."""
+
+    def __init__(self, path):
+        self.path = path
+        with open(os.path.join(path, "meta.json")) as f:
+            self.meta = json.load(f)
+        self.n = int(self.meta["n"])
+        self.rv_unit = u.Unit(tuple(self.meta["rv_unit_dims"]), self.meta["rv_unit_scale"])
+        self._mm = {c: np.load(os.path.join(path, f"{c}.npy"), mmap_mode="r")
+                    for c in self.meta["columns"]}
+        self.s_const = self.meta.get("s_const")
+
+    def __len__(self):
+        return self.n
+
+    @property
+    def has_ln_prior(self):
+        return "ln_prior" in self._mm
+
+    def columns(self, rv_unit=None, lo=0, hi=None):
+        """[P, e, omega, M0, s] for rows [lo, hi) in internal units; ``s`` is a python
+        float when the cache holds a constant jitter."""
+        hi = self.n if hi is None else hi
+        f = 1.0 if rv_unit is None else float(self.rv_unit.to(u.as_unit(rv_unit)))
+        cols = [self._mm[c][lo:hi] for c in _COLS[:4]]
+        if self.s_const is not None:
+            s = self.s_const * f
+        else:
+            s = self._mm["s"][lo:hi]
+            s = s * f if f != 1.0 else s
+        return cols + [s]
+
+    def ln_prior(self, idx=None):
+        lp = self._mm["ln_prior"]
+        return np.asarray(lp if idx is None else lp[np.asarray(idx)])
+
+    def to_samples(self, lo=0, hi=None):
+        hi = self.n if hi is None else hi
+        out = JokerSamples(poly_trend=self.meta["poly_trend"], n_offsets=self.meta["n_offsets"])
+        cols = self.columns(lo=lo, hi=hi)
+        for name, c in zip(_COLS, cols):
+            unit = _INTERNAL.get(name, self.rv_unit)
+            out[name] = u.Quantity(np.full(hi - lo, c) if np.ndim(c) == 0 else np.array(c), unit)
+        if self.s_const is not None:
+            out._uniform_s = True
+        if self.has_ln_prior:
+            out["ln_prior"] = np.array(self._mm["ln_prior"][lo:hi])
+        return out
+
+
+def read_reference_hdf5(filename):
+    """JokerSamples from a file written by the reference's ``JokerSamples.write``
+    (HDF5 dataset ``samples``; column units in the YAML header stored next to it,
+    thejoker/samples.py:480-545, utils.py:75-103).  Needs h5py."""
+    try:
+        import h5py
+    except ImportError as e:  # pragma: no cover - h5py is absent from the build image
+        raise ImportError("reading the reference's HDF5 prior cache needs h5py; convert it "
+                          "once with thejoker_b200.cache.write_prior_cache on a machine that "
+                          "has it") from e
+    import re
+
+    with h5py.File(filename, "r") as f:  # pragma: no cover
+        data = f[JokerSamples._hdf5_path][()]
+        header = "\n".join(h.decode("utf-8") for h in
+                           f[JokerSamples._hdf5_path + ".__table_column_meta__"][()])
+    units, name = {}, None  # pragma: no cover
+    for line in header.splitlines():  # pragma: no cover
+        m = re.match(r"\s*-?\s*\{?\s*name:\s*([\w]+)", line)
+        if m:
+            name = m.group(1)
+        m = re.search(r"unit:\s*([^,}\n]+)", line)
+        if m and name:
+            units[name] = m.group(1).strip()
+    out = JokerSamples()  # pragma: no cover
+    for col in data.dtype.names:  # pragma: no cover
+        if col in out._valid_units:
+            unit = u.as_unit(units.get(col, ""))
+            out[col] = u.Quantity(np.asarray(data[col], dtype=np.float64), unit)
+    return out  # pragma: no cover

@@ -99,7 +99,18 @@ class TheJoker:
     def _columns(self, helper, prior_samples):
         """[P, e, omega, M0, s] host columns in internal units + optional ln_prior."""
         if isinstance(prior_samples, str):
-            prior_samples = JokerSamples.read(prior_samples)
+            from .cache import PriorCache, read_reference_hdf5
+
+            if os.path.isdir(prior_samples):
+                prior_samples = PriorCache(prior_samples)
+            elif prior_samples.endswith((".hdf5", ".h5")):
+                prior_samples = read_reference_hdf5(prior_samples)
+            else:
+                prior_samples = JokerSamples.read(prior_samples)
+        if type(prior_samples).__name__ == "PriorCache":
+            cols = prior_samples.columns(rv_unit=helper.internal_units["s"])
+            ln_prior = prior_samples.ln_prior() if prior_samples.has_ln_prior else None
+            return cols, ln_prior
         if isinstance(prior_samples, JokerSamples):
             cols = prior_samples.columns(units=helper.internal_units, names=helper.packed_order)
             if prior_samples._uniform_s and len(cols[4]):
