@@ -316,10 +316,10 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
     sincos_quarter(tc, w, lo32(tv), sE[k], cE[k]);
     D[k] = d4 * TJB_MC(4);  // E0 - M [rad]
     del[k] = householder3(oc, D[k], sE[k], cE[k]);
-    D[k] += del[k];
     // error map of the step: eps -> ~C eps^4 (tools/kepler_solver_study.py); a lane
-    // that moved by more than 1e-4 takes further passes
-    need[k] = !(fabs(del[k]) <= TJB_MC(2));
+    // that moved by 2^-13 (1.2e-4) or more, or produced a NaN, takes further passes.
+    // The test reads the exponent field on the integer pipe instead of a DSETP.
+    need[k] = (unsigned)(hi32(del[k]) & 0x7fffffff) >= 0x3f200000u;
     any_need = any_need || need[k];
   }
   if (!any_lane(any_need)) {
@@ -335,7 +335,7 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
       double sR = sE[k], cR = cE[k];
       rotate_small(tc, del[k], sR, cR);
       bool nd = need[k];
-      double Dk = D[k];
+      double Dk = D[k] + del[k];
       for (int it = 1; it < kF64MaxIter && any_lane(nd); ++it) {
         const double v2 = fma(Dk, TJB_MC(3), x4[k]);
         const double tv2 = v2 + kMagic;
@@ -345,7 +345,7 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
         if (nd) {
           if (kCountStats) st->extra_f64++;
           Dk += d2;
-          if (fabs(d2) <= TJB_MC(2)) {
+          if ((unsigned)(hi32(d2) & 0x7fffffff) < 0x3f200000u) {
             rotate_small(tc, d2, s2, c2);
             sR = s2;
             cR = c2;

@@ -1,0 +1,41 @@
+"""Small end-to-end pass over every kernel, for compute-sanitizer (memcheck / racecheck /
+initcheck) on the GPU box:  compute-sanitizer --tool memcheck python tools/sanitize_smoke.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import thejoker_b200 as tj  # noqa: E402
+from helpers import default_prior, prior_chunk, star_spec  # noqa: E402
+from thejoker_b200.synthetic import make_data  # noqa: E402
+
+for N, pt, kw in ((7, 1, {}), (16, 2, {"n_surveys": 2}), (33, 3, {})):
+    spec, data, prior = star_spec(N, pt, **kw)
+    helper = tj.CJokerHelper.from_spec(spec, device=0)
+    for n, sl in ((1, None), (1000, None), (4097, (-2.0, 1.0))):
+        chunk = prior_chunk(n, s_lognormal=sl)
+        ll = helper.batch_marginal_ln_likelihood(chunk)
+        assert np.isfinite(ll).all()
+        dev = torch.from_numpy(chunk).cuda()
+        key = helper.new_llmax_key()
+        out = helper.marginal_ll_aos(dev, uniform_s=sl is None, llmax_key=key)
+        rng = np.random.default_rng(1)
+        idx, tot, near = helper.accept(out, key, rng=rng, max_keep=50)
+        uu = torch.rand(n, dtype=torch.float64, device="cuda")
+        idx2, tot2, _ = helper.accept(out, key, uniforms=uu)
+        helper.posterior_aA(chunk[:5])
+        helper.batch_get_posterior_samples(chunk[:3], 2, rng)
+        helper.design_column(chunk[0])
+    helper.pcg64_uniform(np.random.default_rng(0), 100_001, offset=17)
+prior = default_prior(1, sigma_K0=25.0, P_min=5.0, P_max=500.0)
+flat, _ = make_data(8, rng=np.random.default_rng(11), K=1e-4)
+ps = prior.sample(size=20_000, return_logprobs=True, rng=np.random.default_rng(1))
+joker = tj.TheJoker(prior, rng=np.random.default_rng(42))
+joker.rejection_sample(flat, ps, in_memory=True)
+joker.iterative_rejection_sample(flat, ps, n_requested_samples=8, in_memory=True, growth_factor=16)
+joker.rejection_sample(flat, 30_000)
+print("sanitize smoke ok")
