@@ -139,6 +139,13 @@ int tjb_posterior_draw(TjbHandle *h, const double *h_rows, int64_t k, int n_per,
  * extra FP32 steps, extra FP64 steps, non-converged epochs of the solver. */
 int tjb_design_column(TjbHandle *h, const double *h_row, double *h_z, int32_t *h_stats);
 
+/* Solver statistics accumulated by every likelihood launch of this handle since the
+ * last reset: h_stats[0] = extra FP64 Householder passes (lane-epochs that needed more
+ * than one; high eccentricity near pericentre), h_stats[1] = epochs that did not
+ * converge within the iteration cap (their ll is still finite, counted for reporting),
+ * h_stats[2..3] reserved.  Synchronises the handle's streams. */
+int tjb_get_stats(TjbHandle *h, uint64_t *h_stats, int reset);
+
 /* ---- measurement helper: FP64 FMA-chain peak of the device, TFLOP/s ---- */
 int tjb_fp64_peak(TjbHandle *h, int iters, double *h_tflops, double *h_ms);
 

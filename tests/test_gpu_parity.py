@@ -501,3 +501,66 @@ def test_multistar_driver_matches_per_star(torch_cuda):
         for k in ("P", "e", "K", "v0", "dv0_1"):
             assert np.array_equal(ref[k].value, out[i][k].value), (i, k)
         assert ms.last_stats[i]["n_accepted"] >= len(out[i])
+
+
+def test_edge_cases(torch_cuda, oracle_lib):
+    """many epochs (shared-memory opt-in above 48 KB), too many
+    epochs (error, not a crash), e = 0, tiny and huge periods, solver statistics."""
+    import thejoker_b200 as tj
+    from thejoker_b200 import _lib
+
+    # N = 2000 epochs: 64 KB epoch table
+    spec, _, _ = star_spec(2000, 1)
+    helper = tj.CJokerHelper.from_spec(spec, device=0)
+    chunk = prior_chunk(512)
+    ll = helper.batch_marginal_ln_likelihood(chunk)
+    truth, _ = oracle_lib.OracleHelper.from_spec(spec).truth_ll(chunk[:64])
+    assert np.max(rel_err(ll[:64], truth)) < 1e-10
+    # N = 8000: 256 KB > 227 KB of shared memory -> a clean error
+    spec_big, _, _ = star_spec(8000, 1)
+    big = tj.CJokerHelper.from_spec(spec_big, device=0)
+    with pytest.raises(_lib.TjbError):
+        big.batch_marginal_ln_likelihood(chunk)
+    # circular orbits, extreme periods, extreme eccentricities
+    helper, spec, _, _ = make_helper((32, 1))
+    orc = oracle_lib.OracleHelper.from_spec(spec)
+    odd = prior_chunk(64)
+    odd[:16, 1] = 0.0
+    odd[16:24, 0] = 0.05       # 3000 cycles over the baseline
+    odd[24:32, 0] = 1e6        # a sliver of one orbit
+    odd[32:48, 1] = np.linspace(0.95, 0.9995, 16)
+    helper.solver_stats(reset=True)
+    ll = helper.batch_marginal_ln_likelihood(odd)
+    truth, _ = orc.truth_ll(odd)
+    assert np.isfinite(ll).all()
+    assert np.max(rel_err(ll, truth)) < 1e-9
+    st = helper.solver_stats()
+    assert st["not_converged"] == 0 and st["extra_fp64_passes"] > 0
+    # invalid elements give NaN, like the reference's arithmetic would, never a hang
+    bad = prior_chunk(40)
+    bad[3, 1] = 1.2
+    bad[5, 0] = -3.0
+    bad[7, 0] = np.nan
+    out = helper.batch_marginal_ln_likelihood(bad)
+    assert np.isnan(out[3]) and np.isnan(out[7]) and np.isfinite(np.delete(out, [3, 5, 7])).all()
+
+
+def test_prior_cache_path(torch_cuda, tmp_path):
+    """rejection_sample(data, "<cache dir>"): the file path of the reference
+    (thejoker.py:243-255) on the native SoA cache."""
+    import thejoker_b200 as tj
+    from helpers import default_prior
+    from thejoker_b200.cache import write_prior_cache
+    from thejoker_b200.synthetic import make_data
+
+    prior = default_prior(1, sigma_K0=25.0, P_min=5.0, P_max=500.0)
+    flat, _ = make_data(8, rng=np.random.default_rng(11), K=1e-4)
+    ps = prior.sample(size=30_000, return_logprobs=True, rng=np.random.default_rng(1))
+    path = write_prior_cache(ps, str(tmp_path / "cache"))
+    a = tj.TheJoker(prior, rng=np.random.default_rng(4)).rejection_sample(
+        flat, ps, return_logprobs=True, n_prior_samples=20_000)
+    b = tj.TheJoker(prior, rng=np.random.default_rng(4)).rejection_sample(
+        flat, path, return_logprobs=True, n_prior_samples=20_000)
+    assert len(a) == len(b) > 10
+    for k in ("P", "K", "ln_prior", "ln_likelihood"):
+        assert np.array_equal(a[k].value, b[k].value)

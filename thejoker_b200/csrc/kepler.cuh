@@ -18,8 +18,8 @@
 //  * one third-order Householder step in FP64 takes the FP32 estimate
 //    (error ~1e-6) to below 1e-20; sin E / cos E are carried through the step
 //    by an angle-addition update, so only one full double sincos is evaluated;
-//  * polynomial coefficients live in __constant__ memory and are consumed as
-//    constant-bank operands of DFMA (no register moves in the loop);
+//  * polynomial coefficients are pinned in registers for the whole epoch loop (ptxas
+//    otherwise re-loads or re-materialises them every epoch; TJB_COEF_MODE below);
 //  * z is formed without atan2:  cos f = (cosE - e)/(1 - e cosE),
 //    sin f = sqrt(1-e^2) sinE/(1 - e cosE);
 //  * the FP64 step is closed by a warp-uniform convergence test (|delta|), so
@@ -246,6 +246,16 @@ struct SolveStats {
 // more than 1e-4 (kMisc[2]), at most kF64MaxIter times.
 constexpr int kF64MaxIter = 16;
 
+// run-wide solver statistics (device counters, touched only on the rare path):
+// [0] extra FP64 passes (lane-epochs), [1] epochs that hit kF64MaxIter
+TJB_HD void count_event(unsigned long long *gstats, int which) {
+#if defined(__CUDA_ARCH__)
+  if (gstats) atomicAdd(gstats + which, 1ULL);
+#else
+  if (gstats) gstats[which]++;
+#endif
+}
+
 // One third-order Householder step from (D, sE, cE): returns delta.
 //   f = D - e sinE, f1 = 1 - e cosE, f2 = e sinE, f3 = e cosE
 //   u = -f/f1, t = f2/f1, b6 = f3/(6 f1), delta = u (1 + u (-t/2 + u (t^2/2 - b6)))
@@ -277,7 +287,7 @@ TJB_HD void rotate_small(const TrigCoef &tc, double del, double &sE, double &cE)
 // on its warp-mates): lanes that need extra passes iterate under a per-lane flag.
 template <int K, bool kCountStats>
 TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const double *dt, double *z,
-                            SolveStats *st) {
+                            SolveStats *st, unsigned long long *gstats = nullptr) {
   double x4[K], D[K], sE[K], cE[K];
   float Df[K];
 
@@ -344,6 +354,7 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
         const double d2 = householder3(oc, Dk, s2, c2);
         if (nd) {
           if (kCountStats) st->extra_f64++;
+          count_event(gstats, 0);
           Dk += d2;
           if ((unsigned)(hi32(d2) & 0x7fffffff) < 0x3f200000u) {
             rotate_small(tc, d2, s2, c2);
@@ -355,6 +366,7 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
       }
       if (nd) {  // did not converge within kF64MaxIter passes: best estimate, counted
         if (kCountStats) st->not_converged++;
+        count_event(gstats, 1);
         const double v2 = fma(Dk, TJB_MC(3), x4[k]);
         const double tv2 = v2 + kMagic;
         sincos_quarter(tc, v2 - (tv2 - kMagic), lo32(tv2), sR, cR);

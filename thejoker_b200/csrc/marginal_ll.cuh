@@ -56,6 +56,7 @@ struct StarParams {
   int apply_jitter;                 // kJit kernels: 0 -> treat s as 0 (reference behaviour)
   double zero;                      // run-time 0.0, see TrigCoef::load
   TrigCoef trig;                    // polynomial coefficients as kernel-parameter constants
+  unsigned long long *stats;        // device counters of the solver's rare path (may be null)
 };
 
 // order-preserving int64 key of a double: key(a) < key(b) <=> a < b, NaN above +inf
@@ -127,7 +128,7 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab, do
       double dt[kEpochsPerIter], z[kEpochsPerIter];
 #pragma unroll
       for (int j = 0; j < kEpochsPerIter; j++) dt[j] = row[j * RS];
-      rv_unit_columns<kEpochsPerIter, false>(oc, tc, dt, z, nullptr);
+      rv_unit_columns<kEpochsPerIter, false>(oc, tc, dt, z, nullptr, sp.stats);
 #pragma unroll
       for (int j = 0; j < kEpochsPerIter; j++) {
         const double *rj = row + j * RS;
@@ -190,7 +191,7 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab, do
       double dt[kEpochsPerIter], z[kEpochsPerIter];
 #pragma unroll
       for (int j = 0; j < kEpochsPerIter; j++) dt[j] = row[j * RS];
-      rv_unit_columns<kEpochsPerIter, false>(oc, tc, dt, z, nullptr);
+      rv_unit_columns<kEpochsPerIter, false>(oc, tc, dt, z, nullptr, sp.stats);
 #pragma unroll
       for (int j = 0; j < kEpochsPerIter; j++) accumulate(row + j * RS, z[j]);
       lp.renorm();  // at most kEpochsPerIter factors between renormalisations

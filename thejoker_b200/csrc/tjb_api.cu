@@ -67,7 +67,7 @@ struct TjbHandle {
   bool const_valid = false;
   double const_s = 0;
   // scratch
-  DevBuf acc_mask, acc_counts, acc_offsets, acc_totals, misc;
+  DevBuf acc_mask, acc_counts, acc_offsets, acc_totals, misc, stats;
   DevBuf host_stage[2], host_ll[2];
   cudaStream_t aux_stream[2] = {nullptr, nullptr};
   cudaEvent_t aux_event[2] = {nullptr, nullptr};
@@ -84,6 +84,7 @@ int upload_table(TjbHandle *h, DevBuf &buf, const std::vector<double> &tab, Star
                      h->stream));
   CU(cudaStreamSynchronize(h->stream));  // tab is a caller-owned staging buffer
   sp.table = (const double *)buf.p;
+  sp.stats = (unsigned long long *)h->stats.p;
   return TJB_OK;
 }
 
@@ -268,6 +269,11 @@ int tjb_create(const TjbSpec *spec, int device, TjbHandle **out) {
   h->n_sm = prop.multiProcessorCount;
   h->cc_major = prop.major;
   h->cc_minor = prop.minor;
+  if (h->stats.ensure(4 * sizeof(unsigned long long)) ||
+      cudaMemset(h->stats.p, 0, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+    tjb_destroy(h);
+    return fail(TJB_E_NOMEM, "cudaMalloc stats");
+  }
   rc = load_star(h, spec);
   if (rc != TJB_OK) {
     tjb_destroy(h);
@@ -291,7 +297,7 @@ void tjb_destroy(TjbHandle *h) {
   cudaSetDevice(h->device);
   h->tab_const.release(); h->tab_jit.release();
   h->acc_mask.release(); h->acc_counts.release(); h->acc_offsets.release();
-  h->acc_totals.release(); h->misc.release();
+  h->acc_totals.release(); h->misc.release(); h->stats.release();
   for (int i = 0; i < 2; i++) {
     h->host_stage[i].release(); h->host_ll[i].release();
     if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]);
@@ -303,6 +309,19 @@ void tjb_destroy(TjbHandle *h) {
 int tjb_set_stream(TjbHandle *h, void *cuda_stream) {
   if (!h) return fail(TJB_E_INVALID, "null handle");
   h->stream = (cudaStream_t)cuda_stream;
+  return TJB_OK;
+}
+
+int tjb_get_stats(TjbHandle *h, uint64_t *h_stats, int reset) {
+  if (!h || !h_stats) return fail(TJB_E_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < 2; i++)
+    if (h->aux_stream[i]) CU(cudaStreamSynchronize(h->aux_stream[i]));
+  unsigned long long v[4];
+  CU(cudaMemcpy(v, h->stats.p, sizeof(v), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 4; i++) h_stats[i] = v[i];
+  if (reset) CU(cudaMemset(h->stats.p, 0, sizeof(v)));
   return TJB_OK;
 }
 

@@ -427,6 +427,13 @@ class CJokerHelper:
                                                self._ptr(out)))
         return out
 
+    def solver_stats(self, reset=False):
+        """Run-wide counters of the Kepler solver's rare path since the last reset:
+        extra FP64 passes (lane-epochs) and non-converged epochs."""
+        out = (ctypes.c_uint64 * 4)()
+        _lib.check(self._lib.tjb_get_stats(self._h, out, int(bool(reset))))
+        return dict(extra_fp64_passes=int(out[0]), not_converged=int(out[1]))
+
     def fp64_peak(self, iters=20000):
         tf, ms = ctypes.c_double(), ctypes.c_double()
         self._sync_stream()
