@@ -128,7 +128,8 @@ class DeviceEngine:
         self.shards = []
         for d, (lo, hi) in zip(devices, shard_ranges(n_local, len(devices))):
             with torch.cuda.device(d):
-                up = lambda a: torch.from_numpy(np.ascontiguousarray(a[lo:hi], dtype=np.float64)) \
+                # np.array: a private, writable copy (memory-mapped cache columns are read-only)
+                up = lambda a: torch.from_numpy(np.array(a[lo:hi], dtype=np.float64, order="C")) \
                     .to(f"cuda:{d}", non_blocking=False)
                 cols = [up(P), up(e), up(om), up(M0)]
                 s_dev = None if s_is_scalar else up(s)
