@@ -128,9 +128,12 @@ class DeviceEngine:
         self.shards = []
         for d, (lo, hi) in zip(devices, shard_ranges(n_local, len(devices))):
             with torch.cuda.device(d):
-                # np.array: a private, writable copy (memory-mapped cache columns are read-only)
-                up = lambda a: torch.from_numpy(np.array(a[lo:hi], dtype=np.float64, order="C")) \
-                    .to(f"cuda:{d}", non_blocking=False)
+                def up(a):
+                    a = np.ascontiguousarray(a[lo:hi], dtype=np.float64)
+                    if not a.flags.writeable:  # memory-mapped cache columns are read-only
+                        a = a.copy()
+                    return torch.from_numpy(a).to(f"cuda:{d}", non_blocking=False)
+
                 cols = [up(P), up(e), up(om), up(M0)]
                 s_dev = None if s_is_scalar else up(s)
             self._add_shard(make_helper, d, lo, hi, cols, s_dev)
