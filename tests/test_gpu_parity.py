@@ -201,14 +201,15 @@ def test_posterior_aA_and_draws(torch_cuda, oracle_lib):
         assert np.allclose(s_np, s_or, rtol=1e-6, atol=1e-9)
         # device draws: stream consumption equals multivariate_normal's
         r3 = np.random.default_rng(3)
-        s_dev, lls = helper.batch_get_posterior_samples(chunk, 2, r3)
+        s_dev, lls = helper.batch_get_posterior_samples(chunk, 2, r3, draw="device")
         assert np.array_equal(r1.standard_normal(3), r3.standard_normal(3))
         assert s_dev.shape == s_np.shape and np.array_equal(s_dev[:, :5], s_np[:, :5])
     # distribution check on one row
     helper, spec, _, _ = make_helper((16, 1))
     row = prior_chunk(1)
     _, a, A = helper.posterior_aA(row)
-    draws, _ = helper.batch_get_posterior_samples(row, 200_000, np.random.default_rng(0))
+    draws, _ = helper.batch_get_posterior_samples(row, 200_000, np.random.default_rng(0),
+                                                  draw="device")
     x = draws[:, 5:]
     assert np.allclose(x.mean(0), a[0], atol=5 * np.sqrt(np.diag(A[0]) / len(x)))
     C = np.cov(x.T)

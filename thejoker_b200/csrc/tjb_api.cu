@@ -70,7 +70,6 @@ struct TjbHandle {
   DevBuf acc_mask, acc_counts, acc_offsets, acc_totals, misc, stats;
   DevBuf host_stage[2], host_ll[2];
   cudaStream_t aux_stream[2] = {nullptr, nullptr};
-  cudaEvent_t aux_event[2] = {nullptr, nullptr};
   int ll_ctas_per_sm = 0;
 };
 
@@ -301,7 +300,6 @@ void tjb_destroy(TjbHandle *h) {
   for (int i = 0; i < 2; i++) {
     h->host_stage[i].release(); h->host_ll[i].release();
     if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]);
-    if (h->aux_event[i]) cudaEventDestroy(h->aux_event[i]);
   }
   delete h;
 }

@@ -265,10 +265,12 @@ class CJokerHelper:
                                               _vp(a), _vp(A)))
         return ll, a, A
 
-    def batch_get_posterior_samples(self, chunk, n_linear_samples_per, rng, draw="device",
+    def batch_get_posterior_samples(self, chunk, n_linear_samples_per, rng, draw="auto",
                                     clamp_K=False):
         """pyx:471-545.  Returns (samples[n*k, 5+L], ll[n*k]).
 
+        draw="auto" (default): "numpy" for up to 4096 rows -- the reference's numbers --
+        and "device" beyond, where a Python call per row would dominate.
         draw="device": standard normals are taken from ``rng`` in the order the
         reference's ``rng.multivariate_normal`` consumes them ((k, L) per row) and the
         GPU forms x = a + F z with F F^T = A.  Same distribution and same stream
@@ -278,6 +280,8 @@ class CJokerHelper:
         """
         chunk = np.ascontiguousarray(chunk, dtype=np.float64).reshape(-1, 5)
         n, L, k = chunk.shape[0], self.n_linear, int(n_linear_samples_per)
+        if draw == "auto":
+            draw = "numpy" if n <= 4096 else "device"
         if draw == "numpy":
             lls, a, A = self.posterior_aA(chunk, clamp_K)
             out = np.zeros((n, k, 5 + L))

@@ -1,6 +1,7 @@
-"""Host-side pieces of thejoker/likelihood_helpers.py: the design-matrix builders
-(tiny, per star) and the in-memory drivers, which here hand device-resident work to
-the CUDA library instead of looping on the CPU."""
+"""Design-matrix builders for the linear parameters other than K (tiny, per star, host
+side).  Same names and results as thejoker/likelihood_helpers.py:8-37 and :232-233; the
+in-memory drivers of that module live in thejoker.py / sharding.py here because they
+hand device-resident work to the CUDA library instead of looping on the CPU."""
 from __future__ import annotations
 
 import numpy as np
@@ -9,28 +10,28 @@ __all__ = ["get_constant_term_design_matrix", "get_trend_design_matrix", "ln_nor
 
 
 def get_constant_term_design_matrix(data, ids=None):
-    """Constant-term columns of the design matrix: a column of ones plus one
-    indicator column per additional survey id (likelihood_helpers.py:8-25)."""
-    if ids is None:
-        ids = np.zeros(len(data), dtype=int)
-    ids = np.array(ids)
-    unq_ids = np.unique(ids)
-    constant_part = np.zeros((len(data), len(unq_ids)))
-    constant_part[:, 0] = 1.0
-    for j, id_ in enumerate(unq_ids[1:]):
-        constant_part[ids == id_, j + 1] = 1.0
-    return constant_part
+    """Columns for the systemic velocity and the per-survey offsets: a column of ones,
+    then one 0/1 indicator column for every survey id after the first (in sorted id
+    order).  Shape (n_times, n_surveys)."""
+    n = len(data)
+    survey = np.zeros(n, dtype=int) if ids is None else np.asarray(ids)
+    extra = np.unique(survey)[1:]
+    cols = [np.ones(n)] + [np.where(survey == sid, 1.0, 0.0) for sid in extra]
+    return np.stack(cols, axis=1)
 
 
 def get_trend_design_matrix(data, ids, poly_trend):
-    """Design matrix for the linear parameters without the K column:
-    [1 | 1{id==k}.. | dt | dt^2 ..], dt = t - t_ref (likelihood_helpers.py:28-37)."""
-    const_M = get_constant_term_design_matrix(data, ids)
-    dt = data._t_bmjd - data._t_ref_bmjd
-    trend_M = np.vander(dt, N=poly_trend, increasing=True)[:, 1:]
-    return np.ascontiguousarray(np.hstack((const_M, trend_M)))
+    """All columns of the design matrix except the Keplerian one:
+    [1 | survey indicators | dt | dt^2 | ...] with dt = t - t_ref in days and
+    ``poly_trend - 1`` powers of dt.  Shape (n_times, n_linear - 1), C-contiguous."""
+    dt = np.asarray(data._t_bmjd, dtype=float) - data._t_ref_bmjd
+    blocks = [get_constant_term_design_matrix(data, ids)]
+    if poly_trend > 1:
+        blocks.append(np.stack([dt**k for k in range(1, poly_trend)], axis=1))
+    return np.ascontiguousarray(np.concatenate(blocks, axis=1))
 
 
 def ln_normal(x, mu, var):
-    """likelihood_helpers.py:232-233."""
-    return -0.5 * (np.log(2 * np.pi * var) + (x - mu) ** 2 / var)
+    """Log of the normal density N(x | mu, var)."""
+    resid = np.asarray(x) - mu
+    return -0.5 * (resid * resid / var + np.log(2 * np.pi * var))
