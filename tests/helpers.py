@@ -18,9 +18,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def default_prior(poly_trend=1, sigma_K0=30.0, P_min=2.0, P_max=1024.0, v0_offsets=None, s=None,
                   pars=None):
-    sv = [100 * u.km / u.s, 0.5 * u.km / u.s / u.day, 1e-2 * u.km / u.s / u.day**2][:poly_trend]
+    sv = [100 * u.km / u.s] + [0.5 * 50.0 ** (1 - k) * u.km / u.s / u.day**k for k in range(1, 8)]
+    sv = sv[:poly_trend]
     if poly_trend == 1:
         sv = sv[0]
+    elif poly_trend == 0:
+        sv = None
     return tj.JokerPrior.default(P_min=P_min * u.day, P_max=P_max * u.day,
                                  sigma_K0=sigma_K0 * u.km / u.s if sigma_K0 is not None else None,
                                  sigma_v=sv, poly_trend=poly_trend, v0_offsets=v0_offsets, s=s,

@@ -368,3 +368,33 @@ def test_prior_cache_roundtrip(tmp_path):
     except ImportError:
         with pytest.raises(ImportError):
             read_reference_hdf5("nope.hdf5")
+
+
+def test_poly_trend_zero_is_rejected_like_the_reference():
+    """poly_trend=0 still yields the constant column (likelihood_helpers.py:21, 34-37), so
+    the reference's shape check (pyx:174-179) raises; same here."""
+    with pytest.raises(ValueError):
+        star_spec(10, 0)
+
+
+@pytest.mark.parametrize("N,pt,tol", [(30, 4, 1e-10), (40, 6, 1e-9), (24, 7, 1e-7)])
+def test_host_emulated_ll_extreme_n_linear(N, pt, tol):
+    """n_linear up to 8 (K + sextic trend), against the quad truth.  Raw monomials
+    1, dt, dt^2.. are nearly collinear, so accuracy degrades with the order in any
+    double-precision evaluation (the reference's N x N LU is worse); the tolerance per
+    order documents what the L x L LDL^T delivers."""
+    from oracle.oracle import OracleHelper
+
+    spec, _, _ = star_spec(N, pt)
+    assert spec["n_linear"] == 1 + pt
+    chunk = prior_chunk(300, s_lognormal=(-2.0, 1.0))
+    truth, _ = OracleHelper.from_spec(spec).truth_ll(chunk)
+    for force_jit in (False, True):
+        c = chunk.copy()
+        if not force_jit:
+            c[:, 4] = 0.3
+            truth_c, _ = OracleHelper.from_spec(spec).truth_ll(c)
+        else:
+            truth_c = truth
+        got = emu_marginal_ll(spec, c, force_jit=force_jit)
+        assert np.max(rel_err(got, truth_c)) < tol, (N, pt, force_jit)
