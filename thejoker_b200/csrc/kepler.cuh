@@ -208,18 +208,19 @@ struct OrbitConsts {
   float g0f;    // (float)(1 + e^2)
 };
 
-TJB_HD OrbitConsts make_orbit_consts(double P, double e, double omega, double M0) {
+TJB_HD OrbitConsts make_orbit_consts(const TrigCoef &tc, double P, double e, double omega,
+                                     double M0) {
   OrbitConsts oc;
   oc.nu4 = 4.0 / P;
   oc.ph4 = M0 * kTwoOverPi;
   oc.e = e;
   oc.e6 = e * (1.0 / 6.0);
+  // sin / cos of omega through the same quarter-revolution reduction as the epochs
+  // (|omega| is a few radians; the product with 2/pi costs < 1e-15 rad)
+  const double o4 = omega * kTwoOverPi;
+  const double to = o4 + kMagic;
   double so, co;
-#if defined(__CUDA_ARCH__)
-  sincos(omega, &so, &co);
-#else
-  so = sin(omega); co = cos(omega);
-#endif
+  sincos_quarter(tc, o4 - (to - kMagic), lo32(to), so, co);
   oc.a = co;
   oc.b = -sqrt(fma(-e, e, 1.0)) * so;
   oc.ea = e * co;

@@ -27,11 +27,20 @@ TJB_HD constexpr int tri(int i, int j) { return i * L - (i * (i - 1)) / 2 + (j -
 template <int L>
 constexpr int kTri = L * (L + 1) / 2;
 
+// reciprocal of a non-zero normal double (either sign): MUFU seed + third-order step
+TJB_HD double rcp_nz(double x) {
+#if defined(__CUDA_ARCH__)
+  return rcp_pos(x);
+#else
+  return 1.0 / x;
+#endif
+}
+
 // LDL^T of the packed SPD matrix G (overwritten: D on the diagonal, the rows of
-// L^T above it).  Returns false if a pivot is exactly zero (the analogue of
-// dgetrf info != 0, pyx:283-284).
+// L^T above it); rD receives 1/D.  Returns false if a pivot is exactly zero (the
+// analogue of dgetrf info != 0, pyx:283-284).
 template <int L>
-TJB_HD bool ldlt(double *G) {
+TJB_HD bool ldlt(double *G, double *rD) {
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < L; j++) {
@@ -40,7 +49,8 @@ TJB_HD bool ldlt(double *G) {
     for (int k = 0; k < j; k++) d = fma(-G[tri<L>(k, j)] * G[tri<L>(k, j)], G[tri<L>(k, k)], d);
     G[tri<L>(j, j)] = d;
     ok = ok && (d != 0.0);
-    const double rd = 1.0 / d;
+    const double rd = rcp_nz(d);
+    rD[j] = rd;
 #pragma unroll
     for (int i = j + 1; i < L; i++) {
       double v = G[tri<L>(j, i)];
@@ -55,7 +65,8 @@ TJB_HD bool ldlt(double *G) {
 
 // given the factorisation from ldlt(): quad = h^T G^-1 h and prod = det G
 template <int L>
-TJB_HD void ldlt_quad(const double *G, const double *h, double &quad, double &detG) {
+TJB_HD void ldlt_quad(const double *G, const double *rD, const double *h, double &quad,
+                      double &detG) {
   double y[L];
   quad = 0.0;
   detG = 1.0;
@@ -65,22 +76,21 @@ TJB_HD void ldlt_quad(const double *G, const double *h, double &quad, double &de
 #pragma unroll
     for (int k = 0; k < j; k++) v = fma(-G[tri<L>(k, j)], y[k], v);
     y[j] = v;
-    const double d = G[tri<L>(j, j)];
-    quad = fma(v * v, 1.0 / d, quad);
-    detG *= d;
+    quad = fma(v * v, rD[j], quad);
+    detG *= G[tri<L>(j, j)];
   }
 }
 
 // solve G x = h in place (x returned in h) from the factorisation
 template <int L>
-TJB_HD void ldlt_solve(const double *G, double *h) {
+TJB_HD void ldlt_solve(const double *G, const double *rD, double *h) {
 #pragma unroll
   for (int j = 0; j < L; j++) {
 #pragma unroll
     for (int k = 0; k < j; k++) h[j] = fma(-G[tri<L>(k, j)], h[k], h[j]);
   }
 #pragma unroll
-  for (int j = 0; j < L; j++) h[j] = h[j] / G[tri<L>(j, j)];
+  for (int j = 0; j < L; j++) h[j] = h[j] * rD[j];
 #pragma unroll
   for (int j = L - 1; j >= 0; j--) {
 #pragma unroll
@@ -98,7 +108,7 @@ TJB_HD double lambda_K_fixed_mass(double P, double e, double sigma_K0_sq, double
 #else
   const double rc = 1.0 / cbrt(x);
 #endif
-  const double lam = sigma_K0_sq / fma(-e, e, 1.0) * (rc * rc);
+  const double lam = sigma_K0_sq * rcp_nz(fma(-e, e, 1.0)) * (rc * rc);
   return clamp ? fmin(max_K_sq, lam) : lam;
 }
 

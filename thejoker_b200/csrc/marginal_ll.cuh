@@ -102,13 +102,13 @@ template <int L, bool kJit>
 TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab, double P, double e,
                         double omega, double M0, double s) {
   constexpr int RS = row_stride(L);
-  const OrbitConsts oc = make_orbit_consts(P, e, omega, M0);
 #if TJB_COEF_MODE == 3 && defined(__CUDA_ARCH__)
   const TrigCoef &tc = sp.trig;  // constant-bank (kernel parameter) operands
 #else
   TrigCoef tc;
   tc.load(sp.zero);
 #endif
+  const OrbitConsts oc = make_orbit_consts(tc, P, e, omega, M0);
   const int N = sp.n_times;
 
   double G[kTri<L>];
@@ -214,14 +214,15 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab, do
   const double lamK = sp.K_prior_kind == 0
                           ? lambda_K_fixed_mass(P, e, sp.sigma_K0_sq, sp.inv_P0, sp.max_K_sq, true)
                           : sp.Lambda_K;
-  const double ilamK = 1.0 / lamK;
+  const double ilamK = rcp_nz(lamK);
   G[0] += ilamK;
   h[0] = fma(sp.mu_K, ilamK, h[0]);
   quad0 = fma(sp.mu_K * sp.mu_K, ilamK, quad0);
 
-  const bool ok = ldlt<L>(G);
+  double rD[L];
+  const bool ok = ldlt<L>(G, rD);
   double quad, detG;
-  ldlt_quad<L>(G, h, quad, detG);
+  ldlt_quad<L>(G, rD, h, quad, detG);
   const double ll = -0.5 * ((quad0 - quad) + (logdet + log(lamK * detG)));
   // singular Ainv: the reference returns +inf (pyx:283-284, 381-382)
   return ok ? ll : (double)INFINITY;

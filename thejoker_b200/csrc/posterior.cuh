@@ -29,9 +29,9 @@ posterior_kernel(const StarParams sp, const double *__restrict__ rows, const int
   const int r = valid ? gid : k - 1;
   const double P = rows[5 * r + 0], e = rows[5 * r + 1], om = rows[5 * r + 2],
                M0 = rows[5 * r + 3], s = rows[5 * r + 4];
-  const OrbitConsts oc = make_orbit_consts(P, e, om, M0);
   TrigCoef tc;
   tc.load(sp.zero);
+  const OrbitConsts oc = make_orbit_consts(tc, P, e, om, M0);
   const double s2 = sp.apply_jitter ? s * s : 0.0;
 
   double G[kTri<L>], h[L], Syy = 0.0;
@@ -76,9 +76,10 @@ posterior_kernel(const StarParams sp, const double *__restrict__ rows, const int
     G[tri<L>(i, i)] += sp.inv_Lambda[i];
     h[i] += sp.hc[i];
   }
-  const bool ok = ldlt<L>(G);
+  double rD[L];
+  const bool ok = ldlt<L>(G, rD);
   double quad, detG;
-  ldlt_quad<L>(G, h, quad, detG);
+  ldlt_quad<L>(G, rD, h, quad, detG);
   double ll = -0.5 * ((quad0 - quad) + (sp.c0 + lp.log_value() + log(lamK * detG)));
   if (!ok) ll = INFINITY;
 
@@ -86,7 +87,7 @@ posterior_kernel(const StarParams sp, const double *__restrict__ rows, const int
   double a[L];
 #pragma unroll
   for (int i = 0; i < L; i++) a[i] = h[i];
-  ldlt_solve<L>(G, a);
+  ldlt_solve<L>(G, rD, a);
   if (!valid) return;
   if (ll_out) ll_out[r] = ll;
   if (a_out) {
@@ -99,7 +100,7 @@ posterior_kernel(const StarParams sp, const double *__restrict__ rows, const int
       double col[L];
 #pragma unroll
       for (int i = 0; i < L; i++) col[i] = (i == c) ? 1.0 : 0.0;
-      ldlt_solve<L>(G, col);
+      ldlt_solve<L>(G, rD, col);
 #pragma unroll
       for (int i = 0; i < L; i++) A_out[(r * L + i) * L + c] = col[i];
     }
@@ -110,7 +111,7 @@ posterior_kernel(const StarParams sp, const double *__restrict__ rows, const int
       double x[L];
       const double *zn = normals + ((long long)r * n_per + d) * L;
 #pragma unroll
-      for (int i = 0; i < L; i++) x[i] = zn[i] * rsqrt(G[tri<L>(i, i)]);
+      for (int i = 0; i < L; i++) x[i] = zn[i] * sqrt(rD[i]);
 #pragma unroll
       for (int j = L - 1; j >= 0; j--) {
 #pragma unroll
@@ -129,9 +130,9 @@ __global__ void design_column_kernel(const double *__restrict__ dt, const int N,
                                      const double e, const double om, const double M0,
                                      const double zero, double *__restrict__ z,
                                      int *__restrict__ stats) {
-  const OrbitConsts oc = make_orbit_consts(P, e, om, M0);
   TrigCoef tc;
   tc.load(zero);
+  const OrbitConsts oc = make_orbit_consts(tc, P, e, om, M0);
   SolveStats st = {0, 0, 0};
   for (int n = 0; n < N; n++) {
     const double v = rv_unit_column<true>(oc, tc, dt[n], &st);

@@ -24,10 +24,10 @@ extern "C" {
 // z[n] for one sample; returns the solver statistics through stats[3]
 void emu_design_column(double P, double e, double omega, double M0, const double *dt, int N,
                        double *z, int *stats) {
-  OrbitConsts oc = make_orbit_consts(P, e, omega, M0);
   SolveStats st = {0, 0, 0};
   TrigCoef tc;
   tc.load(0.0);
+  OrbitConsts oc = make_orbit_consts(tc, P, e, omega, M0);
   for (int n = 0; n < N; n++) z[n] = rv_unit_column<true>(oc, tc, dt[n], &st);
   if (stats) { stats[0] = st.extra_f32; stats[1] = st.extra_f64; stats[2] = st.not_converged; }
 }
