@@ -202,33 +202,55 @@ def run_ours(args):
     ll_max = helper.llmax_value(kk)
     assert np.isfinite(ll_max) and ll_max >= ll.max().item()
 
-    # ---- e2e: the reference-facing call on a pinned host chunk ----------------------
-    n_e2e = min(n, 1 << args.log2_e2e)
-    host = torch.empty((n_e2e, 5), dtype=torch.float64).pin_memory()
-    host[:, 0].copy_(P[:n_e2e]); host[:, 1].copy_(e[:n_e2e]); host[:, 2].copy_(om[:n_e2e])
-    host[:, 3].copy_(M0[:n_e2e]); host[:, 4].zero_()
-    host_ll = torch.empty(n_e2e, dtype=torch.float64).pin_memory()
-    chunk_np, ll_np = host.numpy(), host_ll.numpy()
+    # ---- e2e: host buffers in, host ll out, copies inside the timed region ------------
+    # (1) prior samples as separate pinned host columns -- what a JokerSamples holds and
+    #     what TheJoker.marginal_ln_likelihood(data, prior_samples) sends
+    #     (CJokerHelper.marginal_ln_likelihood_columns -> tjb_marginal_ll_host_soa);
+    # (2) the literal reference-facing call CJokerHelper.batch_marginal_ln_likelihood on a
+    #     packed (n, 5) pinned chunk (tjb_marginal_ll_host).
     import ctypes
 
     from thejoker_b200 import _lib
 
-    def e2e_step():
-        _lib.check(helper._lib.tjb_marginal_ll_host(helper._h, ctypes.c_void_p(chunk_np.ctypes.data),
-                                                    n_e2e, ctypes.c_void_p(ll_np.ctypes.data)))
-
-    e2e_step()
-    barrier()
+    n_e2e = min(n, 1 << args.log2_e2e)
     e2e_steps = max(1, min(args.steps, 3))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()  # synchronous: returns when ll is back in host memory
-    torch.cuda.synchronize()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_value = n_e2e * world * e2e_steps / float(dt.item())
-    assert np.array_equal(ll_np[:1024], ll[:1024].cpu().numpy())
+    host_ll = torch.empty(n_e2e, dtype=torch.float64).pin_memory()
+    ll_np = host_ll.numpy()
+
+    def time_e2e(fn):
+        fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fn()  # synchronous: returns when ll is back in host memory
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        assert np.array_equal(ll_np[:1024], ll[:1024].cpu().numpy())
+        return n_e2e * world * e2e_steps / float(dt.item())
+
+    cols_host = [t[:n_e2e].cpu().pin_memory() for t in (P, e, om, M0)]
+    cols_np = [t.numpy() for t in cols_host]
+    vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+
+    def e2e_columns():
+        _lib.check(helper._lib.tjb_marginal_ll_host_soa(helper._h, *[vp(c) for c in cols_np], None,
+                                                        0.0, n_e2e, vp(ll_np)))
+
+    e2e_value = time_e2e(e2e_columns)
+    del cols_host, cols_np
+
+    host = torch.empty((n_e2e, 5), dtype=torch.float64).pin_memory()
+    host[:, 0].copy_(P[:n_e2e]); host[:, 1].copy_(e[:n_e2e]); host[:, 2].copy_(om[:n_e2e])
+    host[:, 3].copy_(M0[:n_e2e]); host[:, 4].zero_()
+    chunk_np = host.numpy()
+
+    def e2e_chunk():
+        _lib.check(helper._lib.tjb_marginal_ll_host(helper._h, vp(chunk_np), n_e2e, vp(ll_np)))
+
+    e2e_chunk_value = time_e2e(e2e_chunk)
+    del host, chunk_np
 
     if rank != 0:
         if world > 1:
@@ -279,10 +301,15 @@ def run_ours(args):
                                "samples sharded over the ranks (configs[1]/metric config)",
                    "l2": "inputs (32 B/sample x 2^28/ranks) are larger than L2",
                    "n_prior": n_total, "n_epochs": N_EPOCHS, "sharding": f"contiguous x{world}"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_e2e * 40),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_e2e * 32),
                 "d2h_bytes_per_step": int(n_e2e * 8), "n_per_rank": int(n_e2e), "steps": e2e_steps,
-                "call": "CJokerHelper.batch_marginal_ln_likelihood -> tjb_marginal_ll_host, pinned "
-                        "host chunk (n,5) in, host ll out"},
+                "call": "TheJoker.marginal_ln_likelihood data path: pinned host columns P, e, "
+                        "omega, M0 (s constant) in, host ll out (CJokerHelper."
+                        "marginal_ln_likelihood_columns -> tjb_marginal_ll_host_soa)",
+                "packed_chunk": {"value": e2e_chunk_value, "h2d_bytes_per_step": int(n_e2e * 40),
+                                 "d2h_bytes_per_step": int(n_e2e * 8),
+                                 "call": "CJokerHelper.batch_marginal_ln_likelihood on a pinned "
+                                         "(n,5) chunk -> tjb_marginal_ll_host"}},
         "gpu_launches": args.steps,
         "clocks": clocks,
         "roofline": roofline,

@@ -96,6 +96,13 @@ int tjb_marginal_ll_aos(TjbHandle *h, const double *d_chunk, int uniform_s, int6
  * chunk to the device in slices, runs the kernel and copies ll back, overlapping
  * the three on two streams.  Pinned host buffers give full PCIe bandwidth. */
 int tjb_marginal_ll_host(TjbHandle *h, const double *h_chunk, int64_t n, double *h_ll);
+/* The same for prior samples held as separate HOST columns (what a JokerSamples is:
+ * thejoker.py:129-134 packs them into the (n, 5) chunk first; here they are sent as
+ * they are).  h_s may be NULL: every sample then has jitter s_const and only 32 B per
+ * sample cross PCIe. */
+int tjb_marginal_ll_host_soa(TjbHandle *h, const double *h_P, const double *h_e,
+                             const double *h_omega, const double *h_M0, const double *h_s,
+                             double s_const, int64_t n, double *h_ll);
 
 /* ---- accept step (likelihood_helpers.py:107-109; multiproc_helpers.py:256-258) */
 int tjb_llmax_reset(TjbHandle *h, int64_t *d_llmax_key);

@@ -135,6 +135,10 @@ def test_ll_device_paths_agree(torch_cuda, oracle_lib):
             aos = helper.marginal_ll_aos(dev, uniform_s=False)
         assert np.array_equal(soa.cpu().numpy(), host)
         assert np.array_equal(aos.cpu().numpy(), host)
+        hc = [np.ascontiguousarray(chunk[:, i]) for i in range(5)]
+        host_cols = helper.marginal_ln_likelihood_columns(
+            *hc[:4], s=hc[4] if sl is not None else None, s_const=s_const or 0.0)
+        assert np.array_equal(host_cols, host)
         assert helper.llmax_value(key) == host.max()
         ref = oracle_lib.OracleHelper.from_spec(spec).batch_marginal_ln_likelihood(chunk[:4096], 0)
         assert np.max(rel_err(host[:4096], ref)) < 1e-9

@@ -407,6 +407,44 @@ int tjb_marginal_ll_host(TjbHandle *h, const double *h_chunk, int64_t n, double 
   return TJB_OK;
 }
 
+int tjb_marginal_ll_host_soa(TjbHandle *h, const double *h_P, const double *h_e,
+                             const double *h_omega, const double *h_M0, const double *h_s,
+                             double s_const, int64_t n, double *h_ll) {
+  if (!h) return fail(TJB_E_INVALID, "null handle");
+  if (n < 0) return fail(TJB_E_INVALID, "negative n");
+  if (n == 0) return TJB_OK;
+  if (!h_P || !h_e || !h_omega || !h_M0 || !h_ll) return fail(TJB_E_INVALID, "null host pointer");
+  CU(cudaSetDevice(h->device));
+  const int n_cols = h_s ? 5 : 4;
+  const double *cols[5] = {h_P, h_e, h_omega, h_M0, h_s};
+  const int64_t slice = 1 << 20;
+  const int64_t m_max = std::min(slice, n);
+  for (int i = 0; i < 2; i++) {
+    if (!h->aux_stream[i]) CU(cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking));
+    if (h->host_stage[i].ensure((size_t)m_max * 5 * sizeof(double)) ||
+        h->host_ll[i].ensure((size_t)m_max * sizeof(double)))
+      return fail(TJB_E_NOMEM, "cudaMalloc staging");
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  int b = 0;
+  for (int64_t lo = 0; lo < n; lo += slice, b ^= 1) {
+    const int64_t m = std::min(slice, n - lo);
+    cudaStream_t st = h->aux_stream[b];
+    double *d_in = (double *)h->host_stage[b].p, *d_out = (double *)h->host_ll[b].p;
+    for (int c = 0; c < n_cols; c++)
+      CU(cudaMemcpyAsync(d_in + (size_t)c * m_max, cols[c] + lo, (size_t)m * sizeof(double),
+                         cudaMemcpyHostToDevice, st));
+    PriorView pv = {d_in, d_in + m_max, d_in + 2 * m_max, d_in + 3 * m_max,
+                    h_s ? d_in + 4 * m_max : nullptr, nullptr, 0.0, nullptr};
+    int rc = run_ll(h, pv, h_s == nullptr, s_const, m, d_out, nullptr, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h_ll + lo, d_out, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(h->aux_stream[0]));
+  CU(cudaStreamSynchronize(h->aux_stream[1]));
+  return TJB_OK;
+}
+
 // ---- accept -----------------------------------------------------------------
 
 int64_t tjb_double_to_key(double x) { return (int64_t)ll_to_key(x); }

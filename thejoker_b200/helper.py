@@ -254,6 +254,24 @@ class CJokerHelper:
         _lib.check(self._lib.tjb_marginal_ll_host(self._h, _vp(chunk), n, _vp(ll)))
         return ll
 
+    def marginal_ln_likelihood_columns(self, P, e, omega, M0, s=None, s_const=0.0, out=None):
+        """ll for prior samples held as separate host columns in internal units (the
+        layout of a JokerSamples) -- no (n, 5) packing, and only the columns that vary
+        cross PCIe.  Host arrays in, host array out."""
+        cols = [np.ascontiguousarray(c, dtype=np.float64) for c in (P, e, omega, M0)]
+        n = len(cols[0])
+        if any(len(c) != n for c in cols):
+            raise ValueError("prior columns differ in length")
+        if s is not None:
+            s = np.ascontiguousarray(s, dtype=np.float64)
+            if len(s) != n:
+                raise ValueError("prior columns differ in length")
+        ll = np.full(n, np.nan) if out is None else out
+        _lib.check(self._lib.tjb_marginal_ll_host_soa(
+            self._h, *[_vp(c) for c in cols], _vp(s) if s is not None else None, float(s_const),
+            n, _vp(ll)))
+        return ll
+
     def posterior_aA(self, chunk, clamp_K=False):
         """(ll, a, A) per row: posterior mean / covariance of the linear parameters
         (pyx:394-423, 530).  clamp_K=False reproduces the reference, which does not

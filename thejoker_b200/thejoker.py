@@ -229,6 +229,12 @@ class TheJoker:
         a numpy array; the computation runs on the configured GPUs."""
         helper0 = self._make_joker_helper(data)
         cols, _ = self._columns(helper0, prior_samples)
+        if self.group is None and len(self.devices) == 1:
+            # host columns in, host ll out: copies and kernel pipelined in the library
+            s = cols[4]
+            return helper0.marginal_ln_likelihood_columns(
+                *cols[:4], s=None if np.ndim(s) == 0 else s,
+                s_const=float(s) if np.ndim(s) == 0 else 0.0)
         eng, _ = self._engine(data, cols)
         eng.compute_ll()
         return eng.gather_ll()
