@@ -398,3 +398,26 @@ def test_host_emulated_ll_extreme_n_linear(N, pt, tol):
             truth_c = truth
         got = emu_marginal_ll(spec, c, force_jit=force_jit)
         assert np.max(rel_err(got, truth_c)) < tol, (N, pt, force_jit)
+
+
+def test_thejoker_init_validation():
+    """thejoker/tests/test_sampler.py::test_init (constructor checks need no GPU)."""
+    prior = default_prior(1)
+    tj.TheJoker(prior)
+    tj.TheJoker(prior, rng=np.random.default_rng(1), tempfile_path="/tmp/_tjb_test")
+    with pytest.raises(TypeError):
+        tj.TheJoker("jsdfkj")
+    with pytest.raises(TypeError):
+        tj.TheJoker(prior, rng=np.random.RandomState(1))
+    with pytest.raises(TypeError):
+        tj.TheJoker(prior, pool="sdfks")
+
+    class Pool:  # anything with map / close is accepted, as schwimmbad pools are
+        def map(self, *a):
+            pass
+
+        def close(self):
+            pass
+
+    j = tj.TheJoker(prior, pool=Pool(), devices=[0, 1])
+    assert j.devices == [0, 1] and os.path.isdir(j.tempfile_path)

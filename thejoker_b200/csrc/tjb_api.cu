@@ -417,7 +417,7 @@ int tjb_marginal_ll_host_soa(TjbHandle *h, const double *h_P, const double *h_e,
   CU(cudaSetDevice(h->device));
   const int n_cols = h_s ? 5 : 4;
   const double *cols[5] = {h_P, h_e, h_omega, h_M0, h_s};
-  const int64_t slice = 1 << 20;
+  const int64_t slice = 1 << 22;  // 32 MB per column copy: large DMA transfers
   const int64_t m_max = std::min(slice, n);
   for (int i = 0; i < 2; i++) {
     if (!h->aux_stream[i]) CU(cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking));
