@@ -91,7 +91,7 @@ def host_emulation():
         lib.emu_key_to_ll.argtypes = [ctypes.c_longlong]
         lib.emu_pcg64_double.restype = ctypes.c_double
         lib.emu_pcg64_double.argtypes = [ctypes.c_ulonglong] * 5
-        lib.emu_sincos_quarter.argtypes = [ctypes.c_double, ctypes.c_int, dp, dp]
+        lib.emu_sincos_rev.argtypes = [ctypes.c_double, dp, dp]
         _emu = lib
     return _emu
 

@@ -106,7 +106,14 @@ def test_ll_parity_host_path(torch_cuda, oracle_lib, args, sl, kw):
     # ragged / tiny / empty inputs
     for m in (0, 1, 31, 33, 257):
         part = helper.batch_marginal_ln_likelihood(np.ascontiguousarray(chunk[:m]))
-        assert part.shape == (m,) and np.array_equal(part, ll[:m])
+        assert part.shape == (m,)
+        if sl is not None and m == 1:
+            # a one-row chunk has a uniform jitter by construction and takes the
+            # constant-jitter kernel (weights folded into the table in long double); the
+            # same row inside a mixed chunk goes through the per-sample-jitter kernel
+            assert np.allclose(part, ll[:m], rtol=1e-12, atol=0)
+        else:
+            assert np.array_equal(part, ll[:m])
     with pytest.raises(ValueError):
         helper.batch_marginal_ln_likelihood(chunk.astype(np.float32))
     with pytest.raises(ValueError):

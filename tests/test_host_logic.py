@@ -212,7 +212,9 @@ def test_product_does_not_import_oracle():
 
 
 # ---- device math on the host ---------------------------------------------------------
-def test_sincos_quarter():
+def test_sincos_units():
+    """The FP64 sin/cos of the epoch loop (table node + short polynomial, or the minimax
+    polynomial back-end) against 40-digit mpmath, over many revolutions."""
     import mpmath as mp
 
     lib = host_emulation()
@@ -220,13 +222,14 @@ def test_sincos_quarter():
     s, c = ctypes.c_double(), ctypes.c_double()
     worst = 0.0
     mp.mp.dps = 40
-    for _ in range(2000):
-        w, k = rng.uniform(-0.5, 0.5), int(rng.integers(-8, 8))
-        lib.emu_sincos_quarter(w, k, ctypes.byref(s), ctypes.byref(c))
-        ang = (mp.mpf(k) + mp.mpf(w)) * mp.pi / 2
+    revs = np.concatenate([rng.uniform(-3, 3, 3000), rng.uniform(-500, 500, 500),
+                           np.arange(-8, 9) / 8.0, (np.arange(0, 4096) + 0.5) / 4096])
+    for rev in revs:
+        lib.emu_sincos_rev(float(rev), ctypes.byref(s), ctypes.byref(c))
+        ang = 2 * mp.pi * mp.mpf(float(rev))
         worst = max(worst, abs(float(mp.sin(ang) - mp.mpf(s.value))),
                     abs(float(mp.cos(ang) - mp.mpf(c.value))))
-    assert worst < 3e-16
+    assert worst < 3.5e-16
 
 
 def test_kepler_column_matches_oracle():

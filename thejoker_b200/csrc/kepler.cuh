@@ -11,15 +11,16 @@
 // every two cycles per SM sub-partition, so the kernel is bound by the number of
 // FP64 instructions per epoch as long as everything else fits in the other half
 // of the issue slots.  Hence:
-//  * angles are carried in quarter-revolutions so the argument reduction is an
-//    exact magic-number rounding (no Payne-Hanek, no multiples of 2 pi);
+//  * angles are carried in binary fractions of a revolution (1/1024, or 1/4 for the
+//    polynomial back-end) so the argument reduction is an exact magic-number rounding
+//    (no Payne-Hanek, no multiples of 2 pi);
 //  * the starter and one Householder refinement run on the FP32 / MUFU pipes
 //    (sin.approx, cos.approx, rsqrt.approx, rcp.approx) with no branches;
 //  * one third-order Householder step in FP64 takes the FP32 estimate
 //    (error ~1e-6) to below 1e-20; sin E / cos E are carried through the step
 //    by an angle-addition update, so only one full double sincos is evaluated;
-//  * polynomial coefficients are pinned in registers for the whole epoch loop (ptxas
-//    otherwise re-loads or re-materialises them every epoch; TJB_COEF_MODE below);
+//  * the handful of FP64 constants is pinned in registers for the whole epoch loop
+//    (ptxas otherwise re-loads or re-materialises them every epoch);
 //  * z is formed without atan2:  cos f = (cosE - e)/(1 - e cosE),
 //    sin f = sqrt(1-e^2) sinE/(1 - e cosE);
 //  * the FP64 step is closed by a warp-uniform convergence test (|delta|), so
@@ -40,20 +41,54 @@
 
 namespace tjb {
 
+// Trig back-end of the FP64 stage (both measured on B200):
+//   0  angles in quarter-revolutions; sin/cos by degree-13/14 minimax polynomials and a
+//      quadrant swap (15 FP64 + ~10 integer instructions per evaluation)
+//   1  angles in 1/1024 revolution; sin/cos of the nearest table node from a 16 KB
+//      shared-memory table, rotated by the residual |r| <= pi/1024 through degree-5/4
+//      polynomials (10 FP64 instructions + one LDS.128, no quadrant logic)
+#ifndef TJB_TRIG_TABLE
+#define TJB_TRIG_TABLE 1
+#endif
+
 // 1.5 * 2^52 (1.5 * 2^23): adding it rounds to the nearest integer and leaves
 // that integer in the low mantissa bits.
 constexpr double kMagic = 6755399441055744.0;
 constexpr float kMagicF = 12582912.0f;
-constexpr double kTwoOverPi = 0.63661977236758134308;  // 2/pi
+constexpr double kTwoPi = 6.28318530717958647692528676655900577;
+#if TJB_TRIG_TABLE
+constexpr int kTrigTableSize = 1024;
+constexpr double kUnitsPerRev = 1024.0;
+#else
+constexpr int kTrigTableSize = 0;
+constexpr double kUnitsPerRev = 4.0;
+#endif
+constexpr double kRadPerUnit = kTwoPi / kUnitsPerRev;
+constexpr double kUnitsPerRad = kUnitsPerRev / kTwoPi;
 
-// sin(w pi/2) = w * sum_k S[k] w^2k,  cos(w pi/2) = sum_k C[k] w^2k on |w| <= 1/2:
-// the fdlibm __kernel_sin/__kernel_cos minimax coefficients (|x| <= pi/4) with the
-// powers of pi/2 folded in (tests/test_host_math.py checks the result).
+struct alignas(16) SinCos {
+  double s, c;
+};
+
 #if defined(__CUDA_ARCH__)
 #define TJB_COEF __constant__
 #else
 #define TJB_COEF static const
 #endif
+#if TJB_TRIG_TABLE
+// sin(r h) = r (S0 + S1 r^2 + S2 r^4), cos(r h) = 1 + C1 r^2 + C2 r^4 for |r| <= 1/2,
+// h = 2 pi / 1024 (Taylor; truncation 5e-22 and 1.2e-18)
+constexpr int kNSin = 3, kNCos = 3;
+TJB_COEF double kSinC[3] = {kRadPerUnit, -(kRadPerUnit * kRadPerUnit * kRadPerUnit) / 6.0,
+                            (kRadPerUnit * kRadPerUnit * kRadPerUnit * kRadPerUnit * kRadPerUnit) /
+                                120.0};
+TJB_COEF double kCosC[3] = {1.0, -(kRadPerUnit * kRadPerUnit) / 2.0,
+                            (kRadPerUnit * kRadPerUnit * kRadPerUnit * kRadPerUnit) / 24.0};
+#else
+// sin(w pi/2) = w * sum_k S[k] w^2k,  cos(w pi/2) = sum_k C[k] w^2k on |w| <= 1/2:
+// the fdlibm __kernel_sin/__kernel_cos minimax coefficients (|x| <= pi/4) with the
+// powers of pi/2 folded in (tests/test_host_logic.py::test_sincos_units checks it).
+constexpr int kNSin = 7, kNCos = 8;
 TJB_COEF double kSinC[7] = {1.570796326794896619231322,     -0.6459640975062449269023451,
                             0.07969262624606334392301012,   -0.004681754132625933413797963,
                             0.0001604411526673809583408432, -0.000003598649570240691901625632,
@@ -66,9 +101,9 @@ TJB_COEF double kCosC[8] = {1.0,
                             -0.00002520203791691774237050555,
                             0.0000004710641505803501879438872,
                             -6.324746678866069891109223e-9};
-// 1/6, 1/24, Householder repeat threshold, 2/pi, pi/2 as constant-bank operands
-TJB_COEF double kMisc[5] = {1.0 / 6.0, 1.0 / 24.0, 1.0e-4, 0.63661977236758134308,
-                            1.57079632679489661923};
+#endif
+// 1/6, (unused), (unused), angle units per radian, radians per angle unit
+TJB_COEF double kMisc[5] = {1.0 / 6.0, 1.0 / 24.0, 1.0e-4, kUnitsPerRad, kRadPerUnit};
 
 // ---- bit helpers / pipe-specific primitives -------------------------------
 #if defined(__CUDA_ARCH__)
@@ -87,10 +122,10 @@ TJB_D float frcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-// reciprocal of a positive, normal double: MUFU.RCP64H seed (20 bits, measured:
+// reciprocal of a non-zero, normal double: MUFU.RCP64H seed (20 bits, measured:
 // tools/microbench3.cu) + one third-order step r (1 + t + t^2), t = 1 - x r: relative
-// error <= 2.2e-16 with 3 FMAs.  The argument here is always 1 - e cosE in (1-e, 1+e],
-// so none of the denormal / overflow handling of a general division is needed.
+// error <= 2.2e-16 with 3 FMAs.  The argument in the epoch loop is always 1 - e cosE in
+// (1-e, 1+e], so none of the denormal / overflow handling of a general division is needed.
 TJB_D double rcp_pos(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
@@ -110,82 +145,57 @@ inline float frcp_approx(float x) { return 1.0f / x; }
 inline double rcp_pos(double x) { return 1.0 / x; }
 #endif
 
-// How the loop gets its FP64 constants (measured on B200):
-//   0  pinned in registers (coefficient + run-time zero)
-//   1  __constant__ arrays read in the loop (ptxas emits LDC / LDCU per use)
-//   2  literals (ptxas materialises them with MOVs / immediates)
-//   3  kernel-parameter constants (StarParams::trig, constant bank 0 / uniform registers)
-#ifndef TJB_COEF_MODE
-#define TJB_COEF_MODE 0
-#endif
-TJB_HD constexpr double sin_lit(int i) {
-  return i == 0 ? 1.570796326794896619231322 : i == 1 ? -0.6459640975062449269023451
-       : i == 2 ? 0.07969262624606334392301012 : i == 3 ? -0.004681754132625933413797963
-       : i == 4 ? 0.0001604411526673809583408432 : i == 5 ? -0.000003598649570240691901625632
-       : 5.634704113884750951753422e-8;
-}
-TJB_HD constexpr double cos_lit(int i) {
-  return i == 0 ? 1.0 : i == 1 ? -1.233700550136169827354311 : i == 2 ? 0.2536695079010476193552061
-       : i == 3 ? -0.02086348076333075982186824 : i == 4 ? 0.000919260274390553378473447
-       : i == 5 ? -0.00002520203791691774237050555 : i == 6 ? 0.0000004710641505803501879438872
-       : -6.324746678866069891109223e-9;
-}
-TJB_HD constexpr double misc_lit(int i) {
-  return i == 0 ? 1.0 / 6.0 : i == 1 ? 1.0 / 24.0 : i == 2 ? 1.0e-4 : i == 3 ? 0.63661977236758134308
-       : 1.57079632679489661923;
-}
-#if TJB_COEF_MODE == 0 || TJB_COEF_MODE == 3 || !defined(__CUDA_ARCH__)
 #define TJB_SC(i) tc.s[i]
 #define TJB_CC(i) tc.c[i]
 #define TJB_MC(i) tc.m[i]
-#elif TJB_COEF_MODE == 1
-#define TJB_SC(i) kSinC[i]
-#define TJB_CC(i) kCosC[i]
-#define TJB_MC(i) kMisc[i]
-#else
-#define TJB_SC(i) sin_lit(i)
-#define TJB_CC(i) cos_lit(i)
-#define TJB_MC(i) misc_lit(i)
-#endif
 
-// The polynomial coefficients, pinned in registers for the whole epoch loop.
-// ptxas otherwise re-loads each of them from the constant bank on every epoch
-// (17 LDC per iteration), which makes the loop issue-bound instead of FP64-bound.
+// The FP64 constants of the epoch loop, pinned in registers.  Left to itself ptxas
+// re-loads (LDC) or re-materialises (MOV) each of them on every epoch, which costs issue
+// slots; measured: pinned 2.75e9 samples/s, LDC per use 2.61e9, literals 2.57e9.
 struct TrigCoef {
-  double s[7], c[8], m[5];
+  double s[kNSin], c[kNCos], m[5];
+  const SinCos *table;  // kTrigTableSize nodes, sin/cos(2 pi j / size); null without a table
   // `zero` must be a run-time 0.0 (a kernel parameter): coefficient + zero is an
   // FP64 result ptxas will not rematerialise, so the values stay in registers.
-  TJB_HD void load(double zero) {
-#if (TJB_COEF_MODE == 1 || TJB_COEF_MODE == 2) && defined(__CUDA_ARCH__)
-    (void)zero;
-    return;
-#endif
+  TJB_HD void load(double zero, const SinCos *tab) {
+    table = tab;
 #pragma unroll
-    for (int i = 0; i < 7; i++) s[i] = kSinC[i] + zero;
+    for (int i = 0; i < kNSin; i++) s[i] = kSinC[i] + zero;
 #pragma unroll
-    for (int i = 0; i < 8; i++) c[i] = kCosC[i] + zero;
+    for (int i = 0; i < kNCos; i++) c[i] = kCosC[i] + zero;
 #pragma unroll
     for (int i = 0; i < 5; i++) m[i] = kMisc[i] + zero;
   }
 };
 
-// sin and cos of (k + w) * pi/2 for |w| <= 0.5 and integer quadrant k (any int).
-TJB_HD void sincos_quarter(const TrigCoef &tc, double w, int k, double &s, double &c) {
-  const double w2 = w * w;
-  double ps = fma(TJB_SC(6), w2, TJB_SC(5));
-  double pc = fma(TJB_CC(7), w2, TJB_CC(6));
-  ps = fma(ps, w2, TJB_SC(4));
-  pc = fma(pc, w2, TJB_CC(5));
-  ps = fma(ps, w2, TJB_SC(3));
-  pc = fma(pc, w2, TJB_CC(4));
-  ps = fma(ps, w2, TJB_SC(2));
-  pc = fma(pc, w2, TJB_CC(3));
-  ps = fma(ps, w2, TJB_SC(1));
-  pc = fma(pc, w2, TJB_CC(2));
-  ps = fma(ps, w2, TJB_SC(0));
-  pc = fma(pc, w2, TJB_CC(1));
-  const double sx = ps * w;
-  const double cx = fma(pc, w2, 1.0);
+// sin and cos of an angle v given in angle units (1/kUnitsPerRev revolution), any size
+// up to 2^51: exact reduction by magic-number rounding.
+TJB_HD void sincos_units(const TrigCoef &tc, double v, double &s, double &c) {
+  const double tv = v + kMagic;
+  const double r = v - (tv - kMagic);  // in [-0.5, 0.5]
+  const int k = lo32(tv);              // nearest node / quadrant (mod 2^32)
+  const double r2 = r * r;
+#if TJB_TRIG_TABLE
+  const SinCos node = tc.table[k & (kTrigTableSize - 1)];
+  const double sr = r * fma(r2, fma(r2, TJB_SC(2), TJB_SC(1)), TJB_SC(0));
+  const double cr = fma(r2, fma(r2, TJB_CC(2), TJB_CC(1)), 1.0);
+  s = fma(node.c, sr, node.s * cr);
+  c = fma(-node.s, sr, node.c * cr);
+#else
+  double ps = fma(TJB_SC(6), r2, TJB_SC(5));
+  double pc = fma(TJB_CC(7), r2, TJB_CC(6));
+  ps = fma(ps, r2, TJB_SC(4));
+  pc = fma(pc, r2, TJB_CC(5));
+  ps = fma(ps, r2, TJB_SC(3));
+  pc = fma(pc, r2, TJB_CC(4));
+  ps = fma(ps, r2, TJB_SC(2));
+  pc = fma(pc, r2, TJB_CC(3));
+  ps = fma(ps, r2, TJB_SC(1));
+  pc = fma(pc, r2, TJB_CC(2));
+  ps = fma(ps, r2, TJB_SC(0));
+  pc = fma(pc, r2, TJB_CC(1));
+  const double sx = ps * r;
+  const double cx = fma(pc, r2, 1.0);
   // quadrant rotation: k=0 (s,c) k=1 (c,-s) k=2 (-s,-c) k=3 (-c,s)
   const bool swap = k & 1;
   const double s0 = swap ? cx : sx;
@@ -193,12 +203,13 @@ TJB_HD void sincos_quarter(const TrigCoef &tc, double w, int k, double &s, doubl
   // sign flips on the high words (integer pipe): bit1 of k for sin, bit1 of k+1 for cos
   s = mk64(hi32(s0) ^ ((k << 30) & 0x80000000), lo32(s0));
   c = mk64(hi32(c0) ^ (((k + 1) << 30) & 0x80000000), lo32(c0));
+#endif
 }
 
 // per-sample constants of the Kepler / RV evaluation
 struct OrbitConsts {
-  double nu4;   // 4 / P            [quarter-revolutions per day]
-  double ph4;   // M0 * 2/pi        [quarter-revolutions]
+  double nu;    // kUnitsPerRev / P            [angle units per day]
+  double ph;    // M0 * kUnitsPerRad           [angle units]
   double e;     // eccentricity
   double e6;    // e / 6
   double a;     // cos(omega)
@@ -211,16 +222,14 @@ struct OrbitConsts {
 TJB_HD OrbitConsts make_orbit_consts(const TrigCoef &tc, double P, double e, double omega,
                                      double M0) {
   OrbitConsts oc;
-  oc.nu4 = 4.0 / P;
-  oc.ph4 = M0 * kTwoOverPi;
+  oc.nu = kUnitsPerRev / P;
+  oc.ph = M0 * kUnitsPerRad;
   oc.e = e;
   oc.e6 = e * (1.0 / 6.0);
-  // sin / cos of omega through the same quarter-revolution reduction as the epochs
-  // (|omega| is a few radians; the product with 2/pi costs < 1e-15 rad)
-  const double o4 = omega * kTwoOverPi;
-  const double to = o4 + kMagic;
+  // sin / cos of omega through the same reduction as the epochs (|omega| is a few
+  // radians; the product with kUnitsPerRad costs < 1e-15 rad)
   double so, co;
-  sincos_quarter(tc, o4 - (to - kMagic), lo32(to), so, co);
+  sincos_units(tc, omega * kUnitsPerRad, so, co);
   oc.a = co;
   oc.b = -sqrt(fma(-e, e, 1.0)) * so;
   oc.ea = e * co;
@@ -289,7 +298,7 @@ TJB_HD void rotate_small(const TrigCoef &tc, double del, double &sE, double &cE)
 template <int K, bool kCountStats>
 TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const double *dt, double *z,
                             SolveStats *st, unsigned long long *gstats = nullptr) {
-  double x4[K], D[K], sE[K], cE[K];
+  double x4[K], D[K], sE[K], cE[K];  // x4: mean anomaly in angle units (unreduced)
   float Df[K];
 
   // ---- FP32: reduce, starter D0 = e sinM / sqrt(1 - 2 e cosM + e^2), one
@@ -298,10 +307,10 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
   const float ef = oc.ef;
 #pragma unroll
   for (int k = 0; k < K; k++) {
-    x4[k] = fma(dt[k], oc.nu4, -oc.ph4);  // mean anomaly in quarter-revolutions (unreduced)
+    x4[k] = fma(dt[k], oc.nu, -oc.ph);
     const float x4f = (float)x4[k];
-    const float r4 = (x4f * 0.25f + kMagicF) - kMagicF;      // nearest whole revolution
-    const float Mf = fmaf(r4, -4.0f, x4f) * 1.57079632679f;  // M in [-pi, pi]
+    const float r4 = (x4f * (float)(1.0 / kUnitsPerRev) + kMagicF) - kMagicF;  // whole revolutions
+    const float Mf = fmaf(r4, -(float)kUnitsPerRev, x4f) * (float)kRadPerUnit;  // M in [-pi, pi]
     const float sM = fsin_approx(Mf), cM = fcos_approx(Mf);
     const float D0 = ef * sM * frsqrt_approx(fmaf(-2.0f * ef, cM, oc.g0f));
     const float Ef = Mf + D0;
@@ -320,11 +329,8 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
   bool any_need = false;
 #pragma unroll
   for (int k = 0; k < K; k++) {
-    const double d4 = (double)(Df[k] * 0.63661977236f);  // D0 in quarter-revolutions
-    const double v = x4[k] + d4;
-    const double tv = v + kMagic;
-    const double w = v - (tv - kMagic);  // in [-0.5, 0.5]
-    sincos_quarter(tc, w, lo32(tv), sE[k], cE[k]);
+    const double d4 = (double)(Df[k] * (float)kUnitsPerRad);  // D0 in angle units
+    sincos_units(tc, x4[k] + d4, sE[k], cE[k]);
     D[k] = d4 * TJB_MC(4);  // E0 - M [rad]
     del[k] = householder3(oc, D[k], sE[k], cE[k]);
     // error map of the step: eps -> ~C eps^4 (tools/kepler_solver_study.py); a lane
@@ -348,10 +354,8 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
       bool nd = need[k];
       double Dk = D[k] + del[k];
       for (int it = 1; it < kF64MaxIter && any_lane(nd); ++it) {
-        const double v2 = fma(Dk, TJB_MC(3), x4[k]);
-        const double tv2 = v2 + kMagic;
         double s2, c2;
-        sincos_quarter(tc, v2 - (tv2 - kMagic), lo32(tv2), s2, c2);
+        sincos_units(tc, fma(Dk, TJB_MC(3), x4[k]), s2, c2);
         const double d2 = householder3(oc, Dk, s2, c2);
         if (nd) {
           if (kCountStats) st->extra_f64++;
@@ -368,9 +372,7 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
       if (nd) {  // did not converge within kF64MaxIter passes: best estimate, counted
         if (kCountStats) st->not_converged++;
         count_event(gstats, 1);
-        const double v2 = fma(Dk, TJB_MC(3), x4[k]);
-        const double tv2 = v2 + kMagic;
-        sincos_quarter(tc, v2 - (tv2 - kMagic), lo32(tv2), sR, cR);
+        sincos_units(tc, fma(Dk, TJB_MC(3), x4[k]), sR, cR);
       }
       sE[k] = sR;
       cE[k] = cR;

@@ -55,7 +55,7 @@ struct StarParams {
   double sigma_K0_sq, inv_P0, max_K_sq;
   int apply_jitter;                 // kJit kernels: 0 -> treat s as 0 (reference behaviour)
   double zero;                      // run-time 0.0, see TrigCoef::load
-  TrigCoef trig;                    // polynomial coefficients as kernel-parameter constants
+  const SinCos *trig_table;         // device, kTrigTableSize nodes (null for the polynomial back-end)
   unsigned long long *stats;        // device counters of the solver's rare path (may be null)
 };
 
@@ -99,15 +99,12 @@ struct LogProduct {
 // ---- per-sample evaluation -------------------------------------------------
 // Returns ll for one prior sample.  `tab` is the staged epoch table.
 template <int L, bool kJit>
-TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab, double P, double e,
-                        double omega, double M0, double s) {
+TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab,
+                        const SinCos *__restrict__ trig, double P, double e, double omega,
+                        double M0, double s) {
   constexpr int RS = row_stride(L);
-#if TJB_COEF_MODE == 3 && defined(__CUDA_ARCH__)
-  const TrigCoef &tc = sp.trig;  // constant-bank (kernel parameter) operands
-#else
   TrigCoef tc;
-  tc.load(sp.zero);
-#endif
+  tc.load(sp.zero, trig);
   const OrbitConsts oc = make_orbit_consts(tc, P, e, omega, M0);
   const int N = sp.n_times;
 
@@ -242,7 +239,10 @@ template <int L, bool kJit>
 __global__ void __launch_bounds__(kLLThreads, TJB_LL_MIN_CTAS)
 marginal_ll_kernel(const __grid_constant__ StarParams sp, const PriorView pv, const long long n,
                    double *__restrict__ ll_out, long long *__restrict__ llmax_key) {
-  extern __shared__ double tab[];
+  // dynamic shared memory: [trig table (16 KB, 16-byte aligned) | epoch table]
+  extern __shared__ SinCos smem_trig[];
+  double *tab = reinterpret_cast<double *>(smem_trig + kTrigTableSize);
+  for (int i = threadIdx.x; i < kTrigTableSize; i += blockDim.x) smem_trig[i] = sp.trig_table[i];
   const int tab_len = sp.n_times * row_stride(L);
   for (int i = threadIdx.x; i < tab_len; i += blockDim.x) tab[i] = sp.table[i];
   __syncthreads();
@@ -263,7 +263,7 @@ marginal_ll_kernel(const __grid_constant__ StarParams sp, const PriorView pv, co
       P = pv.P[ii]; e = pv.e[ii]; om = pv.omega[ii]; M0 = pv.M0[ii];
       s = (kJit && pv.s) ? pv.s[ii] : 0.0;
     }
-    const double v = sample_ll<L, kJit>(sp, tab, P, e, om, M0, s);
+    const double v = sample_ll<L, kJit>(sp, tab, smem_trig, P, e, om, M0, s);
     if (valid) {
       ll_out[i] = v;
       const long long k = ll_to_key(v);

@@ -30,7 +30,7 @@ posterior_kernel(const StarParams sp, const double *__restrict__ rows, const int
   const double P = rows[5 * r + 0], e = rows[5 * r + 1], om = rows[5 * r + 2],
                M0 = rows[5 * r + 3], s = rows[5 * r + 4];
   TrigCoef tc;
-  tc.load(sp.zero);
+  tc.load(sp.zero, sp.trig_table);  // a few rows only: the table is read from global memory
   const OrbitConsts oc = make_orbit_consts(tc, P, e, om, M0);
   const double s2 = sp.apply_jitter ? s * s : 0.0;
 
@@ -128,10 +128,10 @@ posterior_kernel(const StarParams sp, const double *__restrict__ rows, const int
 // z[n] for one sample, computed by every lane of one warp (lane 0 writes)
 __global__ void design_column_kernel(const double *__restrict__ dt, const int N, const double P,
                                      const double e, const double om, const double M0,
-                                     const double zero, double *__restrict__ z,
-                                     int *__restrict__ stats) {
+                                     const double zero, const SinCos *__restrict__ trig,
+                                     double *__restrict__ z, int *__restrict__ stats) {
   TrigCoef tc;
-  tc.load(zero);
+  tc.load(zero, trig);
   const OrbitConsts oc = make_orbit_consts(tc, P, e, om, M0);
   SolveStats st = {0, 0, 0};
   for (int n = 0; n < N; n++) {

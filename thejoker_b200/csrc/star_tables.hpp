@@ -59,8 +59,24 @@ inline void star_fill_common(const StarHost &st, StarParams &sp) {
   sp.max_K_sq = st.max_K * st.max_K;
   sp.apply_jitter = st.jitter_mode;
   sp.zero = 0.0;
-  sp.trig.load(0.0);  // host copy of the polynomial coefficients (TJB_COEF_MODE 3)
   for (int i = 1; i < st.L; i++) sp.inv_Lambda[i] = (double)(1.0L / (long double)st.Lambda[i]);
+}
+
+// sin / cos at the kTrigTableSize nodes of the trig table, correctly rounded from long double
+inline std::vector<SinCos> make_trig_table() {
+  std::vector<SinCos> t(kTrigTableSize > 0 ? kTrigTableSize : 1);
+  const long double two_pi = 6.283185307179586476925286766559005768L;
+  for (int j = 0; j < kTrigTableSize; j++) {
+    // exact octant symmetry: evaluate in the first octant-ish range for best accuracy
+    const long double ang = two_pi * (long double)j / (long double)kTrigTableSize;
+    t[j].s = (double)sinl(ang);
+    t[j].c = (double)cosl(ang);
+  }
+  if (kTrigTableSize >= 4) {  // the four axis nodes exactly
+    const int q = kTrigTableSize / 4;
+    t[0] = {0.0, 1.0}; t[q] = {1.0, 0.0}; t[2 * q] = {0.0, -1.0}; t[3 * q] = {-1.0, 0.0};
+  }
+  return t;
 }
 
 constexpr long double kLog2PiL = 1.8378770664093454835606594728112353L;

@@ -67,7 +67,7 @@ struct TjbHandle {
   bool const_valid = false;
   double const_s = 0;
   // scratch
-  DevBuf acc_mask, acc_counts, acc_offsets, acc_totals, misc, stats;
+  DevBuf acc_mask, acc_counts, acc_offsets, acc_totals, misc, stats, trig;
   DevBuf host_stage[2], host_ll[2];
   cudaStream_t aux_stream[2] = {nullptr, nullptr};
   int ll_ctas_per_sm = 0;
@@ -84,6 +84,7 @@ int upload_table(TjbHandle *h, DevBuf &buf, const std::vector<double> &tab, Star
   CU(cudaStreamSynchronize(h->stream));  // tab is a caller-owned staging buffer
   sp.table = (const double *)buf.p;
   sp.stats = (unsigned long long *)h->stats.p;
+  sp.trig_table = (const SinCos *)h->trig.p;
   return TJB_OK;
 }
 
@@ -110,7 +111,8 @@ template <int L, bool J>
 int launch_ll(TjbHandle *h, const StarParams &sp, const PriorView &pv, long long n, double *d_ll,
               long long *d_key, cudaStream_t stream) {
   auto kern = marginal_ll_kernel<L, J>;
-  const size_t smem = (size_t)h->N * row_stride(L) * sizeof(double);
+  const size_t smem = (size_t)kTrigTableSize * sizeof(SinCos) +
+                      (size_t)h->N * row_stride(L) * sizeof(double);
   if (smem > 227 * 1024)
     return fail(TJB_E_INVALID, "epoch table does not fit in shared memory (too many epochs)");
   if (smem > 48 * 1024)
@@ -273,6 +275,15 @@ int tjb_create(const TjbSpec *spec, int device, TjbHandle **out) {
     tjb_destroy(h);
     return fail(TJB_E_NOMEM, "cudaMalloc stats");
   }
+  {
+    const std::vector<SinCos> tt = make_trig_table();
+    if (h->trig.ensure(tt.size() * sizeof(SinCos)) ||
+        cudaMemcpy(h->trig.p, tt.data(), tt.size() * sizeof(SinCos), cudaMemcpyHostToDevice) !=
+            cudaSuccess) {
+      tjb_destroy(h);
+      return fail(TJB_E_NOMEM, "cudaMalloc trig table");
+    }
+  }
   rc = load_star(h, spec);
   if (rc != TJB_OK) {
     tjb_destroy(h);
@@ -296,7 +307,7 @@ void tjb_destroy(TjbHandle *h) {
   cudaSetDevice(h->device);
   h->tab_const.release(); h->tab_jit.release();
   h->acc_mask.release(); h->acc_counts.release(); h->acc_offsets.release();
-  h->acc_totals.release(); h->misc.release(); h->stats.release();
+  h->acc_totals.release(); h->misc.release(); h->stats.release(); h->trig.release();
   for (int i = 0; i < 2; i++) {
     h->host_stage[i].release(); h->host_ll[i].release();
     if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]);
@@ -594,7 +605,8 @@ int tjb_design_column(TjbHandle *h, const double *h_row, double *h_z, int32_t *h
   std::vector<double> dt(N);
   for (int n = 0; n < N; n++) dt[n] = h->star.t[n] - h->star.t_ref;
   CU(cudaMemcpyAsync(d_dt, dt.data(), (size_t)N * 8, cudaMemcpyHostToDevice, h->stream));
-  design_column_kernel<<<1, 32, 0, h->stream>>>(d_dt, N, h_row[0], h_row[1], h_row[2], h_row[3], 0.0, d_z,
+  design_column_kernel<<<1, 32, 0, h->stream>>>(d_dt, N, h_row[0], h_row[1], h_row[2], h_row[3], 0.0,
+                                              (const SinCos *)h->trig.p, d_z,
                                               d_st);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(h_z, d_z, (size_t)N * 8, cudaMemcpyDeviceToHost, h->stream));

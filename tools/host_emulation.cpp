@@ -9,13 +9,18 @@
 
 using namespace tjb;
 
+static const std::vector<SinCos> &trig_table() {
+  static const std::vector<SinCos> t = make_trig_table();
+  return t;
+}
+
 template <int L>
 static void run(const StarParams &sp, const double *tab, bool jit, const double *chunk, long n,
                 double *ll) {
   for (long i = 0; i < n; i++) {
     const double *r = chunk + 5 * i;
-    ll[i] = jit ? sample_ll<L, true>(sp, tab, r[0], r[1], r[2], r[3], r[4])
-                : sample_ll<L, false>(sp, tab, r[0], r[1], r[2], r[3], r[4]);
+    ll[i] = jit ? sample_ll<L, true>(sp, tab, trig_table().data(), r[0], r[1], r[2], r[3], r[4])
+                : sample_ll<L, false>(sp, tab, trig_table().data(), r[0], r[1], r[2], r[3], r[4]);
   }
 }
 
@@ -26,16 +31,17 @@ void emu_design_column(double P, double e, double omega, double M0, const double
                        double *z, int *stats) {
   SolveStats st = {0, 0, 0};
   TrigCoef tc;
-  tc.load(0.0);
+  tc.load(0.0, trig_table().data());
   OrbitConsts oc = make_orbit_consts(tc, P, e, omega, M0);
   for (int n = 0; n < N; n++) z[n] = rv_unit_column<true>(oc, tc, dt[n], &st);
   if (stats) { stats[0] = st.extra_f32; stats[1] = st.extra_f64; stats[2] = st.not_converged; }
 }
 
-void emu_sincos_quarter(double w, int k, double *s, double *c) {
+// sin / cos of an angle given in revolutions (scaled to the back-end's angle unit)
+void emu_sincos_rev(double rev, double *s, double *c) {
   TrigCoef tc;
-  tc.load(0.0);
-  sincos_quarter(tc, w, k, *s, *c);
+  tc.load(0.0, trig_table().data());
+  sincos_units(tc, rev * kUnitsPerRev, *s, *c);
 }
 
 // ll for a chunk through the same code path selection as tjb_api.cu::run_ll:
