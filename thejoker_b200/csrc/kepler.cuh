@@ -56,9 +56,12 @@ namespace tjb {
 constexpr double kMagic = 6755399441055744.0;
 constexpr float kMagicF = 12582912.0f;
 constexpr double kTwoPi = 6.28318530717958647692528676655900577;
+#ifndef TJB_TRIG_TABLE_LOG2
+#define TJB_TRIG_TABLE_LOG2 10
+#endif
 #if TJB_TRIG_TABLE
-constexpr int kTrigTableSize = 1024;
-constexpr double kUnitsPerRev = 1024.0;
+constexpr int kTrigTableSize = 1 << TJB_TRIG_TABLE_LOG2;
+constexpr double kUnitsPerRev = (double)kTrigTableSize;
 #else
 constexpr int kTrigTableSize = 0;
 constexpr double kUnitsPerRev = 4.0;
@@ -77,7 +80,9 @@ struct alignas(16) SinCos {
 #endif
 #if TJB_TRIG_TABLE
 // sin(r h) = r (S0 + S1 r^2 + S2 r^4), cos(r h) = 1 + C1 r^2 + C2 r^4 for |r| <= 1/2,
-// h = 2 pi / 1024 (Taylor; truncation 5e-22 and 1.2e-18)
+// h = 2 pi / table size (Taylor; truncation 5e-22 and 1.2e-18 at 1024 nodes).  From 4096
+// nodes on the r^5 term of the sine is below 3e-18 and is dropped.
+constexpr bool kSinQuintic = kTrigTableSize < 4096;
 constexpr int kNSin = 3, kNCos = 3;
 TJB_COEF double kSinC[3] = {kRadPerUnit, -(kRadPerUnit * kRadPerUnit * kRadPerUnit) / 6.0,
                             (kRadPerUnit * kRadPerUnit * kRadPerUnit * kRadPerUnit * kRadPerUnit) /
@@ -177,7 +182,8 @@ TJB_HD void sincos_units(const TrigCoef &tc, double v, double &s, double &c) {
   const double r2 = r * r;
 #if TJB_TRIG_TABLE
   const SinCos node = tc.table[k & (kTrigTableSize - 1)];
-  const double sr = r * fma(r2, fma(r2, TJB_SC(2), TJB_SC(1)), TJB_SC(0));
+  const double sr = kSinQuintic ? r * fma(r2, fma(r2, TJB_SC(2), TJB_SC(1)), TJB_SC(0))
+                                : r * fma(r2, TJB_SC(1), TJB_SC(0));
   const double cr = fma(r2, fma(r2, TJB_CC(2), TJB_CC(1)), 1.0);
   s = fma(node.c, sr, node.s * cr);
   c = fma(-node.s, sr, node.c * cr);
