@@ -128,11 +128,18 @@ class DeviceEngine:
         self.shards = []
         for d, (lo, hi) in zip(devices, shard_ranges(n_local, len(devices))):
             with torch.cuda.device(d):
+                torch.cuda.current_stream().synchronize()
+
                 def up(a):
                     a = np.ascontiguousarray(a[lo:hi], dtype=np.float64)
                     if not a.flags.writeable:  # memory-mapped cache columns are read-only
                         a = a.copy()
-                    return torch.from_numpy(a).to(f"cuda:{d}", non_blocking=False)
+                    t = torch.from_numpy(a)
+                    if t.numel() >= (1 << 20):
+                        # stage through page-locked memory: one host memcpy + a full-rate
+                        # DMA beats the driver's pageable path for large columns
+                        t = t.pin_memory()
+                    return t.to(f"cuda:{d}", non_blocking=True)
 
                 cols = [up(P), up(e), up(om), up(M0)]
                 s_dev = None if s_is_scalar else up(s)
