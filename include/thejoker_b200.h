@@ -86,6 +86,13 @@ int tjb_device_info(TjbHandle *h, int *n_sm, int *ctas_per_sm, int *cc_major, in
 int tjb_marginal_ll_soa(TjbHandle *h, const double *d_P, const double *d_e,
                         const double *d_omega, const double *d_M0, const double *d_s,
                         double s_const, int64_t n, double *d_ll, int64_t *d_llmax_key);
+/* Fused max exchange for one process driving several GPUs: besides the key passed per
+ * call, every likelihood launch of this handle also max-updates the n given keys, which
+ * live on the listed peer devices (NVLink peer access is enabled here).  After all
+ * shards' kernels have completed, each GPU's key holds the max over all shards -- the
+ * master-side ``lls.max()`` of multiproc_helpers.py:256-258 without a collective call.
+ * n = 0 clears the list. */
+int tjb_set_peer_keys(TjbHandle *h, int64_t *const *d_peer_keys, const int *peer_devices, int n);
 /* Prior rows packed as the reference packs them: d_chunk[n,5] row-major
  * [P, e, omega, M0, s] (pyx:41, 448-451).  uniform_s != 0 promises that column 4
  * is the same for all rows (the host layer checks), enabling the constant-jitter

@@ -50,6 +50,18 @@ def test_one_process_two_gpus():
     b = _run(tj.TheJoker(prior, rng=np.random.default_rng(42), devices=[0, 1]), flat, ps)
     for k in a:
         assert np.array_equal(a[k], b[k]), k
+    # the max exchange is fused into the kernel epilogue over NVLink peer stores
+    from thejoker_b200.sharding import DeviceEngine
+    j2 = tj.TheJoker(prior, rng=np.random.default_rng(42), devices=[0, 1])
+    helper0 = j2._make_joker_helper(flat)
+    cols, _ = j2._columns(helper0, ps)
+    eng, _ = j2._engine(flat, cols)
+    assert isinstance(eng, DeviceEngine) and eng.peer_max
+    eng.compute_ll()
+    eng.global_max_key()
+    eng.synchronize()
+    want = float(np.max(a["ll"]))
+    assert [sh.helper.llmax_value(sh.key) for sh in eng.shards] == [want, want]
 
 
 def _worker(rank, world, port, out_dir):

@@ -61,6 +61,8 @@ SYMBOLS = {
     "tjb_device_info": (ctypes.c_int, [_H] + [ctypes.POINTER(ctypes.c_int)] * 4),
     "tjb_marginal_ll_soa": (ctypes.c_int, [_H, _vp, _vp, _vp, _vp, _vp, ctypes.c_double,
                                            ctypes.c_int64, _vp, _vp]),
+    "tjb_set_peer_keys": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_void_p),
+                                         ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
     "tjb_marginal_ll_aos": (ctypes.c_int, [_H, _vp, ctypes.c_int, ctypes.c_int64, _vp, _vp]),
     "tjb_marginal_ll_host": (ctypes.c_int, [_H, _vp, ctypes.c_int64, _vp]),
     "tjb_marginal_ll_host_soa": (ctypes.c_int, [_H, _vp, _vp, _vp, _vp, _vp, ctypes.c_double,

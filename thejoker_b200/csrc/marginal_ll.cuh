@@ -59,6 +59,19 @@ struct StarParams {
   unsigned long long *stats;        // device counters of the solver's rare path (may be null)
 };
 
+// Where the likelihood kernel publishes its running max.  keys[0..n) are int64 max-keys
+// on this GPU and, through NVLink peer mappings, on the other GPUs that hold shards of
+// the same prior cache: every CTA max-updates all of them with system-scope atomics, so
+// when all shards' kernels have finished each GPU's own key already holds the global
+// max -- the max "all-reduce" of the accept step is fused into the kernel's epilogue and
+// no separate collective or host round trip is needed (one process driving several
+// GPUs; one rank per GPU goes through NCCL instead, sharding.py).
+constexpr int kMaxPeers = 16;
+struct MaxKeys {
+  long long *keys[kMaxPeers];
+  int n;
+};
+
 // order-preserving int64 key of a double: key(a) < key(b) <=> a < b, NaN above +inf
 // (so a max-reduction propagates NaN the way numpy.max does).
 TJB_HD long long ll_to_key(double x) {
@@ -238,7 +251,7 @@ constexpr int kLLThreads = TJB_LL_THREADS;
 template <int L, bool kJit>
 __global__ void __launch_bounds__(kLLThreads, TJB_LL_MIN_CTAS)
 marginal_ll_kernel(const __grid_constant__ StarParams sp, const PriorView pv, const long long n,
-                   double *__restrict__ ll_out, long long *__restrict__ llmax_key) {
+                   double *__restrict__ ll_out, const MaxKeys mk) {
   // dynamic shared memory: [trig table (16 KB, 16-byte aligned) | epoch table]
   extern __shared__ SinCos smem_trig[];
   double *tab = reinterpret_cast<double *>(smem_trig + kTrigTableSize);
@@ -271,7 +284,7 @@ marginal_ll_kernel(const __grid_constant__ StarParams sp, const PriorView pv, co
     }
   }
 
-  if (llmax_key) {
+  if (mk.n > 0) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const long long other = __shfl_xor_sync(0xffffffffu, kmax, o);
@@ -284,7 +297,8 @@ marginal_ll_kernel(const __grid_constant__ StarParams sp, const PriorView pv, co
       long long m = wmax[0];
 #pragma unroll
       for (int w = 1; w < kLLThreads / 32; w++) m = wmax[w] > m ? wmax[w] : m;
-      atomicMax(llmax_key, m);
+      atomicMax(mk.keys[0], m);
+      for (int p = 1; p < mk.n; p++) atomicMax_system(mk.keys[p], m);
     }
   }
 }

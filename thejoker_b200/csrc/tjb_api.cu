@@ -71,6 +71,9 @@ struct TjbHandle {
   DevBuf host_stage[2], host_ll[2];
   cudaStream_t aux_stream[2] = {nullptr, nullptr};
   int ll_ctas_per_sm = 0;
+  // extra (peer) keys the likelihood kernel max-updates besides the one passed per call
+  long long *peer_keys[kMaxPeers] = {nullptr};
+  int n_peer_keys = 0;
 };
 
 namespace {
@@ -123,7 +126,13 @@ int launch_ll(TjbHandle *h, const StarParams &sp, const PriorView &pv, long long
   h->ll_ctas_per_sm = per_sm;
   const long long want = (n + kLLThreads - 1) / kLLThreads;
   const int grid = (int)std::max(1LL, std::min(want, (long long)h->n_sm * per_sm));
-  kern<<<grid, kLLThreads, smem, stream>>>(sp, pv, n, d_ll, d_key);
+  MaxKeys mk;
+  mk.n = 0;
+  if (d_key) {
+    mk.keys[mk.n++] = d_key;
+    for (int p = 0; p < h->n_peer_keys && mk.n < kMaxPeers; p++) mk.keys[mk.n++] = h->peer_keys[p];
+  }
+  kern<<<grid, kLLThreads, smem, stream>>>(sp, pv, n, d_ll, mk);
   CU(cudaGetLastError());
   return TJB_OK;
 }
@@ -318,6 +327,25 @@ void tjb_destroy(TjbHandle *h) {
 int tjb_set_stream(TjbHandle *h, void *cuda_stream) {
   if (!h) return fail(TJB_E_INVALID, "null handle");
   h->stream = (cudaStream_t)cuda_stream;
+  return TJB_OK;
+}
+
+int tjb_set_peer_keys(TjbHandle *h, int64_t *const *d_peer_keys, const int *peer_devices, int n) {
+  if (!h) return fail(TJB_E_INVALID, "null handle");
+  if (n < 0 || n >= kMaxPeers) return fail(TJB_E_INVALID, "too many peer keys");
+  if (n > 0 && (!d_peer_keys || !peer_devices)) return fail(TJB_E_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  for (int p = 0; p < n; p++) {
+    if (peer_devices[p] == h->device) continue;
+    int can = 0;
+    CU(cudaDeviceCanAccessPeer(&can, h->device, peer_devices[p]));
+    if (!can) return fail(TJB_E_CUDA, "no peer access between the devices");
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_devices[p], 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+    else if (e != cudaSuccess) return fail(TJB_E_CUDA, cudaGetErrorString(e));
+  }
+  h->n_peer_keys = n;
+  for (int p = 0; p < n; p++) h->peer_keys[p] = (long long *)d_peer_keys[p];
   return TJB_OK;
 }
 

@@ -364,6 +364,15 @@ class CJokerHelper:
         _lib.check(self._lib.tjb_llmax_reset(self._h, self._ptr(key)))
         return key
 
+    def set_peer_keys(self, keys):
+        """Max-keys on other GPUs (int64[1] CUDA tensors) that every likelihood launch of
+        this helper also updates, through NVLink peer stores (tjb_set_peer_keys)."""
+        n = len(keys)
+        ptrs = (ctypes.c_void_p * max(n, 1))(*[k.data_ptr() for k in keys])
+        devs = (ctypes.c_int * max(n, 1))(*[k.device.index for k in keys])
+        _lib.check(self._lib.tjb_set_peer_keys(self._h, ptrs, devs, n))
+        self._peer_keys = list(keys)  # keep the tensors alive
+
     def llmax_value(self, key):
         out = ctypes.c_double()
         self._sync_stream()

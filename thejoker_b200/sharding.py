@@ -145,6 +145,21 @@ class DeviceEngine:
                 s_dev = None if s_is_scalar else up(s)
             self._add_shard(make_helper, d, lo, hi, cols, s_dev)
 
+    def _link_peers(self):
+        """One process, several GPUs: let every shard's likelihood kernel publish its
+        max into all the other shards' keys over NVLink (fused max exchange).  Falls back
+        to combining the keys on the host if the GPUs cannot map each other."""
+        self.peer_max = False
+        if self.group is not None or len(self.shards) < 2:
+            return
+        try:
+            for sh in self.shards:
+                sh.helper.set_peer_keys([o.key for o in self.shards if o is not sh])
+            self.peer_max = True
+        except Exception:
+            for sh in self.shards:
+                sh.helper.set_peer_keys([])
+
     def _add_shard(self, make_helper, d, lo, hi, cols, s_dev):
         torch = self.torch
         sh = _Shard()
@@ -176,6 +191,7 @@ class DeviceEngine:
         self.n_local = lo
         self.global_offset = int(global_offset)
         self.n_global = int(lo if global_size is None else global_size)
+        self._link_peers()
         return self
 
     def rows(self, local_idx):
@@ -217,9 +233,10 @@ class DeviceEngine:
             self.compute_ll(lo, hi)
 
     def reset_max(self):
+        self.synchronize()
         for sh in self.shards:
             with self.torch.cuda.device(sh.device):
-                sh.key = sh.helper.new_llmax_key()
+                sh.key.copy_(sh.helper.new_llmax_key())
 
     def synchronize(self):
         for sh in self.shards:
@@ -231,7 +248,20 @@ class DeviceEngine:
         with the global key so the accept kernels read it from device memory."""
         torch = self.torch
         keys = [sh.key for sh in self.shards]
-        if len(keys) > 1:
+        if len(keys) > 1 and getattr(self, "peer_max", False):
+            # every kernel already wrote its max into every GPU's key; what remains is
+            # ordering: each GPU's stream waits for the other GPUs' likelihood kernels
+            events = []
+            for sh in self.shards:
+                with torch.cuda.device(sh.device):
+                    ev = torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream(sh.device))
+                    events.append(ev)
+            for sh in self.shards:
+                st = torch.cuda.current_stream(sh.device)
+                for ev in events:
+                    st.wait_event(ev)
+        elif len(keys) > 1:
             m = max(int(k.item()) for k in keys)
             for k in keys:
                 k.fill_(m)
