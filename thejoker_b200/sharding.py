@@ -144,6 +144,7 @@ class DeviceEngine:
                 cols = [up(P), up(e), up(om), up(M0)]
                 s_dev = None if s_is_scalar else up(s)
             self._add_shard(make_helper, d, lo, hi, cols, s_dev)
+        self._link_peers()
 
     def _link_peers(self):
         """One process, several GPUs: let every shard's likelihood kernel publish its
