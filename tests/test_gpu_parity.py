@@ -576,3 +576,61 @@ def test_prior_cache_path(torch_cuda, tmp_path):
     assert len(a) == len(b) > 10
     for k in ("P", "K", "ln_prior", "ln_likelihood"):
         assert np.array_equal(a[k].value, b[k].value)
+
+
+def test_baseline_config3_jitter_trend(torch_cuda, oracle_lib):
+    """BASELINE.json configs[2] in miniature: N=64, jitter as a nonlinear parameter
+    (LogNormal) + poly_trend=2, rejection sampling; accepted set identical to the
+    correct-jitter oracle fed the same samples and the same generator."""
+    import thejoker_b200 as tj
+    from helpers import default_prior
+    from thejoker_b200 import units as u
+    from thejoker_b200.prior import LogNormal
+    from thejoker_b200.synthetic import make_noisy_data
+
+    prior = default_prior(2, sigma_K0=30.0, s=LogNormal("s", -2.0, 1.0, u.km / u.s))
+    data, _ = make_noisy_data(64, seed=42, K=1e-4)
+    ps = prior.sample(size=1 << 16, rng=np.random.default_rng(1))
+    assert not ps._uniform_s
+    joker = tj.TheJoker(prior, rng=np.random.default_rng(42))
+    helper = joker._make_joker_helper(data)
+    chunk, _ = ps.pack(units=helper.internal_units, names=helper.packed_order)
+    got = joker.rejection_sample(data, ps, in_memory=True, max_posterior_samples=256)
+    orc = oracle_lib.OracleHelper.from_spec(helper.spec)
+    assert helper.spec["jitter_mode"] == 1
+    ref = orc.batch_marginal_ln_likelihood(chunk, 0)
+    uu = np.random.default_rng(42).uniform(size=len(chunk))
+    good = oracle_lib.rejection_accept(ref, uu, 256)
+    if oracle_lib.near_threshold_count(ref, uu) == 0:
+        assert np.array_equal(got["P"].value, chunk[good, 0])
+        assert np.array_equal(got["s"].value, chunk[good, 4])
+    assert list(got.keys())[:8] == ["P", "e", "omega", "M0", "s", "K", "v0", "v1"]
+    ll = joker.marginal_ln_likelihood(data, ps)
+    truth, _ = orc.truth_ll(chunk[:4096])
+    ok, r_ref, r_truth, ref_truth = parity_ok(ll[:4096], ref[:4096], truth)
+    assert ok.all() and r_truth.max() < 1e-10
+
+
+def test_baseline_config4_iterative_n256(torch_cuda, oracle_lib):
+    """BASELINE.json configs[3] in miniature: iterative_rejection_sample, 256 epochs,
+    n_requested_samples=256, flat data; identical to the restated file-path driver
+    (safety_factor 4) run on the oracle's ll."""
+    import thejoker_b200 as tj
+    from helpers import default_prior
+    from thejoker_b200.synthetic import make_noisy_data
+
+    prior = default_prior(1, sigma_K0=30.0)
+    data, _ = make_noisy_data(256, seed=42, K=1e-4)
+    ps = prior.sample(size=1 << 15, rng=np.random.default_rng(1))
+    joker = tj.TheJoker(prior, rng=np.random.default_rng(3))
+    helper = joker._make_joker_helper(data)
+    chunk, _ = ps.pack(units=helper.internal_units, names=helper.packed_order)
+    got = joker.iterative_rejection_sample(data, ps, n_requested_samples=256, growth_factor=16,
+                                           in_memory=False)
+    orc = oracle_lib.OracleHelper.from_spec(helper.spec)
+    idx, all_lls = oracle_lib.iterative_rejection_indices(
+        lambda a, b: orc.batch_marginal_ln_likelihood(chunk[a:b], 0), len(chunk),
+        np.random.default_rng(3), 256, growth_factor=16, safety_factor=4)
+    assert len(got) == len(idx) == 256
+    assert np.array_equal(got["P"].value, chunk[idx, 0])
+    assert joker.last_stats["n_ll_evaluated"] == len(all_lls)
