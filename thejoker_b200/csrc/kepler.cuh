@@ -107,8 +107,8 @@ TJB_COEF double kCosC[8] = {1.0,
                             0.0000004710641505803501879438872,
                             -6.324746678866069891109223e-9};
 #endif
-// 1/6, (unused), (unused), angle units per radian, radians per angle unit
-TJB_COEF double kMisc[5] = {1.0 / 6.0, 1.0 / 24.0, 1.0e-4, kUnitsPerRad, kRadPerUnit};
+// 1/6, angle units per radian, radians per angle unit
+TJB_COEF double kMisc[3] = {1.0 / 6.0, kUnitsPerRad, kRadPerUnit};
 
 // ---- bit helpers / pipe-specific primitives -------------------------------
 #if defined(__CUDA_ARCH__)
@@ -158,7 +158,7 @@ inline double rcp_pos(double x) { return 1.0 / x; }
 // re-loads (LDC) or re-materialises (MOV) each of them on every epoch, which costs issue
 // slots; measured: pinned 2.75e9 samples/s, LDC per use 2.61e9, literals 2.57e9.
 struct TrigCoef {
-  double s[kNSin], c[kNCos], m[5];
+  double s[kNSin], c[kNCos], m[3];
   const SinCos *table;  // kTrigTableSize nodes, sin/cos(2 pi j / size); null without a table
   // `zero` must be a run-time 0.0 (a kernel parameter): coefficient + zero is an
   // FP64 result ptxas will not rematerialise, so the values stay in registers.
@@ -169,7 +169,7 @@ struct TrigCoef {
 #pragma unroll
     for (int i = 0; i < kNCos; i++) c[i] = kCosC[i] + zero;
 #pragma unroll
-    for (int i = 0; i < 5; i++) m[i] = kMisc[i] + zero;
+    for (int i = 0; i < 3; i++) m[i] = kMisc[i] + zero;
   }
 };
 
@@ -259,7 +259,7 @@ struct SolveStats {
 
 // A third-order Householder step maps an error eps to ~C eps^4 with C = O(1) for
 // e <~ 0.95 (tools/kepler_solver_study.py): a lane repeats the pass while it moved by
-// more than 1e-4 (kMisc[2]), at most kF64MaxIter times.
+// 2^-13 (1.2e-4) or more, at most kF64MaxIter times.
 constexpr int kF64MaxIter = 16;
 
 // run-wide solver statistics (device counters, touched only on the rare path):
@@ -337,7 +337,7 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
   for (int k = 0; k < K; k++) {
     const double d4 = (double)(Df[k] * (float)kUnitsPerRad);  // D0 in angle units
     sincos_units(tc, x4[k] + d4, sE[k], cE[k]);
-    D[k] = d4 * TJB_MC(4);  // E0 - M [rad]
+    D[k] = d4 * TJB_MC(2);  // E0 - M [rad]
     del[k] = householder3(oc, D[k], sE[k], cE[k]);
     // error map of the step: eps -> ~C eps^4 (tools/kepler_solver_study.py); a lane
     // that moved by 2^-13 (1.2e-4) or more, or produced a NaN, takes further passes.
@@ -361,7 +361,7 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
       double Dk = D[k] + del[k];
       for (int it = 1; it < kF64MaxIter && any_lane(nd); ++it) {
         double s2, c2;
-        sincos_units(tc, fma(Dk, TJB_MC(3), x4[k]), s2, c2);
+        sincos_units(tc, fma(Dk, TJB_MC(1), x4[k]), s2, c2);
         const double d2 = householder3(oc, Dk, s2, c2);
         if (nd) {
           if (kCountStats) st->extra_f64++;
@@ -378,7 +378,7 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
       if (nd) {  // did not converge within kF64MaxIter passes: best estimate, counted
         if (kCountStats) st->not_converged++;
         count_event(gstats, 1);
-        sincos_units(tc, fma(Dk, TJB_MC(3), x4[k]), sR, cR);
+        sincos_units(tc, fma(Dk, TJB_MC(1), x4[k]), sR, cR);
       }
       sE[k] = sR;
       cE[k] = cR;
