@@ -98,3 +98,27 @@ def test_two_nccl_ranks_spmd(tmp_path):
         got = np.load(tmp_path / f"rank{rank}.npz")
         for k in want:
             assert np.array_equal(want[k], got[k]), (rank, k)
+
+
+def test_multistar_sharded_over_two_gpus():
+    """Stars sharded over two GPUs give the same per-star samples as one GPU (per-star
+    child RNG streams make the result independent of the sharding)."""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    import thejoker_b200 as tj
+    from helpers import default_prior
+    from thejoker_b200.synthetic import make_noisy_data
+
+    prior = default_prior(1, sigma_K0=25.0)
+    ps = prior.sample(size=1 << 15, rng=np.random.default_rng(1))
+    stars = [make_noisy_data(int(n), seed=50 + i, K=1e-4)[0]
+             for i, n in enumerate([12, 20, 9, 33, 16])]
+    a = tj.MultiStarJoker(prior, ps, rng=np.random.default_rng(5), devices=[0]) \
+        .rejection_sample(stars, max_posterior_samples=32)
+    b = tj.MultiStarJoker(prior, ps, rng=np.random.default_rng(5), devices=[0, 1]) \
+        .rejection_sample(stars, max_posterior_samples=32)
+    assert len(a) == len(b) == 5
+    for sa, sb in zip(a, b):
+        assert len(sa) == len(sb) > 0
+        for k in ("P", "K", "v0"):
+            assert np.array_equal(sa[k].value, sb[k].value)
