@@ -507,8 +507,8 @@ def test_multistar_driver_matches_per_star(torch_cuda):
     seqs = np.random.default_rng(77).bit_generator._seed_seq.spawn(6)
     for i, star in enumerate(stars):
         child = np.random.Generator(np.random.PCG64(seqs[i]))
-        ref = tj.TheJoker(prior, rng=child).rejection_sample(star, ps, in_memory=True,
-                                                             max_posterior_samples=64)
+        ref = tj.TheJoker(prior, rng=child, draw="device").rejection_sample(
+            star, ps, in_memory=True, max_posterior_samples=64)
         assert len(ref) == len(out[i]) > 0
         for k in ("P", "e", "K", "v0", "dv0_1"):
             assert np.array_equal(ref[k].value, out[i][k].value), (i, k)

@@ -37,15 +37,19 @@ class MultiStarJoker:
     rng : numpy Generator (PCG64)
     devices : CUDA devices driven by this process
     group : torch.distributed group; stars are sharded over ranks, results gathered
+    draw : how the linear parameters of accepted samples are drawn, see
+        CJokerHelper.batch_get_posterior_samples ("device" by default: with hundreds of
+        accepted samples per star a Python call per row would dominate the star's time)
     """
 
     def __init__(self, prior, prior_samples, rng=None, devices=(0,), jitter_mode="apply",
-                 group=None):
+                 group=None, draw="device"):
         self.prior = prior
         self.rng = np.random.default_rng() if rng is None else rng
         self.devices = list(devices)
         self.jitter_mode = jitter_mode
         self.group = group
+        self.draw = draw
         self._samples = prior_samples
         self._dev = {}      # device -> dict(cols, s, ll, helper)
         self._host_cols = None
@@ -137,7 +141,8 @@ class MultiStarJoker:
                     rows = np.empty((len(good), 5))
                     for j, c in enumerate(self._host_cols):
                         rows[:, j] = c[good]
-                    raw, lls = st["helper"].batch_get_posterior_samples(rows, n_linear_samples, child)
+                    raw, lls = st["helper"].batch_get_posterior_samples(rows, n_linear_samples, child,
+                                                                        draw=self.draw)
                 all_data = prepared[i][0]
                 s = JokerSamples.unpack(raw, st["helper"].internal_units, t_ref=all_data.t_ref,
                                         poly_trend=self.prior.poly_trend,

@@ -50,6 +50,9 @@ class TheJoker:
     tempfile_path : str (optional, unused: no temporary cache file is written)
     devices : list of CUDA device indices (default: [LOCAL_RANK or 0])
     jitter_mode : "apply" | "reference" -- see CJokerHelper
+    draw : "auto" | "numpy" | "device" -- how linear parameters are drawn for accepted
+        samples (CJokerHelper.batch_get_posterior_samples); "auto" reproduces the
+        reference's numbers for up to 4096 accepted samples
     group : torch.distributed process group (optional).  SPMD use under torchrun: every
         rank constructs the same TheJoker (same prior samples, same rng seed) and calls
         the same method; each rank evaluates only its contiguous shard of the prior
@@ -58,7 +61,7 @@ class TheJoker:
     """
 
     def __init__(self, prior, pool=None, rng=None, tempfile_path=None, devices=None,
-                 jitter_mode="apply", group=None):
+                 jitter_mode="apply", group=None, draw="auto"):
         if pool is not None and (not hasattr(pool, "map") or not hasattr(pool, "close")):
             raise TypeError("Input pool object must have .map() and .close() methods.")
         self.pool = pool
@@ -80,6 +83,7 @@ class TheJoker:
         self.devices = list(devices)
         self.jitter_mode = jitter_mode
         self.group = group
+        self.draw = draw  # see CJokerHelper.batch_get_posterior_samples
         self.last_stats = {}
 
     @property
@@ -210,7 +214,7 @@ class TheJoker:
         """make_full_samples_inmem (likelihood_helpers.py:69-88) / make_full_samples
         (multiproc_helpers.py:150-182, with per-task child generators)."""
         if in_memory:
-            raw, _ = helper.batch_get_posterior_samples(rows, n_linear_samples, rng)
+            raw, _ = helper.batch_get_posterior_samples(rows, n_linear_samples, rng, draw=self.draw)
         else:
             n_batches = 1 if n_batches is None else n_batches  # max(1, SerialPool.size)
             tasks = batch_tasks(len(rows), n_batches, arr=rows)
@@ -218,7 +222,8 @@ class TheJoker:
             parts = []
             for task, seq in zip(tasks, sg):
                 child = np.random.Generator(np.random.PCG64(seq))
-                parts.append(helper.batch_get_posterior_samples(task[0], n_linear_samples, child)[0])
+                parts.append(helper.batch_get_posterior_samples(task[0], n_linear_samples, child,
+                                                                draw=self.draw)[0])
             raw = np.concatenate(parts) if parts else np.zeros((0, 5 + helper.n_linear))
         return JokerSamples.unpack(raw, helper.internal_units, t_ref=helper.data.t_ref,
                                    poly_trend=self.prior.poly_trend, n_offsets=self.prior.n_offsets)
