@@ -115,3 +115,18 @@ def emu_marginal_ll(spec, chunk, force_jit=False):
 
 def rel_err(a, b):
     return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def mode_chunk(spec, n=400, sigma=0.5, seed=0):
+    """Prior rows scattered tightly around the true orbit of the synthetic star (the
+    posterior mode): the ill-conditioned regime where chi2 << y^T C^-1 y."""
+    P0 = 51.8239
+    M0p = 2.592 - 2 * np.pi * (spec["t0"] - 51544.5) / P0
+    rng = np.random.default_rng(seed)
+    sc = sigma / 0.5
+    chunk = np.zeros((n, 5))
+    chunk[:, 0] = P0 * (1 + rng.normal(0, 1e-5 * sc, n))
+    chunk[:, 1] = 0.3 + rng.normal(0, 2e-3 * sc, n)
+    chunk[:, 2] = 0.283 + rng.normal(0, 5e-3 * sc, n)
+    chunk[:, 3] = M0p + rng.normal(0, 5e-3 * sc, n)
+    return chunk
