@@ -6,24 +6,34 @@
  * cpu_baseline / --impl reference legs use it, and only as the checker / the
  * timed CPU baseline.
  *
- * PARITY STATUS: "parity unpinned" at the Kepler-solver boundary.  The reference
- * (adrn/thejoker) cannot be imported or compiled in this image (astropy, pymc,
- * pytensor, twobody, h5py, tables, schwimmbad are absent) and holds no numeric
- * golden vectors for this path (its tests compare two implementations that both
- * call twobody, with unseeded prior samples).  The linear-algebra part below
- * follows thejoker/src/fast_likelihood.pyx statement by statement and calls the
- * same LAPACK entry points (scipy.linalg.cython_lapack dgetrf/dgetri/dsysv, bound
- * at run time from Python through orc_set_lapack).  The Kepler part restates the
- * published algorithm of the third-party dependency `twobody` (>=0.9.1, unpinned,
- * twobody/src/twobody.c :: c_rv_from_elements), which is not under /root/reference:
- * Newton iteration on E - e sin E = M from a second-order series starter, tolerance
- * and maxiter as passed by fast_likelihood.pyx:35-36, true anomaly by the half-angle
- * atan2 formula, rv = K (cos(f + omega) + e cos omega).  The sign / phase conventions
- * are pinned inside the reference (samples.py:228-229, thejoker.py:441,
- * _keplerian_orbit.py:642-656).
+ * PARITY STATUS: pinned to the reference's own compiled Cython for everything except
+ * the Kepler solve; "parity unpinned" only at that one third-party function.
+ *   - thejoker/src/fast_likelihood.pyx is translated by Cython and compiled unmodified
+ *     from /root/reference (oracle/ref_build/build_ref.py -> oracle/_ref/, git-ignored)
+ *     and driven through its real CJokerHelper.__init__ and public methods
+ *     (oracle/ref_cython.py; astropy / pymc / pytensor are absent, so duck-typed
+ *     stand-ins satisfy its imports).  On every vector of tests/golden/ref_*.npz
+ *     (tests/golden/make_ref_golden.py) and on fresh seeded inputs
+ *     (tests/test_ref_pinning.py) this file reproduces the reference's ll, a, A, Ainv,
+ *     b, B, Binv and posterior samples BIT FOR BIT.
+ *   - The Kepler part restates the published algorithm of the third-party dependency
+ *     `twobody` (>=0.9.1, unpinned; twobody/src/twobody.c :: c_rv_from_elements), which
+ *     is not under /root/reference and not installed, so the compiled reference above
+ *     links THIS file's orc_rv_from_elements in its place: Newton iteration on
+ *     E - e sin E = M from a second-order series starter, tolerance and maxiter as
+ *     passed by fast_likelihood.pyx:35-36, true anomaly by the half-angle atan2 formula,
+ *     rv = K (cos(f + omega) + e cos omega).  The sign / phase conventions are pinned
+ *     inside the reference (samples.py:228-229, thejoker.py:441,
+ *     _keplerian_orbit.py:642-656); the converged E is defined by the equation to
+ *     kepler_tol = 1e-10 whatever the iteration, and joker_truth.c (quad precision)
+ *     bounds what that leaves.
+ * The linear-algebra part follows the pyx statement by statement and calls the same
+ * LAPACK entry points (scipy.linalg.cython_lapack dgetrf/dgetri/dsysv, bound at run time
+ * from Python through orc_set_lapack).
  *
  * Each function cites the reference lines it follows.
  */
+#include <complex.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -333,7 +343,12 @@ static void prepare_sample(Work *w, const OrcSpec *sp, const double *row, int cl
    * intended semantics (src/tests/py_likelihood.py:17-29, 168-170). */
   memcpy(w->use_ivar, sp->jitter_mode ? w->s_ivar : sp->ivar, sizeof(double) * w->N);
   if (sp->K_prior_kind == 0) {
-    w->Lambda[0] = (sp->sigma_K0 * sp->sigma_K0 / (1 - e * e) * pow(P / sp->P0, -2 / 3.));
+    /* Cython 3 (unpinned in the reference's pyproject.toml:7) types `double ** (-2/3.)` as
+     * possibly complex and emits C99 cpow on (x + 0i); glibc's cpow and pow differ in the
+     * last ulp for some x.  Following the generated code keeps Lambda[0] bit-identical to
+     * the compiled reference (oracle/_ref). */
+    w->Lambda[0] = (sp->sigma_K0 * sp->sigma_K0 / (1 - e * e)) *
+                   creal(cpow(P / sp->P0 + 0.0 * I, -2 / 3. + 0.0 * I));
     if (clamp) w->Lambda[0] = fmin(sp->max_K * sp->max_K, w->Lambda[0]);
   }
 }

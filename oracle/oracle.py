@@ -4,7 +4,10 @@ TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
 cpu_baseline / --impl reference legs of bench.py.  The product package
 (thejoker_b200/) never imports this module.
 
-PARITY STATUS: "parity unpinned" -- see the header of joker_oracle.c.
+PARITY STATUS: pinned bit-for-bit to the reference's own compiled Cython
+(oracle/ref_cython.py, tests/test_ref_pinning.py, tests/golden/ref_*.npz) for everything
+but the Kepler solve, which restates the absent third-party `twobody` and is the one
+"parity unpinned" function -- see the header of joker_oracle.c.
 
 `OracleHelper` mirrors the method surface of the reference's CJokerHelper
 (thejoker/src/fast_likelihood.pyx:70-576) on plain arrays.

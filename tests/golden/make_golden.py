@@ -1,12 +1,13 @@
 """Generates tests/golden/*.npz: small input / output vectors for the hot path.
 
 Source of the numbers: the CPU oracle (oracle/joker_oracle.c, the literal double
-restatement of thejoker/src/fast_likelihood.pyx with scipy's LAPACK) and the quad-
-precision truth (oracle/joker_truth.c).  The reference itself cannot be imported or
-compiled in this image and holds no numeric golden vectors for this path (SURVEY.md
-section 8c), so these fixtures are *self-minted*: parity is "unpinned" with respect
-to the reference binary.  What they pin is (i) the oracle against regressions and
-(ii) the CUDA path against the oracle on machines where only the fixtures travel.
+restatement of thejoker/src/fast_likelihood.pyx with scipy's LAPACK -- itself pinned
+bit-for-bit to the reference's compiled Cython, see make_ref_golden.py and
+tests/test_ref_pinning.py) with the jitter APPLIED (the reference ignores it), and the
+quad-precision truth (oracle/joker_truth.c).  These fixtures are self-minted; the
+reference-minted ones are ref_*.npz.  What they pin is (i) the oracle against
+regressions, (ii) the CUDA path against oracle + truth on machines where only the
+fixtures travel.
 
 Run from the repo root:  python tests/golden/make_golden.py
 """

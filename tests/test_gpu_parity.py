@@ -15,7 +15,11 @@ from helpers import prior_chunk, rel_err, star_spec
 
 pytestmark = pytest.mark.gpu
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+_ALL_NPZ = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+# ref_*.npz: minted by the reference's own compiled Cython (golden/make_ref_golden.py);
+# the others by the oracle + quad truth (golden/make_golden.py)
+GOLDEN = [p for p in _ALL_NPZ if not os.path.basename(p).startswith("ref_")]
+REF_GOLDEN = [p for p in _ALL_NPZ if os.path.basename(p).startswith("ref_")]
 
 
 @pytest.fixture(scope="module")
@@ -71,6 +75,40 @@ def test_golden_vectors(torch_cuda, path):
     idx, tot, near = helper.accept(ll_dev, key, uniforms=torch.from_numpy(z["uniforms"]).cuda())
     if near == 0 and np.max(r_ref) < 1e-12:
         assert np.array_equal(idx.cpu().numpy(), z["good"])
+
+
+@pytest.mark.parametrize("path", REF_GOLDEN, ids=[os.path.basename(p)[:-4] for p in REF_GOLDEN])
+def test_reference_cython_golden_vectors(torch_cuda, path):
+    """Vectors produced by the reference's own compiled fast_likelihood.pyx
+    (tests/golden/make_ref_golden.py).  The reference ignores the jitter column
+    (pyx:458 is a dead store), hence jitter_mode="reference"; its posterior entry points
+    do not clamp Lambda_K at max_K^2 (pyx:519-522, 569-572), hence clamp=False."""
+    import thejoker_b200 as tj
+
+    z = np.load(path)
+    spec = {k: (z[k] if z[k].ndim else z[k].item()) for k in SPEC_KEYS}
+    spec["jitter_mode"] = 0
+    helper = tj.CJokerHelper.from_spec(spec, device=0)
+    chunk = np.ascontiguousarray(z["chunk"])
+    ll = helper.batch_marginal_ln_likelihood(chunk)
+    r = rel_err(ll, z["ref_ll"])
+    flat = "flat" in path  # K = 1e-4: chi2 cancels to ~1e-12 of its terms in the reference
+    assert r.max() < (1e-8 if flat else 1e-10), r.max()
+    n_post = len(z["ref_worker_ll"])
+    lls, a, A = helper.posterior_aA(chunk[:n_post], clamp_K=False)
+    assert np.max(rel_err(lls, z["ref_worker_ll"])) < (1e-8 if flat else 1e-10)
+    assert np.allclose(a, z["ref_worker_a"], rtol=1e-8, atol=1e-10)
+    assert np.allclose(A, z["ref_worker_A"], rtol=1e-7, atol=1e-14)
+    # the reference's own draw: numpy multivariate_normal(a, inv(Ainv)) with the same rng
+    # stream reproduces its linear parameters from the device a / A
+    n_draw = len(z["ref_samples"]) // n_post
+    samples, ll_rep = helper.batch_get_posterior_samples(chunk[:n_post], n_draw,
+                                                         np.random.default_rng(11), draw="numpy",
+                                                         clamp_K=False)
+    assert samples.shape == z["ref_samples"].shape
+    assert np.array_equal(samples[:, :5], z["ref_samples"][:, :5])
+    scale = np.sqrt(np.repeat(np.einsum("nii->ni", z["ref_worker_A"]), n_draw, axis=0))
+    assert np.max(np.abs(samples[:, 5:] - z["ref_samples"][:, 5:]) / scale) < 1e-6
 
 
 CASES = [

@@ -15,7 +15,11 @@ from oracle import py_oracle
 from oracle.oracle import (OracleHelper, batch_tasks_ranges, iterative_rejection_indices,
                            near_threshold_count, rejection_accept)
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+_ALL_NPZ = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+# ref_*.npz: minted by the reference's own compiled Cython (golden/make_ref_golden.py);
+# the others by the oracle + quad truth (golden/make_golden.py)
+GOLDEN = [p for p in _ALL_NPZ if not os.path.basename(p).startswith("ref_")]
+REF_GOLDEN = [p for p in _ALL_NPZ if os.path.basename(p).startswith("ref_")]
 
 
 def _spec_from_npz(z):

@@ -1,0 +1,127 @@
+"""Pins the CPU oracle to the reference's own compiled Cython operator.
+
+tests/golden/ref_*.npz hold outputs of thejoker/src/fast_likelihood.pyx itself --
+translated by Cython and compiled unmodified from /root/reference
+(oracle/ref_build/build_ref.py), driven through CJokerHelper.__init__ and its public
+methods (oracle/ref_cython.py, tests/golden/make_ref_golden.py).  Only twobody's
+c_rv_from_elements is not the reference's code (third party, absent: the oracle's
+restatement is linked in its place).
+
+* against the committed vectors: always (CPU, any machine).
+* against the live extension: when oracle/_ref/ is present (built in the container that
+  has /root/reference; the .so also travels to the GPU box) -- there the comparison is
+  exact (==), on fresh seeded inputs.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+from helpers import prior_chunk, star_spec
+
+from oracle import ref_cython
+from oracle.oracle import OracleHelper
+
+REF_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.npz")))
+SPEC_KEYS = ("t", "rv", "ivar", "t0", "trend_M", "mu", "Lambda", "K_prior_kind", "sigma_K0", "P0",
+             "max_K")
+MATS = ("a", "A", "Ainv", "b", "B", "Binv")
+
+
+def _spec(z):
+    return {k: (z[k] if z[k].ndim else z[k].item()) for k in SPEC_KEYS}
+
+
+def test_reference_vectors_are_committed():
+    assert len(REF_GOLDEN) >= 7
+
+
+@pytest.mark.parametrize("path", REF_GOLDEN, ids=[os.path.basename(p)[4:-4] for p in REF_GOLDEN])
+def test_oracle_matches_reference_vectors(path):
+    """ll, every matrix the worker leaves behind, and the posterior draw (same rng stream).
+    The vectors were bit-identical where they were minted; the tolerance only allows for
+    libm / OpenBLAS kernel dispatch on a different CPU."""
+    z = np.load(path)
+    orc = OracleHelper.from_spec(_spec(z), jitter_mode=0)  # the reference ignores s (pyx:458)
+    ll = orc.batch_marginal_ln_likelihood(z["chunk"])
+    assert np.allclose(ll, z["ref_ll"], rtol=1e-12, atol=0)
+    n_post = len(z["ref_worker_ll"])
+    for i in range(n_post):
+        l = orc.test_likelihood_worker(z["chunk"][i])
+        assert np.isclose(l, z["ref_worker_ll"][i], rtol=1e-12, atol=0)
+        for k in MATS:
+            ref = z["ref_worker_" + k][i]
+            assert np.allclose(getattr(orc, k), ref, rtol=1e-10, atol=1e-14 * np.abs(ref).max()), k
+    n_draw = len(z["ref_samples"]) // n_post
+    samples, lls = orc.batch_get_posterior_samples(z["chunk"][:n_post], n_draw,
+                                                   np.random.default_rng(11))
+    assert samples.shape == z["ref_samples"].shape
+    assert np.allclose(samples, z["ref_samples"], rtol=1e-9, atol=1e-9)
+    assert np.allclose(lls, z["ref_samples_ll"], rtol=1e-12, atol=0)
+
+
+def test_reference_ignores_jitter_and_clamps_only_in_batch_ll():
+    """Two quirks of the reference, read off its own outputs: (i) the jitter column does
+    not enter the likelihood (pyx:458 fills s_ivar, the algebra reads ivar); (ii) only
+    batch_marginal_ln_likelihood clamps Lambda_K at max_K^2 (pyx:464 vs 519-522, 569-572)."""
+    z = np.load([p for p in REF_GOLDEN if "l3_jitter" in p][0])
+    assert np.all(z["chunk"][:, 4] > 0)
+    o0 = OracleHelper.from_spec(_spec(z), jitter_mode=0).batch_marginal_ln_likelihood(z["chunk"])
+    o1 = OracleHelper.from_spec(_spec(z), jitter_mode=1).batch_marginal_ln_likelihood(z["chunk"])
+    assert np.allclose(o0, z["ref_ll"], rtol=1e-12)
+    assert not np.allclose(o1, z["ref_ll"], rtol=1e-3)
+
+
+live = pytest.mark.skipif(not ref_cython.available(),
+                          reason="oracle/_ref not built (needs /root/reference at build time)")
+
+LIVE_CASES = [
+    (16, 1, {}), (64, 1, {}), (3, 1, {"normal_K": 10.0}), (20, 1, {"n_surveys": 2}),
+    (24, 2, {"n_surveys": 3}), (12, 3, {}), (40, 4, {}), (64, 1, {"sigma": 0.01}),
+]
+
+
+@live
+@pytest.mark.parametrize("N,pt,kw", LIVE_CASES)
+def test_oracle_equals_live_reference_cython(N, pt, kw):
+    """Fresh seeded inputs through both, exact equality."""
+    spec, _, _ = star_spec(N, pt, seed=7, **kw)
+    ref = ref_cython.RefCythonHelper(spec, poly_trend=spec["n_poly"], n_offsets=spec["n_offsets"])
+    orc = OracleHelper.from_spec(spec, jitter_mode=0)
+    chunk = prior_chunk(300, seed=99, s_lognormal=(-1.0, 1.0))
+    assert np.array_equal(ref.batch_marginal_ln_likelihood(chunk),
+                          orc.batch_marginal_ln_likelihood(chunk))
+    for row in chunk[:5]:
+        ll_ref, mats = ref.test_likelihood_worker(row)
+        assert ll_ref == orc.test_likelihood_worker(row)
+        for k in MATS:
+            assert np.array_equal(mats[k], getattr(orc, k)), k
+    s_ref, l_ref = ref.batch_get_posterior_samples(chunk[:6], 4, np.random.default_rng(5))
+    s_orc, l_orc = orc.batch_get_posterior_samples(chunk[:6], 4, np.random.default_rng(5))
+    assert np.array_equal(np.asarray(s_ref), s_orc) and np.array_equal(np.asarray(l_ref), l_orc)
+
+
+@live
+def test_live_reference_edge_cases():
+    """Empty chunk; e = 0; a zero inverse variance is a division by zero in B (pyx:317)
+    and comes out non-finite in both; wrong trend_M shape raises ValueError (pyx:175-180)."""
+    spec, _, _ = star_spec(10, 1, seed=3)
+    ref = ref_cython.RefCythonHelper(spec, 1, 0)
+    orc = OracleHelper.from_spec(spec, jitter_mode=0)
+    assert ref.batch_marginal_ln_likelihood(np.zeros((0, 5))).shape == (0,)
+    chunk = prior_chunk(16, seed=1)
+    chunk[:, 1] = 0.0
+    assert np.array_equal(ref.batch_marginal_ln_likelihood(chunk),
+                          orc.batch_marginal_ln_likelihood(chunk))
+    bad = dict(spec)
+    bad["trend_M"] = np.ones((10, 2))
+    with pytest.raises(ValueError):
+        ref_cython.RefCythonHelper(bad, 1, 0)
+
+
+@live
+def test_shims_do_not_leak_into_the_process():
+    import sys
+
+    ref_cython.load()
+    assert "astropy" not in sys.modules and "thejoker" not in sys.modules
