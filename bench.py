@@ -415,7 +415,9 @@ def cpu_arm(cores):
     else the oracle port."""
     from oracle import ref_cython
 
-    return ReferencePool(cores) if ref_cython.available() else PortPool(cores)
+    want = os.environ.get("TJB_BENCH_CPU_ARM", "auto")  # "port" forces the restatement
+    use_ref = want == "reference" or (want == "auto" and ref_cython.available())
+    return ReferencePool(cores) if use_ref else PortPool(cores)
 
 
 def _prior_chunk(n):

@@ -4,11 +4,17 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_reference_arm_json_line():
-    env = dict(os.environ, OMP_NUM_THREADS="1")  # what torchrun exports; must not cap the arm
+@pytest.mark.parametrize("arm", ["auto", "port"])
+def test_reference_arm_json_line(arm):
+    from oracle import ref_cython
+
+    # OMP_NUM_THREADS=1 is what torchrun exports; it must not cap the arm
+    env = dict(os.environ, OMP_NUM_THREADS="1", TJB_BENCH_CPU_ARM=arm)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
                         "--steps", "1", "--warmup", "1", "--log2-ref-step", "9"],
                        capture_output=True, text=True, env=env, timeout=600)
@@ -24,7 +30,8 @@ def test_reference_arm_json_line():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["cores"] >= 1
+    kind = "reference" if (arm == "auto" and ref_cython.available()) else "port"
+    assert cb["kind"] == kind and cb["value"] == d["value"] and cb["cores"] >= 1
     assert cb["cores"] == len(os.sched_getaffinity(0))
     assert "workload" in d["config"] and d["vs_baseline"] is None
 
