@@ -23,8 +23,11 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SHIM = os.path.join(_HERE, "ref_build", "shim")
 _SHIM_NAMES = ("astropy", "astropy.units", "thejoker", "thejoker.units", "thejoker.utils",
-               "thejoker.distributions", "thejoker.src", "thejoker.src.fast_likelihood")
+               "thejoker.distributions", "thejoker.logging", "thejoker.samples",
+               "thejoker.likelihood_helpers", "thejoker.src", "thejoker.src.fast_likelihood")
+REF_LIKELIHOOD_HELPERS = "/root/reference/thejoker/likelihood_helpers.py"
 _module = None
+_lh_module = None
 _shim_modules = {}
 
 
@@ -82,6 +85,25 @@ def load():
     return _module
 
 
+def load_likelihood_helpers():
+    """The reference's thejoker/likelihood_helpers.py, executed from where it lies (pure
+    Python: numpy + its package logger; build container only)."""
+    global _lh_module
+    if _lh_module is None:
+        if not os.path.exists(REF_LIKELIHOOD_HELPERS):
+            raise RuntimeError("needs /root/reference (build container only)")
+        with _shims():
+            import thejoker  # noqa: F401
+
+            name = "thejoker.likelihood_helpers"
+            spec = importlib.util.spec_from_file_location(name, REF_LIKELIHOOD_HELPERS)
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[name] = mod
+            spec.loader.exec_module(mod)
+            _lh_module = mod
+    return _lh_module
+
+
 class _Named:
     def __init__(self, name):
         self.name = name
@@ -125,6 +147,7 @@ class RefCythonHelper:
             data.ivar = u.Quantity(np.asarray(spec["ivar"], "f8"), 1 / rv_unit ** 2)
             data._t_bmjd = t
             data._t_ref_bmjd = float(spec["t0"])
+            data.t_ref = None
             data_cls = type("ShimData", (), {"__len__": lambda s: len(t)})
             d = data_cls()
             d.__dict__.update(data.__dict__)
@@ -170,3 +193,17 @@ class RefCythonHelper:
     def batch_get_posterior_samples(self, chunk, n_linear_samples_per, rng):
         return self.helper.batch_get_posterior_samples(
             np.ascontiguousarray(chunk, dtype="f8"), int(n_linear_samples_per), rng)
+
+    # -- the reference's in-memory drivers (thejoker/likelihood_helpers.py:91-229), run on
+    #    this helper: rng.uniform accept, truncation, posterior draws, iteration schedule
+    def rejection_sample_inmem(self, chunk, rng, **kw):
+        lh = load_likelihood_helpers()
+        with _shims():
+            return lh.rejection_sample_inmem(self.helper, np.ascontiguousarray(chunk, "f8"), rng,
+                                             **kw)
+
+    def iterative_rejection_inmem(self, chunk, rng, n_requested_samples, **kw):
+        lh = load_likelihood_helpers()
+        with _shims():
+            return lh.iterative_rejection_inmem(self.helper, np.ascontiguousarray(chunk, "f8"),
+                                                rng, n_requested_samples, **kw)

@@ -19,7 +19,9 @@ _ALL_NPZ = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*
 # ref_*.npz: minted by the reference's own compiled Cython (golden/make_ref_golden.py);
 # the others by the oracle + quad truth (golden/make_golden.py)
 GOLDEN = [p for p in _ALL_NPZ if not os.path.basename(p).startswith("ref_")]
-REF_GOLDEN = [p for p in _ALL_NPZ if os.path.basename(p).startswith("ref_")]
+REF_REJECTION = [p for p in _ALL_NPZ if os.path.basename(p).startswith("ref_rejection_")]
+REF_GOLDEN = [p for p in _ALL_NPZ if os.path.basename(p).startswith("ref_")
+              and p not in REF_REJECTION]
 
 
 @pytest.fixture(scope="module")
@@ -109,6 +111,53 @@ def test_reference_cython_golden_vectors(torch_cuda, path):
     assert np.array_equal(samples[:, :5], z["ref_samples"][:, :5])
     scale = np.sqrt(np.repeat(np.einsum("nii->ni", z["ref_worker_A"]), n_draw, axis=0))
     assert np.max(np.abs(samples[:, 5:] - z["ref_samples"][:, 5:]) / scale) < 1e-6
+
+
+@pytest.mark.parametrize("path", REF_REJECTION,
+                         ids=[os.path.basename(p)[14:-4] for p in REF_REJECTION])
+def test_reference_rejection_driver_vectors(torch_cuda, path):
+    """TheJoker.rejection_sample / iterative_rejection_sample (device ll, fused max, device
+    PCG64 uniforms, compaction, draws) against what the reference's own
+    likelihood_helpers.py:91-229 returned on its compiled helper for the same star, prior
+    rows and Generator seed (tests/golden/make_ref_golden.py)."""
+    import sys
+
+    import thejoker_b200 as tj
+
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden import CASES as GOLDEN_CASES
+
+    z = np.load(path)
+    N, pt, sl, kw = GOLDEN_CASES[os.path.basename(path)[14:-4]]
+    spec, data, prior = star_spec(N, pt, **kw)
+    # the star regenerated here is the one the reference was given
+    assert np.array_equal(spec["t"], z["t"]) and np.array_equal(spec["rv"], z["rv"])
+    assert np.array_equal(spec["ivar"], z["ivar"]) and np.array_equal(spec["Lambda"], z["Lambda"])
+    chunk = np.ascontiguousarray(z["chunk"])
+
+    def packed(samples):
+        return samples.pack(nonlinear_only=False)[0]
+
+    def close(got, ref):
+        assert got.shape == ref.shape, (got.shape, ref.shape)
+        assert np.array_equal(got[:, :5], ref[:, :5])           # the accepted prior rows
+        scale = np.abs(ref[:, 5:]).max(axis=0) + 1e-300
+        assert np.max(np.abs(got[:, 5:] - ref[:, 5:]) / scale) < 1e-6
+
+    mk = lambda seed: tj.TheJoker(prior, rng=np.random.default_rng(seed), devices=[0],
+                                  jitter_mode="reference", draw="numpy")
+    flat = "flat" in path
+    smp, lls = mk(int(z["seed_rej"])).rejection_sample(data, chunk, n_linear_samples=2,
+                                                       return_all_logprobs=True, in_memory=True)
+    assert np.max(rel_err(lls, z["rej_lls"])) < (1e-8 if flat else 1e-10)
+    close(packed(smp), z["rej_raw"])
+    smp = mk(int(z["seed_rej"])).rejection_sample(data, chunk, max_posterior_samples=3,
+                                                  in_memory=True)
+    close(packed(smp), z["rej3_raw"])
+    smp = mk(int(z["seed_iter"])).iterative_rejection_sample(
+        data, chunk, int(z["iter_n_requested"]), init_batch_size=int(z["iter_init_batch_size"]),
+        in_memory=True)
+    close(packed(smp), z["iter_raw"])
 
 
 CASES = [

@@ -19,7 +19,9 @@ _ALL_NPZ = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*
 # ref_*.npz: minted by the reference's own compiled Cython (golden/make_ref_golden.py);
 # the others by the oracle + quad truth (golden/make_golden.py)
 GOLDEN = [p for p in _ALL_NPZ if not os.path.basename(p).startswith("ref_")]
-REF_GOLDEN = [p for p in _ALL_NPZ if os.path.basename(p).startswith("ref_")]
+REF_REJECTION = [p for p in _ALL_NPZ if os.path.basename(p).startswith("ref_rejection_")]
+REF_GOLDEN = [p for p in _ALL_NPZ if os.path.basename(p).startswith("ref_")
+              and p not in REF_REJECTION]
 
 
 def _spec_from_npz(z):

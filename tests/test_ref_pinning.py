@@ -20,9 +20,11 @@ import pytest
 from helpers import prior_chunk, star_spec
 
 from oracle import ref_cython
-from oracle.oracle import OracleHelper
+from oracle.oracle import OracleHelper, iterative_rejection_indices, rejection_accept
 
-REF_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.npz")))
+_REF_ALL = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.npz")))
+REF_REJECTION = [p for p in _REF_ALL if os.path.basename(p).startswith("ref_rejection_")]
+REF_GOLDEN = [p for p in _REF_ALL if p not in REF_REJECTION]
 SPEC_KEYS = ("t", "rv", "ivar", "t0", "trend_M", "mu", "Lambda", "K_prior_kind", "sigma_K0", "P0",
              "max_K")
 MATS = ("a", "A", "Ainv", "b", "B", "Binv")
@@ -58,6 +60,43 @@ def test_oracle_matches_reference_vectors(path):
     assert samples.shape == z["ref_samples"].shape
     assert np.allclose(samples, z["ref_samples"], rtol=1e-9, atol=1e-9)
     assert np.allclose(lls, z["ref_samples_ll"], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("path", REF_REJECTION,
+                         ids=[os.path.basename(p)[14:-4] for p in REF_REJECTION])
+def test_oracle_matches_reference_rejection_drivers(path):
+    """thejoker/likelihood_helpers.py:91-229 run on the compiled reference helper vs the
+    oracle's restatement of the same steps on the same Generator stream: accepted rows,
+    truncation, the linear draws that follow, ln_prior / ln_likelihood bookkeeping, and
+    the iterative schedule."""
+    z = np.load(path)
+    orc = OracleHelper.from_spec(_spec(z), jitter_mode=0)
+    chunk, ln_prior = z["chunk"], z["ln_prior"]
+    # (1) rejection_sample_inmem(..., n_linear_samples=2, return_all_logprobs=True)
+    rng = np.random.default_rng(int(z["seed_rej"]))
+    ll = orc.batch_marginal_ln_likelihood(chunk)
+    assert np.allclose(ll, z["rej_lls"], rtol=1e-12, atol=0)
+    good = rejection_accept(ll, rng.uniform(size=len(ll)))
+    assert np.array_equal(chunk[np.repeat(good, 2)], z["rej_raw"][:, :5])
+    assert np.array_equal(ln_prior[good], z["rej_ln_prior"])
+    assert np.allclose(ll[good], z["rej_ln_likelihood"], rtol=1e-12, atol=0)
+    smp, _ = orc.batch_get_posterior_samples(chunk[good], 2, rng)
+    assert np.allclose(smp, z["rej_raw"], rtol=1e-9, atol=1e-9)
+    # (2) max_posterior_samples=3
+    rng = np.random.default_rng(int(z["seed_rej"]))
+    good3 = rejection_accept(ll, rng.uniform(size=len(ll)), max_posterior_samples=3)
+    smp, _ = orc.batch_get_posterior_samples(chunk[good3], 1, rng)
+    assert np.allclose(smp, z["rej3_raw"], rtol=1e-9, atol=1e-9)
+    # (3) iterative_rejection_inmem(n_requested=4, init_batch_size=256)
+    rng = np.random.default_rng(int(z["seed_iter"]))
+    idx, lls_seen = iterative_rejection_indices(
+        lambda a, b: orc.batch_marginal_ln_likelihood(chunk[a:b]), len(chunk), rng,
+        int(z["iter_n_requested"]), init_batch_size=int(z["iter_init_batch_size"]))
+    assert np.array_equal(chunk[idx], z["iter_raw"][:, :5])
+    assert np.array_equal(ln_prior[idx], z["iter_ln_prior"])
+    assert np.allclose(lls_seen[idx], z["iter_ln_likelihood"], rtol=1e-12, atol=0)
+    smp, _ = orc.batch_get_posterior_samples(chunk[idx], 1, rng)
+    assert np.allclose(smp, z["iter_raw"], rtol=1e-9, atol=1e-9)
 
 
 def test_reference_ignores_jitter_and_clamps_only_in_batch_ll():
