@@ -207,3 +207,20 @@ class RefCythonHelper:
         with _shims():
             return lh.iterative_rejection_inmem(self.helper, np.ascontiguousarray(chunk, "f8"),
                                                 rng, n_requested_samples, **kw)
+
+
+def reference_function(rel_path, name, namespace=None):
+    """One top-level function of a reference module, compiled from the file where it lies
+    (ast-extracted, so that module-level imports of absent packages are not executed).
+    Build container only."""
+    import ast
+
+    path = os.path.join("/root/reference", rel_path)
+    tree = ast.parse(open(path).read(), filename=path)
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            ns = {"np": np}
+            ns.update(namespace or {})
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+            return ns[name]
+    raise KeyError(name)

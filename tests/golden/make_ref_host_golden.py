@@ -1,0 +1,71 @@
+"""tests/golden/ref_host_logic.json: outputs of the reference's own host-side helpers on
+the path -- utils.py::batch_tasks (22-72) and likelihood_helpers.py::
+get_constant_term_design_matrix / get_trend_design_matrix / ln_normal (8-37, 232-233) --
+executed from the files where they lie under /root/reference (build container only).
+
+    python tests/golden/make_ref_host_golden.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle.ref_cython import load_likelihood_helpers, reference_function  # noqa: E402
+
+
+class FakeData:
+    def __init__(self, t, t_ref):
+        self._t_bmjd, self._t_ref_bmjd = np.asarray(t, float), float(t_ref)
+
+    def __len__(self):
+        return len(self._t_bmjd)
+
+
+def design_cases():
+    rng = np.random.default_rng(17)
+    out = []
+    for n, ids_kind, poly in [(5, None, 1), (7, "two", 1), (9, "three", 2), (6, None, 3),
+                              (8, "gap", 4), (4, "two", 5)]:
+        t = np.sort(rng.uniform(55000.0, 56000.0, n))
+        ids = {None: None, "two": rng.integers(0, 2, n), "three": rng.integers(0, 3, n),
+               "gap": rng.choice([2, 5, 9], n)}[ids_kind]
+        if ids is not None:
+            ids[0] = ids.min()  # keep every case's first id present
+        out.append((t, float(t.min()), None if ids is None else ids.tolist(), poly))
+    return out
+
+
+def main():
+    batch_tasks = reference_function("thejoker/utils.py", "batch_tasks")
+    lh = load_likelihood_helpers()
+    rec = {"batch_tasks": [], "design": [], "ln_normal": []}
+    for n_tasks, n_batches, start in [(10, 3, 0), (10, 3, 7), (3, 8, 0), (0, 4, 0), (16, 4, 2),
+                                      (17, 16, 0), (1 << 28, 8, 0), (1000, 0, 5), (5, 5, 1),
+                                      (268435456, 7, 1024)]:
+        tasks = batch_tasks(n_tasks, n_batches, start_idx=start, args=["x"])
+        rec["batch_tasks"].append({"n_tasks": n_tasks, "n_batches": n_batches, "start_idx": start,
+                                   "tasks": [[list(t[0]), t[1], t[2]] for t in tasks]})
+    arr = np.arange(23) * 10
+    tasks = batch_tasks(11, 4, arr=arr, start_idx=3)
+    rec["batch_tasks_arr"] = {"arr": arr.tolist(), "n_tasks": 11, "n_batches": 4, "start_idx": 3,
+                              "tasks": [[t[0].tolist(), t[1]] for t in tasks]}
+    for t, t_ref, ids, poly in design_cases():
+        data = FakeData(t, t_ref)
+        M = lh.get_trend_design_matrix(data, ids, poly)
+        C = lh.get_constant_term_design_matrix(data, ids)
+        rec["design"].append({"t": t.tolist(), "t_ref": t_ref, "ids": ids, "poly_trend": poly,
+                              "trend_M": M.tolist(), "const_M": C.tolist()})
+    for x, mu, var in [(0.3, 0.1, 2.0), (-5.0, 1.0, 0.01), (1e3, 0.0, 1e4)]:
+        rec["ln_normal"].append({"x": x, "mu": mu, "var": var, "value": float(lh.ln_normal(x, mu, var))})
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_host_logic.json")
+    with open(path, "w") as f:
+        json.dump(rec, f)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

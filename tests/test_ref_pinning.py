@@ -164,3 +164,55 @@ def test_shims_do_not_leak_into_the_process():
 
     ref_cython.load()
     assert "astropy" not in sys.modules and "thejoker" not in sys.modules
+
+
+# -- host-side helpers of the path against the reference's own functions --------------------
+def _host_golden():
+    import json
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "ref_host_logic.json")) as f:
+        return json.load(f)
+
+
+def test_batch_tasks_matches_reference():
+    """thejoker/utils.py:22-72 (outputs minted by tests/golden/make_ref_host_golden.py)."""
+    from thejoker_b200.sharding import batch_tasks, shard_ranges
+
+    from oracle.oracle import batch_tasks_ranges
+
+    g = _host_golden()
+    for c in g["batch_tasks"]:
+        got = batch_tasks(c["n_tasks"], c["n_batches"], start_idx=c["start_idx"], args=["x"])
+        assert [[list(t[0]), t[1], t[2]] for t in got] == c["tasks"], c
+        assert [list(r) for r in batch_tasks_ranges(c["n_tasks"], c["n_batches"],
+                                                    c["start_idx"])] == [t[0] for t in c["tasks"]]
+        if c["start_idx"] == 0 and c["n_batches"] > 0 and c["n_tasks"] >= c["n_batches"]:
+            assert [list(r) for r in shard_ranges(c["n_tasks"], c["n_batches"])] == \
+                [t[0] for t in c["tasks"]]
+    c = g["batch_tasks_arr"]
+    got = batch_tasks(c["n_tasks"], c["n_batches"], arr=np.array(c["arr"]), start_idx=c["start_idx"])
+    assert [[t[0].tolist(), t[1]] for t in got] == c["tasks"]
+
+
+def test_design_matrices_match_reference():
+    """thejoker/likelihood_helpers.py:8-37, 232-233."""
+    from thejoker_b200.likelihood_helpers import (get_constant_term_design_matrix,
+                                                  get_trend_design_matrix, ln_normal)
+
+    class FakeData:
+        def __init__(self, t, t_ref):
+            self._t_bmjd, self._t_ref_bmjd = np.asarray(t, float), float(t_ref)
+
+        def __len__(self):
+            return len(self._t_bmjd)
+
+    g = _host_golden()
+    for c in g["design"]:
+        data = FakeData(c["t"], c["t_ref"])
+        ids = None if c["ids"] is None else np.array(c["ids"])
+        assert np.array_equal(get_constant_term_design_matrix(data, ids), np.array(c["const_M"]))
+        M = get_trend_design_matrix(data, ids, c["poly_trend"])
+        ref = np.array(c["trend_M"]).reshape(M.shape)
+        assert np.array_equal(M, ref), (c["poly_trend"], np.max(np.abs(M - ref) / np.abs(ref)))
+    for c in g["ln_normal"]:
+        assert np.isclose(ln_normal(c["x"], c["mu"], c["var"]), c["value"], rtol=1e-15, atol=0)

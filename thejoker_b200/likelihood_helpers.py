@@ -27,7 +27,12 @@ def get_trend_design_matrix(data, ids, poly_trend):
     dt = np.asarray(data._t_bmjd, dtype=float) - data._t_ref_bmjd
     blocks = [get_constant_term_design_matrix(data, ids)]
     if poly_trend > 1:
-        blocks.append(np.stack([dt**k for k in range(1, poly_trend)], axis=1))
+        # running products (dt, dt*dt, (dt*dt)*dt, ...): bit-identical to the reference's
+        # np.vander(dt, N=poly_trend, increasing=True)[:, 1:], unlike dt**k for k >= 3
+        powers = [dt]
+        for _ in range(2, poly_trend):
+            powers.append(powers[-1] * dt)
+        blocks.append(np.stack(powers, axis=1))
     return np.ascontiguousarray(np.concatenate(blocks, axis=1))
 
 
