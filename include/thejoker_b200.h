@@ -110,6 +110,17 @@ int tjb_marginal_ll_host(TjbHandle *h, const double *h_chunk, int64_t n, double 
 int tjb_marginal_ll_host_soa(TjbHandle *h, const double *h_P, const double *h_e,
                              const double *h_omega, const double *h_M0, const double *h_s,
                              double s_const, int64_t n, double *h_ll);
+/* The same host columns, but the ll values stay on the device (d_ll[n]) with their running
+ * max in *d_llmax_key (may be NULL), ready for tjb_accept: the prior cache is streamed
+ * through the GPU slice by slice and never becomes resident.  This is how
+ * rejection_sample_inmem / iterative_rejection_inmem (likelihood_helpers.py:91-229) and
+ * the read_batch loop of the pool workers (multiproc_helpers.py:63-98) are served when the
+ * prior samples live in host memory or in a memory-mapped cache file.  Pageable host
+ * memory is staged through a page-locked ring by host threads (both host entry points). */
+int tjb_marginal_ll_host_soa_resident(TjbHandle *h, const double *h_P, const double *h_e,
+                                      const double *h_omega, const double *h_M0,
+                                      const double *h_s, double s_const, int64_t n, double *d_ll,
+                                      int64_t *d_llmax_key);
 
 /* ---- accept step (likelihood_helpers.py:107-109; multiproc_helpers.py:256-258) */
 int tjb_llmax_reset(TjbHandle *h, int64_t *d_llmax_key);

@@ -238,6 +238,66 @@ def test_ll_device_paths_agree(torch_cuda, oracle_lib):
         assert np.max(rel_err(host[:4096], ref)) < 1e-9
 
 
+@pytest.mark.parametrize("n", [1, 1000, (1 << 18) + 5, 3 * (1 << 18) + 77, (1 << 21) + 12345])
+def test_host_streaming_paths(torch_cuda, n):
+    """Host columns streamed through the GPU (pageable memory via the page-locked ring,
+    page-locked memory directly; ll to the host or left on the device with its max) give
+    the bits of the resident-column kernel, for ragged sizes around the slice size."""
+    torch = torch_cuda
+    helper, spec, _, _ = make_helper((16, 1))
+    for sl in (None, (-2.0, 1.0)):
+        chunk = prior_chunk(n, s_lognormal=sl)
+        hc = [np.ascontiguousarray(chunk[:, i]) for i in range(5)]
+        s = hc[4] if sl is not None else None
+        dev = [torch.from_numpy(c).cuda() for c in hc]
+        key0 = helper.new_llmax_key()
+        ref = helper.marginal_ll_soa(*dev[:4], s=dev[4] if sl is not None else None,
+                                     llmax_key=key0).cpu().numpy()
+        # pageable in, pageable out
+        assert np.array_equal(helper.marginal_ln_likelihood_columns(*hc[:4], s=s), ref)
+        # page-locked in and out
+        pin = [torch.from_numpy(c).pin_memory().numpy() for c in hc]
+        out = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
+        helper.marginal_ln_likelihood_columns(*pin[:4], s=pin[4] if sl is not None else None,
+                                              out=out)
+        assert np.array_equal(out, ref)
+        # pageable in, ll stays on the device, running max in the key
+        key = helper.new_llmax_key()
+        d_ll = helper.marginal_ll_host_columns(*hc[:4], s=s, llmax_key=key)
+        assert np.array_equal(d_ll.cpu().numpy(), ref)
+        assert helper.llmax_value(key) == helper.llmax_value(key0) == ref.max()
+        # read-only (memory-mapped style) sources
+        ro = [c.copy() for c in hc]
+        for c in ro:
+            c.flags.writeable = False
+        d_ll = helper.marginal_ll_host_columns(*ro[:4], s=ro[4] if sl is not None else None)
+        assert np.array_equal(d_ll.cpu().numpy(), ref)
+
+
+def test_engine_streamed_equals_resident(torch_cuda):
+    """DeviceEngine over host columns: streaming (default) and resident modes give the
+    same ll, max, accepted indices and rows, also for sub-ranges (iterative sampler)."""
+    from thejoker_b200.sharding import DeviceEngine
+
+    helper, spec, data, prior = make_helper((16, 1), K=1e-4)
+    import thejoker_b200 as tj
+
+    make = lambda d: tj.CJokerHelper.from_spec(spec, device=d)
+    n = 300_000
+    chunk = prior_chunk(n)
+    cols = [np.ascontiguousarray(chunk[:, i]) for i in range(4)] + [None]
+    outs = []
+    for resident in (False, True):
+        eng = DeviceEngine(make, cols, devices=[0], resident=resident)
+        eng.compute_ll(0, 70_000)
+        eng.compute_ll(70_000, n)
+        idx, tot, near = eng.accept(np.random.default_rng(3), max_keep=500)
+        outs.append((eng.download_ll(0, n), eng.max_value(), idx, tot, eng.rows(idx[:50])))
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+    assert outs[0][3] > 0
+
+
 def test_jitter_modes(torch_cuda, oracle_lib):
     """jitter_mode='reference' ignores s like the reference's Cython does
     (fast_likelihood.pyx:458); 'apply' matches the intended semantics

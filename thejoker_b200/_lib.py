@@ -67,6 +67,9 @@ SYMBOLS = {
     "tjb_marginal_ll_host": (ctypes.c_int, [_H, _vp, ctypes.c_int64, _vp]),
     "tjb_marginal_ll_host_soa": (ctypes.c_int, [_H, _vp, _vp, _vp, _vp, _vp, ctypes.c_double,
                                                 ctypes.c_int64, _vp]),
+    "tjb_marginal_ll_host_soa_resident": (ctypes.c_int, [_H, _vp, _vp, _vp, _vp, _vp,
+                                                         ctypes.c_double, ctypes.c_int64, _vp,
+                                                         _vp]),
     "tjb_llmax_reset": (ctypes.c_int, [_H, _vp]),
     "tjb_llmax_update": (ctypes.c_int, [_H, _vp, ctypes.c_int64, _vp]),
     "tjb_llmax_get": (ctypes.c_int, [_H, _vp, _dp]),

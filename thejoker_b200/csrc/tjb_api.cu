@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/thejoker_b200.h"
@@ -53,6 +54,27 @@ struct DevBuf {
   }
 };
 
+// page-locked host staging (ring slots of the host-streaming paths)
+struct PinBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return 0;
+    release();
+    if (cudaHostAlloc(&p, need, cudaHostAllocDefault) != cudaSuccess) {
+      p = nullptr;
+      return -1;
+    }
+    bytes = need;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+
 }  // namespace
 
 struct TjbHandle {
@@ -69,6 +91,8 @@ struct TjbHandle {
   // scratch
   DevBuf acc_mask, acc_counts, acc_offsets, acc_totals, misc, stats, trig;
   DevBuf host_stage[2], host_ll[2];
+  PinBuf pin_in[2], pin_out[2];
+  cudaEvent_t pin_in_free[2] = {nullptr, nullptr};
   cudaStream_t aux_stream[2] = {nullptr, nullptr};
   int ll_ctas_per_sm = 0;
   // extra (peer) keys the likelihood kernel max-updates besides the one passed per call
@@ -319,6 +343,8 @@ void tjb_destroy(TjbHandle *h) {
   h->acc_totals.release(); h->misc.release(); h->stats.release(); h->trig.release();
   for (int i = 0; i < 2; i++) {
     h->host_stage[i].release(); h->host_ll[i].release();
+    h->pin_in[i].release(); h->pin_out[i].release();
+    if (h->pin_in_free[i]) cudaEventDestroy(h->pin_in_free[i]);
     if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]);
   }
   delete h;
@@ -446,6 +472,121 @@ int tjb_marginal_ll_host(TjbHandle *h, const double *h_chunk, int64_t n, double 
   return TJB_OK;
 }
 
+namespace {
+
+// true when the driver would have to stage a copy from / to this host pointer itself
+// (ordinary pageable memory): its staged path runs at a fraction of the PCIe rate
+bool is_pageable(const void *ptr) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+// dst[c][0..count) = src[c][0..count) for n_cols columns, split over host threads
+void parallel_copy(double *const *dst, const double *const *src, int n_cols, size_t count) {
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const int per_col = (int)std::max(1u, std::min(4u, hw / (unsigned)n_cols));
+  if (count < (1u << 16) || hw == 1) {
+    for (int c = 0; c < n_cols; c++) std::memcpy(dst[c], src[c], count * sizeof(double));
+    return;
+  }
+  std::vector<std::thread> pool;
+  pool.reserve((size_t)n_cols * per_col);
+  for (int c = 0; c < n_cols; c++)
+    for (int k = 0; k < per_col; k++) {
+      const size_t a = count * k / per_col, b = count * (k + 1) / per_col;
+      pool.emplace_back([=] { std::memcpy(dst[c] + a, src[c] + a, (b - a) * sizeof(double)); });
+    }
+  for (auto &t : pool) t.join();
+}
+
+// Streams host columns through the GPU in slices on two streams: host (pageable ->
+// page-locked ring, threaded) | H2D | kernel | D2H all overlap.  The ll values go to
+// h_ll (host) or stay in d_ll (device, with the running max in d_key), or both.
+int host_soa_stream(TjbHandle *h, const double *const cols[5], int n_cols, double s_const,
+                    int64_t n, double *h_ll, double *d_ll, int64_t *d_key) {
+  CU(cudaSetDevice(h->device));
+  bool stage_in = false;
+  for (int c = 0; c < n_cols; c++) stage_in = stage_in || is_pageable(cols[c]);
+  const bool stage_out = h_ll && is_pageable(h_ll);
+  // slice: at least 8 slices for overlap, 2 MB..32 MB per column copy
+  int64_t slice = 1 << 22;
+  while (slice > (1 << 18) && slice * 8 > n) slice >>= 1;
+  const int64_t m_max = std::min(slice, n);
+  for (int i = 0; i < 2; i++) {
+    if (!h->aux_stream[i]) CU(cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking));
+    if (!h->pin_in_free[i]) CU(cudaEventCreateWithFlags(&h->pin_in_free[i], cudaEventDisableTiming));
+    if (h->host_stage[i].ensure((size_t)m_max * 5 * sizeof(double)) ||
+        (!d_ll && h->host_ll[i].ensure((size_t)m_max * sizeof(double))))
+      return fail(TJB_E_NOMEM, "cudaMalloc staging");
+    if ((stage_in && h->pin_in[i].ensure((size_t)m_max * n_cols * sizeof(double))) ||
+        (stage_out && h->pin_out[i].ensure((size_t)m_max * sizeof(double))))
+      return fail(TJB_E_NOMEM, "cudaHostAlloc staging");
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  int64_t out_lo[2] = {-1, -1}, out_m[2] = {0, 0};  // slices parked in pin_out[b]
+  auto drain_out = [&](int b) -> int {              // pin_out[b] -> h_ll once its D2H is done
+    if (out_lo[b] < 0) return TJB_OK;
+    CU(cudaStreamSynchronize(h->aux_stream[b]));
+    std::memcpy(h_ll + out_lo[b], h->pin_out[b].p, (size_t)out_m[b] * sizeof(double));
+    out_lo[b] = -1;
+    return TJB_OK;
+  };
+  int b = 0;
+  int64_t n_slices = 0;
+  for (int64_t lo = 0; lo < n; lo += slice, b ^= 1, n_slices++) {
+    const int64_t m = std::min(slice, n - lo);
+    cudaStream_t st = h->aux_stream[b];
+    double *d_in = (double *)h->host_stage[b].p;
+    double *d_out = d_ll ? d_ll + lo : (double *)h->host_ll[b].p;
+    const double *src[5];
+    if (stage_in) {
+      if (n_slices >= 2) CU(cudaEventSynchronize(h->pin_in_free[b]));  // slot's last H2D done
+      double *dst[5];
+      for (int c = 0; c < n_cols; c++) {
+        dst[c] = (double *)h->pin_in[b].p + (size_t)c * m_max;
+        src[c] = cols[c] + lo;
+      }
+      parallel_copy(dst, src, n_cols, (size_t)m);
+      for (int c = 0; c < n_cols; c++) src[c] = dst[c];
+    } else {
+      for (int c = 0; c < n_cols; c++) src[c] = cols[c] + lo;
+    }
+    for (int c = 0; c < n_cols; c++)
+      CU(cudaMemcpyAsync(d_in + (size_t)c * m_max, src[c], (size_t)m * sizeof(double),
+                         cudaMemcpyHostToDevice, st));
+    if (stage_in) CU(cudaEventRecord(h->pin_in_free[b], st));
+    PriorView pv = {d_in, d_in + m_max, d_in + 2 * m_max, d_in + 3 * m_max,
+                    n_cols == 5 ? d_in + 4 * m_max : nullptr, nullptr, 0.0, nullptr};
+    int rc = run_ll(h, pv, n_cols == 4, s_const, m, d_out, (long long *)d_key, st);
+    if (rc) return rc;
+    if (h_ll) {
+      if (stage_out) {
+        rc = drain_out(b);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(h->pin_out[b].p, d_out, (size_t)m * sizeof(double),
+                           cudaMemcpyDeviceToHost, st));
+        out_lo[b] = lo;
+        out_m[b] = m;
+      } else {
+        CU(cudaMemcpyAsync(h_ll + lo, d_out, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+      }
+    }
+  }
+  CU(cudaStreamSynchronize(h->aux_stream[0]));
+  CU(cudaStreamSynchronize(h->aux_stream[1]));
+  for (int i = 0; i < 2; i++) {
+    int rc = drain_out(i);
+    if (rc) return rc;
+  }
+  return TJB_OK;
+}
+
+}  // namespace
+
 int tjb_marginal_ll_host_soa(TjbHandle *h, const double *h_P, const double *h_e,
                              const double *h_omega, const double *h_M0, const double *h_s,
                              double s_const, int64_t n, double *h_ll) {
@@ -453,35 +594,21 @@ int tjb_marginal_ll_host_soa(TjbHandle *h, const double *h_P, const double *h_e,
   if (n < 0) return fail(TJB_E_INVALID, "negative n");
   if (n == 0) return TJB_OK;
   if (!h_P || !h_e || !h_omega || !h_M0 || !h_ll) return fail(TJB_E_INVALID, "null host pointer");
-  CU(cudaSetDevice(h->device));
-  const int n_cols = h_s ? 5 : 4;
   const double *cols[5] = {h_P, h_e, h_omega, h_M0, h_s};
-  const int64_t slice = 1 << 22;  // 32 MB per column copy: large DMA transfers
-  const int64_t m_max = std::min(slice, n);
-  for (int i = 0; i < 2; i++) {
-    if (!h->aux_stream[i]) CU(cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking));
-    if (h->host_stage[i].ensure((size_t)m_max * 5 * sizeof(double)) ||
-        h->host_ll[i].ensure((size_t)m_max * sizeof(double)))
-      return fail(TJB_E_NOMEM, "cudaMalloc staging");
-  }
-  CU(cudaStreamSynchronize(h->stream));
-  int b = 0;
-  for (int64_t lo = 0; lo < n; lo += slice, b ^= 1) {
-    const int64_t m = std::min(slice, n - lo);
-    cudaStream_t st = h->aux_stream[b];
-    double *d_in = (double *)h->host_stage[b].p, *d_out = (double *)h->host_ll[b].p;
-    for (int c = 0; c < n_cols; c++)
-      CU(cudaMemcpyAsync(d_in + (size_t)c * m_max, cols[c] + lo, (size_t)m * sizeof(double),
-                         cudaMemcpyHostToDevice, st));
-    PriorView pv = {d_in, d_in + m_max, d_in + 2 * m_max, d_in + 3 * m_max,
-                    h_s ? d_in + 4 * m_max : nullptr, nullptr, 0.0, nullptr};
-    int rc = run_ll(h, pv, h_s == nullptr, s_const, m, d_out, nullptr, st);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(h_ll + lo, d_out, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
-  }
-  CU(cudaStreamSynchronize(h->aux_stream[0]));
-  CU(cudaStreamSynchronize(h->aux_stream[1]));
-  return TJB_OK;
+  return host_soa_stream(h, cols, h_s ? 5 : 4, s_const, n, h_ll, nullptr, nullptr);
+}
+
+int tjb_marginal_ll_host_soa_resident(TjbHandle *h, const double *h_P, const double *h_e,
+                                      const double *h_omega, const double *h_M0,
+                                      const double *h_s, double s_const, int64_t n, double *d_ll,
+                                      int64_t *d_llmax_key) {
+  if (!h) return fail(TJB_E_INVALID, "null handle");
+  if (n < 0) return fail(TJB_E_INVALID, "negative n");
+  if (n == 0) return TJB_OK;
+  if (!h_P || !h_e || !h_omega || !h_M0) return fail(TJB_E_INVALID, "null host pointer");
+  if (!d_ll) return fail(TJB_E_INVALID, "null device pointer");
+  const double *cols[5] = {h_P, h_e, h_omega, h_M0, h_s};
+  return host_soa_stream(h, cols, h_s ? 5 : 4, s_const, n, nullptr, d_ll, d_llmax_key);
 }
 
 // ---- accept -----------------------------------------------------------------

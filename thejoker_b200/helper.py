@@ -401,6 +401,33 @@ class CJokerHelper:
                                                  self._ptr(llmax_key)))
         return out
 
+    def marginal_ll_host_columns(self, P, e, omega, M0, s=None, s_const=0.0, out=None,
+                                 llmax_key=None):
+        """ll for HOST columns (numpy / memory-mapped, internal units), left on the device
+        in ``out`` with the running max in ``llmax_key``: the columns are streamed through
+        the GPU in slices (pageable memory via a page-locked ring) and never become
+        resident.  Blocks until done (the GIL is released)."""
+        import torch
+
+        cols = [np.ascontiguousarray(c, dtype=np.float64) for c in (P, e, omega, M0)]
+        n = len(cols[0])
+        if any(len(c) != n for c in cols):
+            raise ValueError("prior columns differ in length")
+        if s is not None:
+            s = np.ascontiguousarray(s, dtype=np.float64)
+            if len(s) != n:
+                raise ValueError("prior columns differ in length")
+        if out is None:
+            out = torch.empty(n, dtype=torch.float64, device=f"cuda:{self.device}")
+        self._check_dev(out, torch.float64, "out")
+        if out.numel() != n:
+            raise ValueError("out has the wrong length")
+        self._sync_stream()
+        _lib.check(self._lib.tjb_marginal_ll_host_soa_resident(
+            self._h, *[_vp(c) for c in cols], _vp(s) if s is not None else None, float(s_const),
+            n, self._ptr(out), self._ptr(llmax_key)))
+        return out
+
     def marginal_ll_aos(self, chunk, uniform_s=False, out=None, llmax_key=None):
         import torch
 

@@ -111,7 +111,7 @@ class DeviceEngine:
     """
 
     def __init__(self, make_helper, columns, devices=(0,), group=None, global_offset=0,
-                 global_size=None):
+                 global_size=None, resident=False):
         import torch
 
         self.torch = torch
@@ -126,23 +126,27 @@ class DeviceEngine:
         if not s_is_scalar and n_local > 0 and np.all(s == s[0]):
             s_is_scalar, self.s_const = True, float(s[0])
         self.shards = []
+        # resident=False (default): the host columns stay where they are (numpy arrays or
+        # memory-mapped cache files) and every compute_ll() streams just the requested
+        # range through the GPU (tjb_marginal_ll_host_soa_resident) -- nothing of the cache
+        # is uploaded that the sampler does not evaluate (the iterative sampler usually
+        # stops after a small prefix), and H2D overlaps the kernel.
+        # resident=True: upload each shard once, for caches that are evaluated repeatedly.
+        self.host_cols = None if resident else [P, e, om, M0, None if s_is_scalar else s]
         for d, (lo, hi) in zip(devices, shard_ranges(n_local, len(devices))):
-            with torch.cuda.device(d):
-                torch.cuda.current_stream().synchronize()
+            cols, s_dev = None, None
+            if resident:
+                with torch.cuda.device(d):
+                    torch.cuda.current_stream().synchronize()
 
-                def up(a):
-                    a = np.ascontiguousarray(a[lo:hi], dtype=np.float64)
-                    if not a.flags.writeable:  # memory-mapped cache columns are read-only
-                        a = a.copy()
-                    t = torch.from_numpy(a)
-                    if t.numel() >= (1 << 20):
-                        # stage through page-locked memory: one host memcpy + a full-rate
-                        # DMA beats the driver's pageable path for large columns
-                        t = t.pin_memory()
-                    return t.to(f"cuda:{d}", non_blocking=True)
+                    def up(a):
+                        a = np.ascontiguousarray(a[lo:hi], dtype=np.float64)
+                        if not a.flags.writeable:  # memory-mapped cache columns are read-only
+                            a = a.copy()
+                        return torch.from_numpy(a).to(f"cuda:{d}", non_blocking=True)
 
-                cols = [up(P), up(e), up(om), up(M0)]
-                s_dev = None if s_is_scalar else up(s)
+                    cols = [up(P), up(e), up(om), up(M0)]
+                    s_dev = None if s_is_scalar else up(s)
             self._add_shard(make_helper, d, lo, hi, cols, s_dev)
         self._link_peers()
 
@@ -200,6 +204,12 @@ class DeviceEngine:
         torch = self.torch
         local_idx = np.asarray(local_idx, dtype=np.int64)
         out = np.empty((len(local_idx), 5))
+        if getattr(self, "host_cols", None) is not None:
+            for j, c in enumerate(self.host_cols[:4]):
+                out[:, j] = np.asarray(c)[local_idx]
+            sc = self.host_cols[4]
+            out[:, 4] = self.s_const if sc is None else np.asarray(sc)[local_idx]
+            return out
         for sh in self.shards:
             m = (local_idx >= sh.lo) & (local_idx < sh.hi)
             if not m.any():
@@ -216,6 +226,8 @@ class DeviceEngine:
         shard's running-max key is updated.  Asynchronous."""
         hi = self.n_local if hi is None else hi
         torch = self.torch
+        if getattr(self, "host_cols", None) is not None:
+            return self._compute_ll_streamed(lo, hi)
         for sh in self.shards:
             a, b = max(lo, sh.lo), min(hi, sh.hi)
             if a >= b:
@@ -225,6 +237,32 @@ class DeviceEngine:
                 sh.helper.marginal_ll_soa(*[c[sl] for c in sh.cols],
                                           s=None if sh.s is None else sh.s[sl],
                                           s_const=self.s_const, out=sh.ll[sl], llmax_key=sh.key)
+
+    def _compute_ll_streamed(self, lo, hi):
+        """Host-resident cache: each GPU streams its part of [lo, hi) from host memory;
+        one host thread per GPU (the library call blocks, ctypes releases the GIL)."""
+        torch = self.torch
+        work = []
+        for sh in self.shards:
+            a, b = max(lo, sh.lo), min(hi, sh.hi)
+            if a < b:
+                work.append((sh, a, b))
+
+        def run(item):
+            sh, a, b = item
+            P, e, om, M0, s = self.host_cols
+            with torch.cuda.device(sh.device):
+                sh.helper.marginal_ll_host_columns(
+                    P[a:b], e[a:b], om[a:b], M0[a:b], s=None if s is None else s[a:b],
+                    s_const=self.s_const, out=sh.ll[a - sh.lo:b - sh.lo], llmax_key=sh.key)
+
+        if len(work) == 1:
+            run(work[0])
+        elif work:
+            from concurrent.futures import ThreadPoolExecutor
+
+            with ThreadPoolExecutor(len(work)) as ex:
+                list(ex.map(run, work))
 
     def compute_ll_global(self, glo, ghi):
         """ll for the part of the GLOBAL index range [glo, ghi) this process owns."""
