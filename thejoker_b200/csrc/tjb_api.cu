@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -75,6 +76,20 @@ struct PinBuf {
   }
 };
 
+// Staging resources of the host-streaming entry points, one set per device for the whole
+// process: handles are short-lived (one per star) while the page-locked ring is expensive
+// to allocate (cudaHostAlloc ~ 0.5 ms / MB), so it outlives them.  A call holds the
+// device's mutex from its first use of the pool to its final synchronisation.
+struct StagePool {
+  std::mutex mu;
+  DevBuf host_stage[2], host_ll[2];
+  PinBuf pin_in[2], pin_out[2];
+  cudaEvent_t pin_in_free[2] = {nullptr, nullptr};
+  cudaStream_t aux_stream[2] = {nullptr, nullptr};
+};
+constexpr int kMaxStageDevices = 64;
+StagePool g_stage[kMaxStageDevices];
+
 }  // namespace
 
 struct TjbHandle {
@@ -90,10 +105,7 @@ struct TjbHandle {
   double const_s = 0;
   // scratch
   DevBuf acc_mask, acc_counts, acc_offsets, acc_totals, misc, stats, trig;
-  DevBuf host_stage[2], host_ll[2];
-  PinBuf pin_in[2], pin_out[2];
-  cudaEvent_t pin_in_free[2] = {nullptr, nullptr};
-  cudaStream_t aux_stream[2] = {nullptr, nullptr};
+  StagePool *stg = nullptr;  // this device's host-streaming resources (shared by handles)
   int ll_ctas_per_sm = 0;
   // extra (peer) keys the likelihood kernel max-updates besides the one passed per call
   long long *peer_keys[kMaxPeers] = {nullptr};
@@ -300,6 +312,11 @@ int tjb_create(const TjbSpec *spec, int device, TjbHandle **out) {
 
   TjbHandle *h = new TjbHandle();
   h->device = device;
+  if (device < 0 || device >= kMaxStageDevices) {
+    delete h;
+    return fail(TJB_E_INVALID, "device index out of range");
+  }
+  h->stg = &g_stage[device];
   h->n_sm = prop.multiProcessorCount;
   h->cc_major = prop.major;
   h->cc_minor = prop.minor;
@@ -341,12 +358,6 @@ void tjb_destroy(TjbHandle *h) {
   h->tab_const.release(); h->tab_jit.release();
   h->acc_mask.release(); h->acc_counts.release(); h->acc_offsets.release();
   h->acc_totals.release(); h->misc.release(); h->stats.release(); h->trig.release();
-  for (int i = 0; i < 2; i++) {
-    h->host_stage[i].release(); h->host_ll[i].release();
-    h->pin_in[i].release(); h->pin_out[i].release();
-    if (h->pin_in_free[i]) cudaEventDestroy(h->pin_in_free[i]);
-    if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]);
-  }
   delete h;
 }
 
@@ -380,7 +391,7 @@ int tjb_get_stats(TjbHandle *h, uint64_t *h_stats, int reset) {
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));
   for (int i = 0; i < 2; i++)
-    if (h->aux_stream[i]) CU(cudaStreamSynchronize(h->aux_stream[i]));
+    if (h->stg->aux_stream[i]) CU(cudaStreamSynchronize(h->stg->aux_stream[i]));
   unsigned long long v[4];
   CU(cudaMemcpy(v, h->stats.p, sizeof(v), cudaMemcpyDeviceToHost));
   for (int i = 0; i < 4; i++) h_stats[i] = v[i];
@@ -424,54 +435,6 @@ int tjb_marginal_ll_aos(TjbHandle *h, const double *d_chunk, int uniform_s, int6
   return run_ll(h, pv, uniform_s != 0, s0, n, d_ll, (long long *)d_llmax_key, h->stream);
 }
 
-int tjb_marginal_ll_host(TjbHandle *h, const double *h_chunk, int64_t n, double *h_ll) {
-  if (!h) return fail(TJB_E_INVALID, "null handle");
-  if (n < 0) return fail(TJB_E_INVALID, "negative n");
-  if (n == 0) return TJB_OK;
-  if (!h_chunk || !h_ll) return fail(TJB_E_INVALID, "null host pointer");
-  CU(cudaSetDevice(h->device));
-  // Optimistic execution: assume every row carries the jitter of row 0 (true for
-  // the default prior, s = const) and run the constant-jitter kernel, which also
-  // checks the assumption on the rows it reads; if any row disagrees, rerun with
-  // the per-sample-jitter kernel.  No host pass over the chunk is needed.
-  const double s0 = h_chunk[4];
-  const int64_t slice = 1 << 20;
-  for (int i = 0; i < 2; i++) {
-    if (!h->aux_stream[i]) CU(cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking));
-    const int64_t m = std::min(slice, n);
-    if (h->host_stage[i].ensure((size_t)m * 5 * sizeof(double)) ||
-        h->host_ll[i].ensure((size_t)m * sizeof(double)))
-      return fail(TJB_E_NOMEM, "cudaMalloc staging");
-  }
-  if (h->acc_totals.ensure(2 * sizeof(unsigned long long))) return fail(TJB_E_NOMEM, "cudaMalloc");
-  int *d_flag = (int *)h->acc_totals.p;
-  CU(cudaStreamSynchronize(h->stream));  // order after earlier work on the handle's stream
-  CU(cudaMemset(d_flag, 0, sizeof(int)));
-  for (int pass = 0; pass < 2; pass++) {
-    const bool uniform = (pass == 0);
-    if (!uniform && h->jitter_mode == 0) break;
-    int b = 0;
-    for (int64_t lo = 0; lo < n; lo += slice, b ^= 1) {
-      const int64_t m = std::min(slice, n - lo);
-      cudaStream_t st = h->aux_stream[b];
-      double *d_in = (double *)h->host_stage[b].p, *d_out = (double *)h->host_ll[b].p;
-      CU(cudaMemcpyAsync(d_in, h_chunk + 5 * lo, (size_t)m * 5 * sizeof(double),
-                         cudaMemcpyHostToDevice, st));
-      PriorView pv = {nullptr, nullptr, nullptr, nullptr, nullptr, d_in, s0,
-                      (uniform && h->jitter_mode) ? d_flag : nullptr};
-      int rc = run_ll(h, pv, uniform, s0, m, d_out, nullptr, st);
-      if (rc) return rc;
-      CU(cudaMemcpyAsync(h_ll + lo, d_out, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
-    }
-    CU(cudaStreamSynchronize(h->aux_stream[0]));
-    CU(cudaStreamSynchronize(h->aux_stream[1]));
-    int flag = 0;
-    CU(cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
-    if (!flag) break;
-  }
-  return TJB_OK;
-}
-
 namespace {
 
 // true when the driver would have to stage a copy from / to this host pointer itself
@@ -488,7 +451,7 @@ bool is_pageable(const void *ptr) {
 // dst[c][0..count) = src[c][0..count) for n_cols columns, split over host threads
 void parallel_copy(double *const *dst, const double *const *src, int n_cols, size_t count) {
   const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-  const int per_col = (int)std::max(1u, std::min(4u, hw / (unsigned)n_cols));
+  const int per_col = (int)std::max(1u, std::min(n_cols == 1 ? 8u : 4u, hw / (unsigned)n_cols));
   if (count < (1u << 16) || hw == 1) {
     for (int c = 0; c < n_cols; c++) std::memcpy(dst[c], src[c], count * sizeof(double));
     return;
@@ -503,12 +466,101 @@ void parallel_copy(double *const *dst, const double *const *src, int n_cols, siz
   for (auto &t : pool) t.join();
 }
 
+}  // namespace
+
+int tjb_marginal_ll_host(TjbHandle *h, const double *h_chunk, int64_t n, double *h_ll) {
+  if (!h) return fail(TJB_E_INVALID, "null handle");
+  if (n < 0) return fail(TJB_E_INVALID, "negative n");
+  if (n == 0) return TJB_OK;
+  if (!h_chunk || !h_ll) return fail(TJB_E_INVALID, "null host pointer");
+  CU(cudaSetDevice(h->device));
+  std::lock_guard<std::mutex> lock(h->stg->mu);
+  StagePool &sp = *h->stg;
+  // Optimistic execution: assume every row carries the jitter of row 0 (true for
+  // the default prior, s = const) and run the constant-jitter kernel, which also
+  // checks the assumption on the rows it reads; if any row disagrees, rerun with
+  // the per-sample-jitter kernel.  No host pass over the chunk is needed.
+  const double s0 = h_chunk[4];
+  const int64_t slice = 1 << 20;
+  const int64_t m_max = std::min(slice, n);
+  const bool stage_in = is_pageable(h_chunk), stage_out = is_pageable(h_ll);
+  for (int i = 0; i < 2; i++) {
+    if (!sp.aux_stream[i]) CU(cudaStreamCreateWithFlags(&sp.aux_stream[i], cudaStreamNonBlocking));
+    if (!sp.pin_in_free[i]) CU(cudaEventCreateWithFlags(&sp.pin_in_free[i], cudaEventDisableTiming));
+    if (sp.host_stage[i].ensure((size_t)m_max * 5 * sizeof(double)) ||
+        sp.host_ll[i].ensure((size_t)m_max * sizeof(double)))
+      return fail(TJB_E_NOMEM, "cudaMalloc staging");
+    if ((stage_in && sp.pin_in[i].ensure((size_t)m_max * 5 * sizeof(double))) ||
+        (stage_out && sp.pin_out[i].ensure((size_t)m_max * sizeof(double))))
+      return fail(TJB_E_NOMEM, "cudaHostAlloc staging");
+  }
+  if (h->acc_totals.ensure(2 * sizeof(unsigned long long))) return fail(TJB_E_NOMEM, "cudaMalloc");
+  int *d_flag = (int *)h->acc_totals.p;
+  CU(cudaStreamSynchronize(h->stream));  // order after earlier work on the handle's stream
+  CU(cudaMemset(d_flag, 0, sizeof(int)));
+  int64_t out_lo[2] = {-1, -1}, out_m[2] = {0, 0};
+  auto drain_out = [&](int b) -> int {  // pin_out[b] -> h_ll once its D2H is done
+    if (out_lo[b] < 0) return TJB_OK;
+    CU(cudaStreamSynchronize(sp.aux_stream[b]));
+    std::memcpy(h_ll + out_lo[b], sp.pin_out[b].p, (size_t)out_m[b] * sizeof(double));
+    out_lo[b] = -1;
+    return TJB_OK;
+  };
+  for (int pass = 0; pass < 2; pass++) {
+    const bool uniform = (pass == 0);
+    if (!uniform && h->jitter_mode == 0) break;
+    int b = 0;
+    int64_t n_slices = 0;
+    for (int64_t lo = 0; lo < n; lo += slice, b ^= 1, n_slices++) {
+      const int64_t m = std::min(slice, n - lo);
+      cudaStream_t st = sp.aux_stream[b];
+      double *d_in = (double *)sp.host_stage[b].p, *d_out = (double *)sp.host_ll[b].p;
+      const double *src = h_chunk + 5 * lo;
+      if (stage_in) {
+        if (n_slices >= 2) CU(cudaEventSynchronize(sp.pin_in_free[b]));
+        double *dst = (double *)sp.pin_in[b].p;
+        parallel_copy(&dst, &src, 1, (size_t)m * 5);
+        src = dst;
+      }
+      CU(cudaMemcpyAsync(d_in, src, (size_t)m * 5 * sizeof(double), cudaMemcpyHostToDevice, st));
+      if (stage_in) CU(cudaEventRecord(sp.pin_in_free[b], st));
+      PriorView pv = {nullptr, nullptr, nullptr, nullptr, nullptr, d_in, s0,
+                      (uniform && h->jitter_mode) ? d_flag : nullptr};
+      int rc = run_ll(h, pv, uniform, s0, m, d_out, nullptr, st);
+      if (rc) return rc;
+      if (stage_out) {
+        rc = drain_out(b);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(sp.pin_out[b].p, d_out, (size_t)m * sizeof(double),
+                           cudaMemcpyDeviceToHost, st));
+        out_lo[b] = lo;
+        out_m[b] = m;
+      } else {
+        CU(cudaMemcpyAsync(h_ll + lo, d_out, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+      }
+    }
+    CU(cudaStreamSynchronize(sp.aux_stream[0]));
+    CU(cudaStreamSynchronize(sp.aux_stream[1]));
+    for (int i = 0; i < 2; i++) {
+      int rc = drain_out(i);
+      if (rc) return rc;
+    }
+    int flag = 0;
+    CU(cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (!flag) break;
+  }
+  return TJB_OK;
+}
+
+namespace {
+
 // Streams host columns through the GPU in slices on two streams: host (pageable ->
 // page-locked ring, threaded) | H2D | kernel | D2H all overlap.  The ll values go to
 // h_ll (host) or stay in d_ll (device, with the running max in d_key), or both.
 int host_soa_stream(TjbHandle *h, const double *const cols[5], int n_cols, double s_const,
                     int64_t n, double *h_ll, double *d_ll, int64_t *d_key) {
   CU(cudaSetDevice(h->device));
+  std::lock_guard<std::mutex> lock(h->stg->mu);
   bool stage_in = false;
   for (int c = 0; c < n_cols; c++) stage_in = stage_in || is_pageable(cols[c]);
   const bool stage_out = h_ll && is_pageable(h_ll);
@@ -517,21 +569,21 @@ int host_soa_stream(TjbHandle *h, const double *const cols[5], int n_cols, doubl
   while (slice > (1 << 18) && slice * 8 > n) slice >>= 1;
   const int64_t m_max = std::min(slice, n);
   for (int i = 0; i < 2; i++) {
-    if (!h->aux_stream[i]) CU(cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking));
-    if (!h->pin_in_free[i]) CU(cudaEventCreateWithFlags(&h->pin_in_free[i], cudaEventDisableTiming));
-    if (h->host_stage[i].ensure((size_t)m_max * 5 * sizeof(double)) ||
-        (!d_ll && h->host_ll[i].ensure((size_t)m_max * sizeof(double))))
+    if (!h->stg->aux_stream[i]) CU(cudaStreamCreateWithFlags(&h->stg->aux_stream[i], cudaStreamNonBlocking));
+    if (!h->stg->pin_in_free[i]) CU(cudaEventCreateWithFlags(&h->stg->pin_in_free[i], cudaEventDisableTiming));
+    if (h->stg->host_stage[i].ensure((size_t)m_max * 5 * sizeof(double)) ||
+        (!d_ll && h->stg->host_ll[i].ensure((size_t)m_max * sizeof(double))))
       return fail(TJB_E_NOMEM, "cudaMalloc staging");
-    if ((stage_in && h->pin_in[i].ensure((size_t)m_max * n_cols * sizeof(double))) ||
-        (stage_out && h->pin_out[i].ensure((size_t)m_max * sizeof(double))))
+    if ((stage_in && h->stg->pin_in[i].ensure((size_t)m_max * n_cols * sizeof(double))) ||
+        (stage_out && h->stg->pin_out[i].ensure((size_t)m_max * sizeof(double))))
       return fail(TJB_E_NOMEM, "cudaHostAlloc staging");
   }
   CU(cudaStreamSynchronize(h->stream));
   int64_t out_lo[2] = {-1, -1}, out_m[2] = {0, 0};  // slices parked in pin_out[b]
   auto drain_out = [&](int b) -> int {              // pin_out[b] -> h_ll once its D2H is done
     if (out_lo[b] < 0) return TJB_OK;
-    CU(cudaStreamSynchronize(h->aux_stream[b]));
-    std::memcpy(h_ll + out_lo[b], h->pin_out[b].p, (size_t)out_m[b] * sizeof(double));
+    CU(cudaStreamSynchronize(h->stg->aux_stream[b]));
+    std::memcpy(h_ll + out_lo[b], h->stg->pin_out[b].p, (size_t)out_m[b] * sizeof(double));
     out_lo[b] = -1;
     return TJB_OK;
   };
@@ -539,15 +591,15 @@ int host_soa_stream(TjbHandle *h, const double *const cols[5], int n_cols, doubl
   int64_t n_slices = 0;
   for (int64_t lo = 0; lo < n; lo += slice, b ^= 1, n_slices++) {
     const int64_t m = std::min(slice, n - lo);
-    cudaStream_t st = h->aux_stream[b];
-    double *d_in = (double *)h->host_stage[b].p;
-    double *d_out = d_ll ? d_ll + lo : (double *)h->host_ll[b].p;
+    cudaStream_t st = h->stg->aux_stream[b];
+    double *d_in = (double *)h->stg->host_stage[b].p;
+    double *d_out = d_ll ? d_ll + lo : (double *)h->stg->host_ll[b].p;
     const double *src[5];
     if (stage_in) {
-      if (n_slices >= 2) CU(cudaEventSynchronize(h->pin_in_free[b]));  // slot's last H2D done
+      if (n_slices >= 2) CU(cudaEventSynchronize(h->stg->pin_in_free[b]));  // slot's last H2D done
       double *dst[5];
       for (int c = 0; c < n_cols; c++) {
-        dst[c] = (double *)h->pin_in[b].p + (size_t)c * m_max;
+        dst[c] = (double *)h->stg->pin_in[b].p + (size_t)c * m_max;
         src[c] = cols[c] + lo;
       }
       parallel_copy(dst, src, n_cols, (size_t)m);
@@ -558,7 +610,7 @@ int host_soa_stream(TjbHandle *h, const double *const cols[5], int n_cols, doubl
     for (int c = 0; c < n_cols; c++)
       CU(cudaMemcpyAsync(d_in + (size_t)c * m_max, src[c], (size_t)m * sizeof(double),
                          cudaMemcpyHostToDevice, st));
-    if (stage_in) CU(cudaEventRecord(h->pin_in_free[b], st));
+    if (stage_in) CU(cudaEventRecord(h->stg->pin_in_free[b], st));
     PriorView pv = {d_in, d_in + m_max, d_in + 2 * m_max, d_in + 3 * m_max,
                     n_cols == 5 ? d_in + 4 * m_max : nullptr, nullptr, 0.0, nullptr};
     int rc = run_ll(h, pv, n_cols == 4, s_const, m, d_out, (long long *)d_key, st);
@@ -567,7 +619,7 @@ int host_soa_stream(TjbHandle *h, const double *const cols[5], int n_cols, doubl
       if (stage_out) {
         rc = drain_out(b);
         if (rc) return rc;
-        CU(cudaMemcpyAsync(h->pin_out[b].p, d_out, (size_t)m * sizeof(double),
+        CU(cudaMemcpyAsync(h->stg->pin_out[b].p, d_out, (size_t)m * sizeof(double),
                            cudaMemcpyDeviceToHost, st));
         out_lo[b] = lo;
         out_m[b] = m;
@@ -576,8 +628,8 @@ int host_soa_stream(TjbHandle *h, const double *const cols[5], int n_cols, doubl
       }
     }
   }
-  CU(cudaStreamSynchronize(h->aux_stream[0]));
-  CU(cudaStreamSynchronize(h->aux_stream[1]));
+  CU(cudaStreamSynchronize(h->stg->aux_stream[0]));
+  CU(cudaStreamSynchronize(h->stg->aux_stream[1]));
   for (int i = 0; i < 2; i++) {
     int rc = drain_out(i);
     if (rc) return rc;

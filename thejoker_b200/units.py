@@ -83,7 +83,11 @@ class Unit:
         other = as_unit(other)
         if self.dims != other.dims:
             raise UnitsError(f"'{self}' and '{other}' are not convertible")
-        return np.asarray(value, dtype=float) * (self.scale / other.scale)
+        factor = self.scale / other.scale
+        value = np.asarray(value, dtype=float)
+        # same unit: hand back the array itself (as astropy does) -- a 2^28-row prior
+        # column must not be copied just to be multiplied by one
+        return value if factor == 1.0 else value * factor
 
     def __repr__(self):
         return f"Unit('{self}')"

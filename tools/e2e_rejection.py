@@ -41,30 +41,30 @@ for name, d in (("data", data), ("flat", flat)):
     joker = tj.TheJoker(prior, rng=np.random.default_rng(42))
     t, s = timed(lambda: joker.rejection_sample(d, ps, max_posterior_samples=256, in_memory=True))
     out[f"rejection_2p24_host_prior_{name}"] = dict(seconds=t, n_samples=len(s), samples_per_s=n / t,
-                                                  stats=joker.last_stats)
+                                                  stats=dict(joker.last_stats))
 # (a2) host prior, 2^26 samples (2.1 GB of pageable numpy columns): plain + iterative
 n = 1 << 26
 ps = prior.sample(size=n, rng=np.random.default_rng(2))
 joker = tj.TheJoker(prior, rng=np.random.default_rng(42))
 t, s = timed(lambda: joker.rejection_sample(flat, ps, max_posterior_samples=256, in_memory=True))
 out["rejection_2p26_host_prior_flat"] = dict(seconds=t, n_samples=len(s), samples_per_s=n / t,
-                                             stats=joker.last_stats)
+                                             stats=dict(joker.last_stats))
 t, s = timed(lambda: joker.rejection_sample(data, ps, max_posterior_samples=256, in_memory=True))
 out["rejection_2p26_host_prior_data"] = dict(seconds=t, n_samples=len(s), samples_per_s=n / t,
-                                             stats=joker.last_stats)
+                                             stats=dict(joker.last_stats))
 t, s = timed(lambda: joker.iterative_rejection_sample(flat, ps, n_requested_samples=256))
 out["iterative_2p26_host_prior_flat_256"] = dict(seconds=t, n_samples=len(s),
-                                                 stats=joker.last_stats)
+                                                 stats=dict(joker.last_stats))
 t, s = timed(lambda: joker.iterative_rejection_sample(data, ps, n_requested_samples=8))
 out["iterative_2p26_host_prior_data_8"] = dict(seconds=t, n_samples=len(s),
-                                               stats=joker.last_stats)
+                                               stats=dict(joker.last_stats))
 del ps
 # (b) device prior, 2^28 samples
 n = 1 << 28
 joker = tj.TheJoker(prior, rng=np.random.default_rng(42))
 t, s = timed(lambda: joker.rejection_sample(flat, n, max_posterior_samples=256), reps=2)
 out["rejection_2p28_device_prior_flat"] = dict(seconds=t, n_samples=len(s), samples_per_s=n / t,
-                                               stats=joker.last_stats)
+                                               stats=dict(joker.last_stats))
 # (c) accept alone on 2^28 resident lls, numpy-identical uniforms generated on the device
 helper = joker._make_joker_helper(flat)
 ll = torch.randn(n, dtype=torch.float64, device="cuda") * 3 - 50
