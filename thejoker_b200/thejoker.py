@@ -116,9 +116,13 @@ class TheJoker:
             ln_prior = prior_samples.ln_prior() if prior_samples.has_ln_prior else None
             return cols, ln_prior
         if isinstance(prior_samples, JokerSamples):
-            cols = prior_samples.columns(units=helper.internal_units, names=helper.packed_order)
-            if prior_samples._uniform_s and len(cols[4]):
-                cols[4] = float(cols[4][0])
+            names = list(helper.packed_order)
+            if prior_samples._uniform_s and len(prior_samples):
+                # constant jitter: convert one element, not a 2^28-row column
+                cols = prior_samples.columns(units=helper.internal_units, names=names[:4])
+                cols.append(float(prior_samples["s"][:1].to_value(helper.internal_units["s"])[0]))
+            else:
+                cols = prior_samples.columns(units=helper.internal_units, names=names)
             ln_prior = prior_samples["ln_prior"].value if "ln_prior" in prior_samples else None
             return cols, ln_prior
         arr = np.asarray(prior_samples, dtype=np.float64)

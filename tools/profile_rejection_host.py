@@ -19,7 +19,11 @@ prior = default_prior(1, sigma_K0=30.0, P_min=2.0, P_max=1024.0)
 flat, _ = make_noisy_data(64, seed=42, K=1e-4)
 ps = prior.sample(size=1 << log2n, rng=np.random.default_rng(1))
 joker = tj.TheJoker(prior, rng=np.random.default_rng(42))
-run = lambda: joker.rejection_sample(flat, ps, max_posterior_samples=256, in_memory=True)
+mode = sys.argv[2] if len(sys.argv) > 2 else "rejection"
+if mode == "iterative":
+    run = lambda: joker.iterative_rejection_sample(flat, ps, n_requested_samples=256)
+else:
+    run = lambda: joker.rejection_sample(flat, ps, max_posterior_samples=256, in_memory=True)
 run()
 torch.cuda.synchronize()
 pr = cProfile.Profile()
@@ -27,4 +31,4 @@ pr.enable()
 run()
 torch.cuda.synchronize()
 pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
+pstats.Stats(pr).sort_stats("cumulative").print_stats(22)
