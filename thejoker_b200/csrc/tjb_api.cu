@@ -36,20 +36,61 @@ int fail(int code, const std::string &msg) {
       return fail(TJB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
   } while (0)
 
+// Device allocations of the handles go through a small per-device cache of released
+// blocks: a handle lives for one star, and cudaMalloc / cudaFree (which synchronises the
+// device) dominated its creation and destruction.  Blocks are handed out again only to
+// requests of a similar size; tjb_destroy synchronises the device before releasing.
+constexpr int kMaxDevices = 64;
+struct BlockCache {
+  std::mutex mu;
+  std::vector<std::pair<void *, size_t>> blocks[kMaxDevices];
+  size_t held[kMaxDevices] = {0};
+  static constexpr size_t kMaxHeld = (size_t)1 << 30;
+  void *take(int dev, size_t need, size_t *got) {
+    std::lock_guard<std::mutex> lock(mu);
+    auto &v = blocks[dev];
+    int best = -1;
+    for (int i = 0; i < (int)v.size(); i++)
+      if (v[i].second >= need && v[i].second <= std::max<size_t>(2 * need, 4096) &&
+          (best < 0 || v[i].second < v[best].second))
+        best = i;
+    if (best < 0) return nullptr;
+    void *p = v[best].first;
+    *got = v[best].second;
+    held[dev] -= v[best].second;
+    v.erase(v.begin() + best);
+    return p;
+  }
+  bool give(int dev, void *p, size_t bytes) {
+    std::lock_guard<std::mutex> lock(mu);
+    if (held[dev] + bytes > kMaxHeld || blocks[dev].size() >= 256) return false;
+    blocks[dev].emplace_back(p, bytes);
+    held[dev] += bytes;
+    return true;
+  }
+};
+BlockCache g_blocks;
+
 struct DevBuf {
   void *p = nullptr;
   size_t bytes = 0;
+  int dev = -1;
   int ensure(size_t need) {
     if (need <= bytes) return 0;
-    if (p) cudaFree(p);
-    p = nullptr;
-    bytes = 0;
-    if (cudaMalloc(&p, need) != cudaSuccess) return -1;
+    release();
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+    need = (need + 255) & ~(size_t)255;
+    p = g_blocks.take(dev, need, &bytes);
+    if (p) return 0;
+    if (cudaMalloc(&p, need) != cudaSuccess) {
+      p = nullptr;
+      return -1;
+    }
     bytes = need;
     return 0;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p && !g_blocks.give(dev, p, bytes)) cudaFree(p);
     p = nullptr;
     bytes = 0;
   }
@@ -87,8 +128,18 @@ struct StagePool {
   cudaEvent_t pin_in_free[2] = {nullptr, nullptr};
   cudaStream_t aux_stream[2] = {nullptr, nullptr};
 };
-constexpr int kMaxStageDevices = 64;
+constexpr int kMaxStageDevices = kMaxDevices;
 StagePool g_stage[kMaxStageDevices];
+
+// per-device constants shared by every handle: SM count / compute capability and the
+// sin/cos node table of the Kepler solver (never freed)
+struct DeviceShared {
+  std::mutex mu;
+  bool ready = false;
+  int n_sm = 0, cc_major = 0, cc_minor = 0;
+  void *trig = nullptr;
+};
+DeviceShared g_shared[kMaxDevices];
 
 }  // namespace
 
@@ -104,7 +155,8 @@ struct TjbHandle {
   bool const_valid = false;
   double const_s = 0;
   // scratch
-  DevBuf acc_mask, acc_counts, acc_offsets, acc_totals, misc, stats, trig;
+  DevBuf acc_mask, acc_counts, acc_offsets, acc_totals, misc, stats;
+  void *trig = nullptr;  // shared per-device sin/cos table (DeviceShared)
   StagePool *stg = nullptr;  // this device's host-streaming resources (shared by handles)
   int ll_ctas_per_sm = 0;
   // extra (peer) keys the likelihood kernel max-updates besides the one passed per call
@@ -123,7 +175,7 @@ int upload_table(TjbHandle *h, DevBuf &buf, const std::vector<double> &tab, Star
   CU(cudaStreamSynchronize(h->stream));  // tab is a caller-owned staging buffer
   sp.table = (const double *)buf.p;
   sp.stats = (unsigned long long *)h->stats.p;
-  sp.trig_table = (const SinCos *)h->trig.p;
+  sp.trig_table = (const SinCos *)h->trig;
   return TJB_OK;
 }
 
@@ -305,34 +357,36 @@ int tjb_create(const TjbSpec *spec, int device, TjbHandle **out) {
     return fail(TJB_E_CUDA, "no CUDA device available: libthejoker_b200 has no CPU path");
   if (device < 0 || device >= n_dev) return fail(TJB_E_INVALID, "device index out of range");
   CU(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10)
+  if (device >= kMaxDevices) return fail(TJB_E_INVALID, "device index out of range");
+  DeviceShared &ds = g_shared[device];
+  {
+    std::lock_guard<std::mutex> lock(ds.mu);
+    if (!ds.ready) {
+      CU(cudaDeviceGetAttribute(&ds.n_sm, cudaDevAttrMultiProcessorCount, device));
+      CU(cudaDeviceGetAttribute(&ds.cc_major, cudaDevAttrComputeCapabilityMajor, device));
+      CU(cudaDeviceGetAttribute(&ds.cc_minor, cudaDevAttrComputeCapabilityMinor, device));
+      if (ds.cc_major >= 10) {
+        const std::vector<SinCos> tt = make_trig_table();
+        CU(cudaMalloc(&ds.trig, tt.size() * sizeof(SinCos)));
+        CU(cudaMemcpy(ds.trig, tt.data(), tt.size() * sizeof(SinCos), cudaMemcpyHostToDevice));
+      }
+      ds.ready = true;
+    }
+  }
+  if (ds.cc_major < 10)
     return fail(TJB_E_CUDA, "device is not sm_100-class; this library is built for sm_100a only");
 
   TjbHandle *h = new TjbHandle();
   h->device = device;
-  if (device < 0 || device >= kMaxStageDevices) {
-    delete h;
-    return fail(TJB_E_INVALID, "device index out of range");
-  }
   h->stg = &g_stage[device];
-  h->n_sm = prop.multiProcessorCount;
-  h->cc_major = prop.major;
-  h->cc_minor = prop.minor;
+  h->n_sm = ds.n_sm;
+  h->cc_major = ds.cc_major;
+  h->cc_minor = ds.cc_minor;
+  h->trig = ds.trig;
   if (h->stats.ensure(4 * sizeof(unsigned long long)) ||
       cudaMemset(h->stats.p, 0, 4 * sizeof(unsigned long long)) != cudaSuccess) {
     tjb_destroy(h);
     return fail(TJB_E_NOMEM, "cudaMalloc stats");
-  }
-  {
-    const std::vector<SinCos> tt = make_trig_table();
-    if (h->trig.ensure(tt.size() * sizeof(SinCos)) ||
-        cudaMemcpy(h->trig.p, tt.data(), tt.size() * sizeof(SinCos), cudaMemcpyHostToDevice) !=
-            cudaSuccess) {
-      tjb_destroy(h);
-      return fail(TJB_E_NOMEM, "cudaMalloc trig table");
-    }
   }
   rc = load_star(h, spec);
   if (rc != TJB_OK) {
@@ -355,9 +409,10 @@ int tjb_update_star(TjbHandle *h, const TjbSpec *spec) {
 void tjb_destroy(TjbHandle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  cudaDeviceSynchronize();  // released blocks are reused by the next handle
   h->tab_const.release(); h->tab_jit.release();
   h->acc_mask.release(); h->acc_counts.release(); h->acc_offsets.release();
-  h->acc_totals.release(); h->misc.release(); h->stats.release(); h->trig.release();
+  h->acc_totals.release(); h->misc.release(); h->stats.release();
   delete h;
 }
 
@@ -813,7 +868,7 @@ int tjb_design_column(TjbHandle *h, const double *h_row, double *h_z, int32_t *h
   for (int n = 0; n < N; n++) dt[n] = h->star.t[n] - h->star.t_ref;
   CU(cudaMemcpyAsync(d_dt, dt.data(), (size_t)N * 8, cudaMemcpyHostToDevice, h->stream));
   design_column_kernel<<<1, 32, 0, h->stream>>>(d_dt, N, h_row[0], h_row[1], h_row[2], h_row[3], 0.0,
-                                              (const SinCos *)h->trig.p, d_z,
+                                              (const SinCos *)h->trig, d_z,
                                               d_st);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(h_z, d_z, (size_t)N * 8, cudaMemcpyDeviceToHost, h->stream));

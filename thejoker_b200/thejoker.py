@@ -130,8 +130,10 @@ class TheJoker:
             raise ValueError("packed prior samples must have shape (n, 5)")
         return [np.ascontiguousarray(arr[:, i]) for i in range(5)], None
 
-    def _engine(self, data, cols):
-        helpers = {}
+    def _engine(self, data, cols, helper0=None):
+        # helper0: the helper the caller already built to read units / columns; reused
+        # for its device instead of creating a second handle for the same star
+        helpers = {} if helper0 is None else {helper0.device: helper0}
 
         def make(d):
             if d not in helpers:
@@ -244,7 +246,7 @@ class TheJoker:
             return helper0.marginal_ln_likelihood_columns(
                 *cols[:4], s=None if np.ndim(s) == 0 else s,
                 s_const=float(s) if np.ndim(s) == 0 else 0.0)
-        eng, _ = self._engine(data, cols)
+        eng, _ = self._engine(data, cols, helper0)
         eng.compute_ll()
         return eng.gather_ll()
 
@@ -291,7 +293,7 @@ class TheJoker:
         if max_posterior_samples is None:
             max_posterior_samples = n_use
 
-        eng, helper = self._engine(data, cols)
+        eng, helper = self._engine(data, cols, helper0)
         eng.compute_ll()
         good, _ = self._uniform_accept(eng, n_use, max_posterior_samples)
         full_idx = good if sel is None else sel[good]
@@ -372,11 +374,11 @@ class TheJoker:
             all_idx = self.rng.choice(n_total, size=n_max, replace=False)
             cols = [c if np.ndim(c) == 0 else c[all_idx] for c in cols]
         else:
-            all_idx = np.arange(0, n_max, 1)
+            all_idx = None  # identity (np.arange(n_max) would cost 2 GB at 2^28 rows)
             if n_max < n_total:
                 cols = [c if np.ndim(c) == 0 else c[:n_max] for c in cols]
 
-        eng, helper = self._engine(data, cols)
+        eng, helper = self._engine(data, cols, helper0)
         start_idx = 0
         n_accum = 0
         good = np.zeros(0, dtype=np.int64)
@@ -405,7 +407,7 @@ class TheJoker:
             raise RuntimeError("Hit maximum number of iterations!")
 
         good = good[:n_requested_samples]
-        full_idx = all_idx[good]
+        full_idx = good if all_idx is None else all_idx[good]
         samples = self._full_samples(helper, self._rows(cols, good), self.rng, n_linear_samples,
                                      in_memory, n_batches)
         if return_logprobs:
