@@ -139,6 +139,11 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    numa_cpus = None
+    if world > 1 and os.environ.get("TJB_BENCH_NUMA_BIND", "1") == "1":
+        from thejoker_b200.sharding import bind_to_device_cpus
+
+        numa_cpus = bind_to_device_cpus(local)  # e2e staging buffers on the GPU's node
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
@@ -303,6 +308,7 @@ def run_ours(args):
                    "n_prior": n_total, "n_epochs": N_EPOCHS, "sharding": f"contiguous x{world}"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_e2e * 32),
                 "d2h_bytes_per_step": int(n_e2e * 8), "n_per_rank": int(n_e2e), "steps": e2e_steps,
+                "rank0_cpu_binding": numa_cpus,
                 "call": "TheJoker.marginal_ln_likelihood data path: pinned host columns P, e, "
                         "omega, M0 (s constant) in, host ll out (CJokerHelper."
                         "marginal_ln_likelihood_columns -> tjb_marginal_ll_host_soa)",

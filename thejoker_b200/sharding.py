@@ -45,6 +45,33 @@ def batch_tasks(n_tasks, n_batches, arr=None, args=None, start_idx=0):
     return tasks
 
 
+def bind_to_device_cpus(device):
+    """Restrict this process to the host CPUs local to ``device`` (NVML's CPU affinity
+    of the GPU, intersected with the CPUs the process may already use), so that the
+    page-locked staging buffers of the host-streaming paths are allocated -- first touch
+    -- on the GPU's own NUMA node.  For one-process-per-GPU launches (torchrun); call it
+    before the first allocation.  Returns the CPU set in effect, or None if nothing was
+    changed (no NVML, a single node, or an empty intersection)."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device))
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, n_words)
+        local = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        want = local & allowed
+        if not want or want == allowed:
+            return None
+        os.sched_setaffinity(0, want)
+        return sorted(want)
+    except Exception:
+        return None
+
+
 def shard_ranges(n, n_shards):
     """[(lo, hi)] per shard; always n_shards entries (empty ranges when n < n_shards)."""
     if n >= n_shards:
