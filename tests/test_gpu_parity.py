@@ -274,6 +274,39 @@ def test_host_streaming_paths(torch_cuda, n):
         assert np.array_equal(d_ll.cpu().numpy(), ref)
 
 
+def test_host_streaming_from_concurrent_threads(torch_cuda):
+    """Handles are per star but the staging pool is per device: calls from several host
+    threads (each with its own handle) serialise on it and stay correct; so does the
+    block cache when handles are created and destroyed concurrently."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import thejoker_b200 as tj
+
+    specs = [star_spec(n_t, 1, seed=5 + n_t)[0] for n_t in (8, 16, 24, 32)]
+    chunk = prior_chunk((1 << 19) + 3)
+    hc = [np.ascontiguousarray(chunk[:, i]) for i in range(4)]
+    refs = []
+    for sp in specs:
+        h = tj.CJokerHelper.from_spec(sp, device=0)
+        refs.append(h.marginal_ln_likelihood_columns(*hc))
+        del h
+
+    def work(i):
+        outs = []
+        for _ in range(3):
+            h = tj.CJokerHelper.from_spec(specs[i], device=0)
+            outs.append(h.marginal_ll_host_columns(*hc).cpu().numpy())
+            outs.append(h.batch_marginal_ln_likelihood(chunk[:70_000]))
+            del h
+        return outs
+
+    with ThreadPoolExecutor(4) as ex:
+        results = list(ex.map(work, range(4)))
+    for ref, outs in zip(refs, results):
+        for k, o in enumerate(outs):
+            assert np.array_equal(o, ref[:len(o)]), k
+
+
 def test_engine_streamed_equals_resident(torch_cuda):
     """DeviceEngine over host columns: streaming (default) and resident modes give the
     same ll, max, accepted indices and rows, also for sub-ranges (iterative sampler)."""

@@ -31,6 +31,14 @@ for N, pt, kw in ((7, 1, {}), (16, 2, {"n_surveys": 2}), (33, 3, {})):
         helper.batch_get_posterior_samples(chunk[:3], 2, rng)
         helper.design_column(chunk[0])
     helper.pcg64_uniform(np.random.default_rng(0), 100_001, offset=17)
+    if N == 7:
+        # host-streaming paths over several ring slots (pageable source, staged)
+        big = prior_chunk(2 * (1 << 18) + 1000)
+        hc = [np.ascontiguousarray(big[:, i]) for i in range(4)]
+        d_ll = helper.marginal_ll_host_columns(*hc, llmax_key=helper.new_llmax_key())
+        h_ll = helper.marginal_ln_likelihood_columns(*hc)
+        assert np.array_equal(d_ll.cpu().numpy(), h_ll)
+        assert np.array_equal(helper.batch_marginal_ln_likelihood(big), h_ll)
 prior = default_prior(1, sigma_K0=25.0, P_min=5.0, P_max=500.0)
 flat, _ = make_data(8, rng=np.random.default_rng(11), K=1e-4)
 ps = prior.sample(size=20_000, return_logprobs=True, rng=np.random.default_rng(1))
