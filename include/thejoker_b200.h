@@ -163,6 +163,13 @@ int tjb_posterior_draw(TjbHandle *h, const double *h_rows, int64_t k, int n_per,
 /* row 0 of M_T for one sample (pyx:453-455): z[N]; h_stats[3] (optional) returns
  * extra FP32 steps, extra FP64 steps, non-converged epochs of the solver. */
 int tjb_design_column(TjbHandle *h, const double *h_row, double *h_z, int32_t *h_stats);
+/* ln of the un-marginalised likelihood of k full posterior samples
+ * (JokerSamples.ln_unmarginalized_likelihood, thejoker/samples.py:611-632): h_rows[k, 5+L]
+ * row-major [P, e, omega, M0, s, K, v0, (offsets), v1, ...] -- the layout
+ * batch_get_posterior_samples returns (pyx:531-542) -- in internal units;
+ * h_ll[k] = sum_n ln N(rv_n | M_n . x, 1/ivar_n + s^2).  The jitter always enters here,
+ * whatever jitter_mode says (the reference's samples.py does apply it). */
+int tjb_unmarginalized_ll(TjbHandle *h, const double *h_rows, int64_t k, double *h_ll);
 
 /* Solver statistics accumulated by every likelihood launch of this handle since the
  * last reset: h_stats[0] = extra FP64 Householder passes (lane-epochs that needed more

@@ -586,6 +586,36 @@ def test_multi_survey_offsets(torch_cuda, oracle_lib):
     assert list(s.keys())[:8] == ["P", "e", "omega", "M0", "s", "K", "v0", "dv0_1"]
 
 
+@pytest.mark.parametrize("args,kw", [((24, 2), {"n_surveys": 3}), ((40, 1), {}), ((12, 3), {})])
+def test_unmarginalized_likelihood_device(torch_cuda, oracle_lib, args, kw):
+    """tjb_unmarginalized_ll vs the formula of samples.py:611-632 evaluated in numpy on the
+    oracle's design column, and (no offsets) vs the host method of JokerSamples."""
+    import thejoker_b200 as tj
+
+    helper, spec, data, prior = make_helper(args, **kw)
+    orc = oracle_lib.OracleHelper.from_spec(spec)
+    chunk = prior_chunk(200, s_lognormal=(-1.0, 1.0))
+    rows, _ = helper.batch_get_posterior_samples(chunk, 2, np.random.default_rng(3))
+    got = helper.ln_unmarginalized_likelihood(rows)
+    T = np.asarray(spec["trend_M"]).reshape(len(spec["t"]), -1)
+    want = np.empty(len(rows))
+    for i, r in enumerate(rows):
+        model = r[5] * orc.design_column(r[:5]) + T @ r[6:]
+        var = 1.0 / spec["ivar"] + r[4] ** 2
+        want[i] = np.sum(-0.5 * ((spec["rv"] - model) ** 2 / var + np.log(2 * np.pi * var)))
+    assert np.max(rel_err(got, want)) < 1e-10
+    assert helper.ln_unmarginalized_likelihood(rows[:0]).shape == (0,)
+    with pytest.raises(ValueError):
+        helper.ln_unmarginalized_likelihood(rows[:, :-1])
+    samples = tj.JokerSamples.unpack(rows, helper.internal_units, t_ref=data.t_ref,
+                                     poly_trend=prior.poly_trend, n_offsets=prior.n_offsets)
+    dev = samples.ln_unmarginalized_likelihood(data, helper=helper)
+    assert np.array_equal(dev, got)
+    if not kw:
+        host = samples.ln_unmarginalized_likelihood(data)
+        assert np.max(rel_err(host, got)) < 1e-9
+
+
 def test_large_n_properties(torch_cuda):
     """Size-independent checks at BASELINE scale (2^24 samples, N=64): the fused max
     equals the max of the written ll, permutation equivariance, finite everywhere."""

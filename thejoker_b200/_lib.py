@@ -83,6 +83,7 @@ SYMBOLS = {
     "tjb_posterior_aA": (ctypes.c_int, [_H, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp]),
     "tjb_posterior_draw": (ctypes.c_int, [_H, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _vp,
                                           _vp, _vp]),
+    "tjb_unmarginalized_ll": (ctypes.c_int, [_H, _vp, ctypes.c_int64, _vp]),
     "tjb_design_column": (ctypes.c_int, [_H, _vp, _vp, _vp]),
     "tjb_get_stats": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int]),
     "tjb_fp64_peak": (ctypes.c_int, [_H, ctypes.c_int, _dp, _dp]),

@@ -145,6 +145,41 @@ __global__ void design_column_kernel(const double *__restrict__ dt, const int N,
   }
 }
 
+// ln of the UN-marginalised likelihood of full posterior samples (samples.py:611-632):
+// rows [P, e, omega, M0, s, x_0 .. x_{L-1}] with x in design-column order (K, v0,
+// offsets, v1, ...); tab = the per-sample-jitter epoch table [dt, 1/ivar, y - centre,
+// T_1 .. T_{L-1}].  ll = sum_n ln N(y_n | x_0 z_n + sum_k x_k T_nk, 1/ivar_n + s^2).
+// One thread per sample; a handful to a few million samples, so the table is read
+// through the read-only cache rather than staged.
+__global__ void __launch_bounds__(128)
+unmarginalized_ll_kernel(const double *__restrict__ tab, const int N, const int L, const int RS,
+                         const double centre, const double *__restrict__ rows, const long long n,
+                         const double zero, const SinCos *__restrict__ trig,
+                         double *__restrict__ ll) {
+  TrigCoef tc;
+  tc.load(zero, trig);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n_pad = (n + 31) & ~31LL;  // whole warps: the solver votes across lanes
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+    const bool live = i < n;
+    const double *row = rows + (live ? i : 0) * (5 + L);
+    const OrbitConsts oc = make_orbit_consts(tc, row[0], row[1], row[2], row[3]);
+    const double s2 = row[4] * row[4];
+    double acc = 0.0;
+    for (int m = 0; m < N; m++) {
+      const double *tr = tab + (size_t)m * RS;
+      const double z = rv_unit_column<false>(oc, tc, __ldg(tr), nullptr);
+      double model = row[5] * z;
+      if (L > 1) model = fma(row[6] - centre, __ldg(tr + 3), model);
+      for (int k = 2; k < L; k++) model = fma(row[5 + k], __ldg(tr + 2 + k), model);
+      const double var = __ldg(tr + 1) + s2;
+      const double r = __ldg(tr + 2) - model;
+      acc += r * r / var + log(6.283185307179586 * var);
+    }
+    if (live) ll[i] = -0.5 * acc;
+  }
+}
+
 // dependent-FMA chains, 8 independent accumulators per thread
 __global__ void __launch_bounds__(256) fp64_peak_kernel(const int iters, double *out) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,

@@ -879,6 +879,29 @@ int tjb_design_column(TjbHandle *h, const double *h_row, double *h_z, int32_t *h
   return TJB_OK;
 }
 
+int tjb_unmarginalized_ll(TjbHandle *h, const double *h_rows, int64_t n, double *h_ll) {
+  if (!h) return fail(TJB_E_INVALID, "null handle");
+  if (n < 0) return fail(TJB_E_INVALID, "negative n");
+  if (n == 0) return TJB_OK;
+  if (!h_rows || !h_ll) return fail(TJB_E_INVALID, "null host pointer");
+  CU(cudaSetDevice(h->device));
+  const int N = h->N, L = h->L, W = 5 + L;
+  if (h->misc.ensure((size_t)n * (W + 1) * sizeof(double))) return fail(TJB_E_NOMEM, "cudaMalloc");
+  double *d_rows = (double *)h->misc.p, *d_ll = d_rows + (size_t)n * W;
+  CU(cudaMemcpyAsync(d_rows, h_rows, (size_t)n * W * sizeof(double), cudaMemcpyHostToDevice,
+                     h->stream));
+  const int threads = 128;
+  const int grid = (int)std::min<long long>((n + threads - 1) / threads, (long long)h->n_sm * 16);
+  unmarginalized_ll_kernel<<<grid, threads, 0, h->stream>>>(
+      (const double *)h->tab_jit.p, N, L, row_stride(L),
+      h->star.centred ? (double)h->star.centre : 0.0, d_rows, n, 0.0, (const SinCos *)h->trig,
+      d_ll);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(h_ll, d_ll, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return TJB_OK;
+}
+
 int tjb_fp64_peak(TjbHandle *h, int iters, double *h_tflops, double *h_ms) {
   if (!h || !h_tflops) return fail(TJB_E_INVALID, "null argument");
   CU(cudaSetDevice(h->device));

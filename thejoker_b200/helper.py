@@ -317,6 +317,20 @@ class CJokerHelper:
                                                     _vp(normals), _vp(out), _vp(lls)))
         return out, np.repeat(lls, k)
 
+    def ln_unmarginalized_likelihood(self, rows):
+        """ln of the un-marginalised likelihood of full posterior samples, on the GPU
+        (samples.py:611-632): ``rows`` is the packed (k, 5 + n_linear) array
+        ``batch_get_posterior_samples`` returns, [P, e, omega, M0, s, K, v0, (offsets),
+        v1, ...] in internal units.  Survey offsets are part of the model here (the
+        reference's version builds the orbit from K and the polynomial trend only)."""
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        if rows.ndim != 2 or rows.shape[1] != 5 + self.n_linear:
+            raise ValueError(f"rows must have shape (k, {5 + self.n_linear})")
+        ll = np.full(rows.shape[0], np.nan)
+        self._sync_stream()
+        _lib.check(self._lib.tjb_unmarginalized_ll(self._h, _vp(rows), rows.shape[0], _vp(ll)))
+        return ll
+
     def test_likelihood_worker(self, chunk_row):
         """pyx:547-576: ll for one row; leaves a, A, b readable."""
         row = np.ascontiguousarray(chunk_row, dtype=np.float64).reshape(5)

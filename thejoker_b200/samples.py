@@ -218,9 +218,16 @@ class JokerSamples:
         return new
 
     # -- (unmarginalised) likelihood of posterior samples ----------------------
-    def ln_unmarginalized_likelihood(self, data):
-        """samples.py:611-632, with the orbit evaluated by a plain numpy Kepler solve
-        (host side; a handful of posterior samples)."""
+    def ln_unmarginalized_likelihood(self, data, helper=None):
+        """samples.py:611-632.  Without ``helper``: the orbit is evaluated by a plain numpy
+        Kepler solve on the host (a handful of posterior samples; like the reference, the
+        model is K z + polynomial trend, without survey offsets).  With a ``CJokerHelper``
+        built for ``data``: evaluated on the GPU over the helper's full design matrix
+        (offsets included), any number of samples."""
+        if helper is not None:
+            names = list(helper.internal_units.keys())[: 5 + helper.n_linear]
+            rows, _ = self.pack(units=helper.internal_units, names=names, nonlinear_only=False)
+            return helper.ln_unmarginalized_likelihood(rows)
         from .likelihood_helpers import ln_normal
         from .synthetic import rv_curve
 
