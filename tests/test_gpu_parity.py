@@ -607,9 +607,9 @@ def test_unmarginalized_likelihood_device(torch_cuda, oracle_lib, args, kw):
     assert helper.ln_unmarginalized_likelihood(rows[:0]).shape == (0,)
     with pytest.raises(ValueError):
         helper.ln_unmarginalized_likelihood(rows[:, :-1])
-    samples = tj.JokerSamples.unpack(rows, helper.internal_units, t_ref=data.t_ref,
+    samples = tj.JokerSamples.unpack(rows, helper.internal_units, t_ref=helper.data.t_ref,
                                      poly_trend=prior.poly_trend, n_offsets=prior.n_offsets)
-    dev = samples.ln_unmarginalized_likelihood(data, helper=helper)
+    dev = samples.ln_unmarginalized_likelihood(helper.data, helper=helper)
     assert np.array_equal(dev, got)
     if not kw:
         host = samples.ln_unmarginalized_likelihood(data)
