@@ -28,7 +28,8 @@ for N, pt, kw in ((7, 1, {}), (16, 2, {"n_surveys": 2}), (33, 3, {})):
         uu = torch.rand(n, dtype=torch.float64, device="cuda")
         idx2, tot2, _ = helper.accept(out, key, uniforms=uu)
         helper.posterior_aA(chunk[:5])
-        helper.batch_get_posterior_samples(chunk[:3], 2, rng)
+        rows, _ = helper.batch_get_posterior_samples(chunk[:3], 2, rng)
+        assert np.isfinite(helper.ln_unmarginalized_likelihood(rows)).all()
         helper.design_column(chunk[0])
     helper.pcg64_uniform(np.random.default_rng(0), 100_001, offset=17)
     if N == 7:
