@@ -40,16 +40,21 @@ class MultiStarJoker:
     draw : how the linear parameters of accepted samples are drawn, see
         CJokerHelper.batch_get_posterior_samples ("device" by default: with hundreds of
         accepted samples per star a Python call per row would dominate the star's time)
+    streams_per_device : stars in flight per GPU (default 2); results do not depend on it
     """
 
     def __init__(self, prior, prior_samples, rng=None, devices=(0,), jitter_mode="apply",
-                 group=None, draw="device"):
+                 group=None, draw="device", streams_per_device=2):
         self.prior = prior
         self.rng = np.random.default_rng() if rng is None else rng
         self.devices = list(devices)
         self.jitter_mode = jitter_mode
         self.group = group
         self.draw = draw
+        # stars in flight per GPU: each slot has its own library handle, ll buffer, CUDA
+        # stream and host thread, so one star's host work (index read-back, row gather,
+        # unpacking) overlaps the next star's likelihood kernel
+        self.streams_per_device = max(1, int(streams_per_device))
         self._samples = prior_samples
         self._dev = {}      # device -> dict(cols, s, ll, helper)
         self._host_cols = None
@@ -71,13 +76,20 @@ class MultiStarJoker:
             uniform_s = True
         self._host_cols = cols
         self._s_const = float(cols[4][0]) if uniform_s and len(cols[4]) else 0.0
+        n = len(cols[0])
         for d in self.devices:
             with torch.cuda.device(d):
                 up = lambda a: torch.from_numpy(a).to(f"cuda:{d}")
-                self._dev[d] = dict(
-                    cols=[up(c) for c in cols[:4]], s=None if uniform_s else up(cols[4]),
-                    ll=torch.empty(len(cols[0]), dtype=torch.float64, device=f"cuda:{d}"),
-                    helper=helper0 if d == self.devices[0] else first_helper_factory(d))
+                slots = []
+                for k in range(self.streams_per_device):
+                    first = d == self.devices[0] and k == 0
+                    slots.append(dict(
+                        helper=helper0 if first else first_helper_factory(d),
+                        ll=torch.empty(n, dtype=torch.float64, device=f"cuda:{d}"),
+                        stream=torch.cuda.Stream(device=d)))
+                self._dev[d] = dict(cols=[up(c) for c in cols[:4]],
+                                    s=None if uniform_s else up(cols[4]), slots=slots)
+                torch.cuda.synchronize(d)  # the slots' streams read the uploaded columns
 
     def rejection_sample(self, stars, max_posterior_samples=256, n_linear_samples=1,
                          return_logprobs=False):
@@ -112,46 +124,52 @@ class MultiStarJoker:
 
         results = {}
         stats = {}
-        # one star in flight per device: launch on every device, then collect
-        cursors = [r_lo + a for a, b in dev_ranges]
-        ends = [r_lo + b for a, b in dev_ranges]
-        while any(c < e for c, e in zip(cursors, ends)):
-            active = []
-            for di, d in enumerate(self.devices):
-                if cursors[di] >= ends[di]:
-                    continue
-                i = cursors[di]
-                cursors[di] += 1
-                st = self._dev[d]
-                all_data, ids, trend_M = prepared[i]
-                with torch.cuda.device(d):
-                    st["helper"].update_star(all_data, self.prior, trend_M)
-                    key = st["helper"].new_llmax_key()
-                    st["helper"].marginal_ll_soa(*st["cols"], s=st["s"], s_const=self._s_const,
-                                                 out=st["ll"], llmax_key=key)
-                active.append((i, d, key))
-            for i, d, key in active:
-                st = self._dev[d]
-                child = np.random.Generator(np.random.PCG64(seqs[i]))
-                with torch.cuda.device(d):
-                    idx, total, near = st["helper"].accept(st["ll"], key, rng=child,
-                                                           max_keep=max_keep)
+
+        def run_slot(d, slot, star_indices):
+            """All the stars of one slot, in order, on the slot's own stream."""
+            st = self._dev[d]
+            sl = st["slots"][slot]
+            helper, ll = sl["helper"], sl["ll"]
+            with torch.cuda.device(d), torch.cuda.stream(sl["stream"]):
+                for i in star_indices:
+                    all_data, ids, trend_M = prepared[i]
+                    helper.update_star(all_data, self.prior, trend_M)
+                    key = helper.new_llmax_key()
+                    helper.marginal_ll_soa(*st["cols"], s=st["s"], s_const=self._s_const, out=ll,
+                                           llmax_key=key)
+                    child = np.random.Generator(np.random.PCG64(seqs[i]))
+                    idx, total, near = helper.accept(ll, key, rng=child, max_keep=max_keep)
                     child.bit_generator.advance(n_prior)
                     good = idx.cpu().numpy()
                     rows = np.empty((len(good), 5))
                     for j, c in enumerate(self._host_cols):
                         rows[:, j] = c[good]
-                    raw, lls = st["helper"].batch_get_posterior_samples(rows, n_linear_samples, child,
-                                                                        draw=self.draw)
-                all_data = prepared[i][0]
-                s = JokerSamples.unpack(raw, st["helper"].internal_units, t_ref=all_data.t_ref,
-                                        poly_trend=self.prior.poly_trend,
-                                        n_offsets=self.prior.n_offsets)
-                if return_logprobs:
-                    s["ln_likelihood"] = lls
-                results[i] = s
-                stats[i] = dict(n_accepted=total, n_near_threshold=near,
-                                ll_max=st["helper"].llmax_value(key))
+                    raw, lls = helper.batch_get_posterior_samples(rows, n_linear_samples, child,
+                                                                  draw=self.draw)
+                    smp = JokerSamples.unpack(raw, helper.internal_units, t_ref=all_data.t_ref,
+                                              poly_trend=self.prior.poly_trend,
+                                              n_offsets=self.prior.n_offsets)
+                    if return_logprobs:
+                        smp["ln_likelihood"] = lls
+                    results[i] = smp
+                    stats[i] = dict(n_accepted=total, n_near_threshold=near,
+                                    ll_max=helper.llmax_value(key))
+
+        work = []
+        for d, (a, b) in zip(self.devices, dev_ranges):
+            k = self.streams_per_device
+            for slot in range(k):
+                mine = list(range(r_lo + a + slot, r_lo + b, k))
+                if mine:
+                    work.append((d, slot, mine))
+        if len(work) == 1:
+            run_slot(*work[0])
+        elif work:
+            from concurrent.futures import ThreadPoolExecutor
+
+            with ThreadPoolExecutor(len(work)) as ex:
+                for f in [ex.submit(run_slot, *w) for w in work]:
+                    f.result()
         if self.group is not None:
             import torch.distributed as dist
 

@@ -20,6 +20,7 @@ from thejoker_b200.synthetic import make_noisy_data  # noqa: E402
 
 n_stars = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 log2_prior = int(sys.argv[2]) if len(sys.argv) > 2 else 22
+streams = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 rng = np.random.default_rng(0)
 prior = default_prior(1, sigma_K0=30.0, v0_offsets=[Normal("dv0_1", 0.0, 5.0, u.km / u.s)])
 ps = prior.sample(size=1 << log2_prior, rng=np.random.default_rng(1))
@@ -32,18 +33,19 @@ for i in range(n_stars):
     stars.append([tj.RVData(full._t_bmjd[:cut], full.rv[:cut], full.rv_err[:cut]),
                   tj.RVData(full._t_bmjd[cut:], (full.rv.value[cut:] + off) * u.km / u.s,
                             full.rv_err[cut:])])
-ms = tj.MultiStarJoker(prior, ps, rng=np.random.default_rng(2), devices=[0])
+ms = tj.MultiStarJoker(prior, ps, rng=np.random.default_rng(2), devices=[0],
+                       streams_per_device=streams)
 ms.rejection_sample(stars[:4], max_posterior_samples=256)  # upload + warm-up
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 out = ms.rejection_sample(stars, max_posterior_samples=256)
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
-rec = dict(n_stars=n_stars, n_prior=1 << log2_prior, seconds=dt, stars_per_s=n_stars / dt,
+rec = dict(streams_per_device=streams, n_stars=n_stars, n_prior=1 << log2_prior, seconds=dt, stars_per_s=n_stars / dt,
            prior_evaluations_per_s=n_stars * (1 << log2_prior) / dt,
            mean_epochs=float(np.mean([len(s[0]) + len(s[1]) for s in stars])),
            mean_posterior_samples=float(np.mean([len(o) for o in out])),
            extrapolated_4096_stars_s=4096 * dt / n_stars)
 print(json.dumps(rec))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(rec, open(os.path.join(ROOT, "gpurun_out", "multistar.json"), "w"), indent=1)
+json.dump(rec, open(os.path.join(ROOT, "gpurun_out", f"multistar_s{streams}.json"), "w"), indent=1)
