@@ -40,11 +40,11 @@ class MultiStarJoker:
     draw : how the linear parameters of accepted samples are drawn, see
         CJokerHelper.batch_get_posterior_samples ("device" by default: with hundreds of
         accepted samples per star a Python call per row would dominate the star's time)
-    streams_per_device : stars in flight per GPU (default 2); results do not depend on it
+    streams_per_device : stars in flight per GPU (default 4); results do not depend on it
     """
 
     def __init__(self, prior, prior_samples, rng=None, devices=(0,), jitter_mode="apply",
-                 group=None, draw="device", streams_per_device=2):
+                 group=None, draw="device", streams_per_device=4):
         self.prior = prior
         self.rng = np.random.default_rng() if rng is None else rng
         self.devices = list(devices)
@@ -100,11 +100,12 @@ class MultiStarJoker:
 
         n_stars = len(stars)
         seqs = self.rng.bit_generator._seed_seq.spawn(n_stars)
-        prepared = [validate_prepare_data(d, self.prior.poly_trend, self.prior.n_offsets)
-                    for d in stars]
+        # per-star data preparation happens in the slot threads, overlapped with GPU work
+        prepare = lambda i: validate_prepare_data(stars[i], self.prior.poly_trend,
+                                                  self.prior.n_offsets)
 
         def factory(dev):
-            all_data, ids, trend_M = prepared[0]
+            all_data, ids, trend_M = prepare(0)
             return CJokerHelper(all_data, self.prior, trend_M, device=dev,
                                 jitter_mode=self.jitter_mode)
 
@@ -132,7 +133,7 @@ class MultiStarJoker:
             helper, ll = sl["helper"], sl["ll"]
             with torch.cuda.device(d), torch.cuda.stream(sl["stream"]):
                 for i in star_indices:
-                    all_data, ids, trend_M = prepared[i]
+                    all_data, ids, trend_M = prepare(i)
                     helper.update_star(all_data, self.prior, trend_M)
                     key = helper.new_llmax_key()
                     helper.marginal_ll_soa(*st["cols"], s=st["s"], s_const=self._s_const, out=ll,

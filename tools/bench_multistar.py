@@ -20,7 +20,7 @@ from thejoker_b200.synthetic import make_noisy_data  # noqa: E402
 
 n_stars = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 log2_prior = int(sys.argv[2]) if len(sys.argv) > 2 else 22
-streams = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+streams = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 rng = np.random.default_rng(0)
 prior = default_prior(1, sigma_K0=30.0, v0_offsets=[Normal("dv0_1", 0.0, 5.0, u.km / u.s)])
 ps = prior.sample(size=1 << log2_prior, rng=np.random.default_rng(1))
