@@ -41,7 +41,12 @@ def ext_path():
 
 
 def available() -> bool:
-    p = ext_path()
+    """True when the compiled reference operator can be loaded (built here if the
+    reference sources are present; a failed build only means "not available")."""
+    try:
+        p = ext_path()
+    except Exception:
+        return False
     return p is not None and os.path.exists(p)
 
 
