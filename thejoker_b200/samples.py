@@ -218,32 +218,38 @@ class JokerSamples:
         return new
 
     # -- (unmarginalised) likelihood of posterior samples ----------------------
-    def ln_unmarginalized_likelihood(self, data, helper=None):
-        """samples.py:611-632.  Without ``helper``: the orbit is evaluated by a plain numpy
-        Kepler solve on the host (a handful of posterior samples; like the reference, the
-        model is K z + polynomial trend, without survey offsets).  With a ``CJokerHelper``
-        built for ``data``: evaluated on the GPU over the helper's full design matrix
-        (offsets included), any number of samples."""
+    def ln_unmarginalized_likelihood(self, data, helper=None, device=None):
+        """samples.py:611-632, evaluated on the GPU (``tjb_unmarginalized_ll``; there is
+        no host implementation).
+
+        Without ``helper`` the model is the reference's: K z(t) plus the polynomial trend
+        ``v0 + v1 dt + ...`` about ``t_ref`` -- survey offsets are not part of it, as in
+        ``get_orbit`` (samples.py:296-343).  With a ``CJokerHelper`` built for the same
+        data the helper's full design matrix (offsets included) is used."""
         if helper is not None:
             names = list(helper.internal_units.keys())[: 5 + helper.n_linear]
             rows, _ = self.pack(units=helper.internal_units, names=names, nonlinear_only=False)
             return helper.ln_unmarginalized_likelihood(rows)
-        from .likelihood_helpers import ln_normal
-        from .synthetic import rv_curve
+        from .helper import CJokerHelper
 
         unit = data.rv.unit
-        data_rv = data.rv.value
-        data_var = data.rv_err.to_value(unit) ** 2
-        n = len(self)
-        s_vars = self["s"].to_value(unit) ** 2 if "s" in self.tbl else np.zeros(n)
         t_ref = self.t_ref if self.t_ref is not None else data._t_ref_bmjd
-        dt = data._t_bmjd - t_ref
-        lls = np.full(n, np.nan)
-        for i in range(n):
-            model = rv_curve(data._t_bmjd, t_ref, self["P"].to_value(u.day)[i], self["e"].value[i],
-                             self["omega"].to_value(u.rad)[i], self["M0"].to_value(u.rad)[i],
-                             self["K"].to_value(unit)[i])
-            for j in range(self.poly_trend):
-                model = model + self[f"v{j}"].to_value(unit / u.day**j)[i] * dt**j
-            lls[i] = ln_normal(model, data_rv, data_var + s_vars[i]).sum()
-        return lls
+        dt = np.asarray(data._t_bmjd, dtype=float) - t_ref
+        cols = [np.ones_like(dt)]
+        for _ in range(1, self.poly_trend):
+            cols.append(cols[-1] * dt)
+        L = 1 + self.poly_trend
+        spec = dict(t=data._t_bmjd, rv=data.rv.value, ivar=data.ivar.to_value(1 / unit**2),
+                    t0=t_ref, trend_M=np.stack(cols, axis=1), mu=np.zeros(L), Lambda=np.ones(L),
+                    K_prior_kind=1, sigma_K0=1.0, P0=1.0, max_K=1.0, jitter_mode=1)
+        n = len(self)
+        rows = np.zeros((n, 5 + L))
+        rows[:, 0] = self["P"].to_value(u.day)
+        rows[:, 1] = self["e"].value
+        rows[:, 2] = self["omega"].to_value(u.rad)
+        rows[:, 3] = self["M0"].to_value(u.rad)
+        rows[:, 4] = self["s"].to_value(unit) if "s" in self.tbl else 0.0
+        rows[:, 5] = self["K"].to_value(unit)
+        for j in range(self.poly_trend):
+            rows[:, 6 + j] = self[f"v{j}"].to_value(unit / u.day**j)
+        return CJokerHelper.from_spec(spec, device=device).ln_unmarginalized_likelihood(rows)
