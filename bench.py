@@ -244,6 +244,25 @@ def run_ours(args):
                                                         0.0, n_e2e, vp(ll_np)))
 
     e2e_value = time_e2e(e2e_columns)
+
+    # (1b) the same call on ordinary (pageable) numpy columns, as a user's JokerSamples
+    #      holds them: staged through the library's page-locked ring by host threads
+    e2e_pageable = None
+    if world == 1:
+        n_pg = min(n_e2e, 1 << 26)
+        cols_pg = [np.array(c[:n_pg]) for c in cols_np]
+        ll_pg = np.empty(n_pg)
+        run_pg = lambda: helper.marginal_ln_likelihood_columns(*cols_pg, out=ll_pg)
+        run_pg()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            run_pg()
+        e2e_pageable = {"value": n_pg * e2e_steps / (time.perf_counter() - t0), "n": int(n_pg),
+                        "h2d_bytes_per_step": int(n_pg * 32), "d2h_bytes_per_step": int(n_pg * 8),
+                        "call": "CJokerHelper.marginal_ln_likelihood_columns on pageable numpy "
+                                "columns, pageable ll out"}
+        assert np.array_equal(ll_pg[:1024], ll[:1024].cpu().numpy())
+        del cols_pg, ll_pg
     del cols_host, cols_np
 
     host = torch.empty((n_e2e, 5), dtype=torch.float64).pin_memory()
@@ -308,7 +327,7 @@ def run_ours(args):
                    "n_prior": n_total, "n_epochs": N_EPOCHS, "sharding": f"contiguous x{world}"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_e2e * 32),
                 "d2h_bytes_per_step": int(n_e2e * 8), "n_per_rank": int(n_e2e), "steps": e2e_steps,
-                "rank0_cpu_binding": numa_cpus,
+                "rank0_cpu_binding": numa_cpus, "pageable_columns": e2e_pageable,
                 "call": "TheJoker.marginal_ln_likelihood data path: pinned host columns P, e, "
                         "omega, M0 (s constant) in, host ll out (CJokerHelper."
                         "marginal_ln_likelihood_columns -> tjb_marginal_ll_host_soa)",
