@@ -557,7 +557,9 @@ int tjb_marginal_ll_host(TjbHandle *h, const double *h_chunk, int64_t n, double 
   auto drain_out = [&](int b) -> int {  // pin_out[b] -> h_ll once its D2H is done
     if (out_lo[b] < 0) return TJB_OK;
     CU(cudaStreamSynchronize(sp.aux_stream[b]));
-    std::memcpy(h_ll + out_lo[b], sp.pin_out[b].p, (size_t)out_m[b] * sizeof(double));
+    double *dst = h_ll + out_lo[b];
+    const double *src = (const double *)sp.pin_out[b].p;
+    parallel_copy(&dst, &src, 1, (size_t)out_m[b]);
     out_lo[b] = -1;
     return TJB_OK;
   };
@@ -571,6 +573,10 @@ int tjb_marginal_ll_host(TjbHandle *h, const double *h_chunk, int64_t n, double 
       cudaStream_t st = sp.aux_stream[b];
       double *d_in = (double *)sp.host_stage[b].p, *d_out = (double *)sp.host_ll[b].p;
       const double *src = h_chunk + 5 * lo;
+      if (stage_out) {  // this slot's previous slice must be out of pin_out first
+        int rc = drain_out(b);
+        if (rc) return rc;
+      }
       if (stage_in) {
         if (n_slices >= 2) CU(cudaEventSynchronize(sp.pin_in_free[b]));
         double *dst = (double *)sp.pin_in[b].p;
@@ -584,8 +590,6 @@ int tjb_marginal_ll_host(TjbHandle *h, const double *h_chunk, int64_t n, double 
       int rc = run_ll(h, pv, uniform, s0, m, d_out, nullptr, st);
       if (rc) return rc;
       if (stage_out) {
-        rc = drain_out(b);
-        if (rc) return rc;
         CU(cudaMemcpyAsync(sp.pin_out[b].p, d_out, (size_t)m * sizeof(double),
                            cudaMemcpyDeviceToHost, st));
         out_lo[b] = lo;
@@ -638,7 +642,9 @@ int host_soa_stream(TjbHandle *h, const double *const cols[5], int n_cols, doubl
   auto drain_out = [&](int b) -> int {              // pin_out[b] -> h_ll once its D2H is done
     if (out_lo[b] < 0) return TJB_OK;
     CU(cudaStreamSynchronize(h->stg->aux_stream[b]));
-    std::memcpy(h_ll + out_lo[b], h->stg->pin_out[b].p, (size_t)out_m[b] * sizeof(double));
+    double *dst = h_ll + out_lo[b];
+    const double *src = (const double *)h->stg->pin_out[b].p;
+    parallel_copy(&dst, &src, 1, (size_t)out_m[b]);
     out_lo[b] = -1;
     return TJB_OK;
   };
@@ -650,6 +656,10 @@ int host_soa_stream(TjbHandle *h, const double *const cols[5], int n_cols, doubl
     double *d_in = (double *)h->stg->host_stage[b].p;
     double *d_out = d_ll ? d_ll + lo : (double *)h->stg->host_ll[b].p;
     const double *src[5];
+    if (stage_out) {  // this slot's previous slice (two back) must be out of pin_out first
+      int rc = drain_out(b);
+      if (rc) return rc;
+    }
     if (stage_in) {
       if (n_slices >= 2) CU(cudaEventSynchronize(h->stg->pin_in_free[b]));  // slot's last H2D done
       double *dst[5];
@@ -672,8 +682,6 @@ int host_soa_stream(TjbHandle *h, const double *const cols[5], int n_cols, doubl
     if (rc) return rc;
     if (h_ll) {
       if (stage_out) {
-        rc = drain_out(b);
-        if (rc) return rc;
         CU(cudaMemcpyAsync(h->stg->pin_out[b].p, d_out, (size_t)m * sizeof(double),
                            cudaMemcpyDeviceToHost, st));
         out_lo[b] = lo;

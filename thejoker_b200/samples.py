@@ -239,7 +239,7 @@ class JokerSamples:
         for _ in range(1, self.poly_trend):
             cols.append(cols[-1] * dt)
         L = 1 + self.poly_trend
-        spec = dict(t=data._t_bmjd, rv=data.rv.value, ivar=data.ivar.to_value(1 / unit**2),
+        spec = dict(t=data._t_bmjd, rv=data.rv.value, ivar=data.ivar.to_value(u.one / unit**2),
                     t0=t_ref, trend_M=np.stack(cols, axis=1), mu=np.zeros(L), Lambda=np.ones(L),
                     K_prior_kind=1, sigma_K0=1.0, P0=1.0, max_K=1.0, jitter_mode=1)
         n = len(self)
