@@ -9,15 +9,20 @@ are independent; the 8-byte max-key all-reduce of the accept step runs once afte
 timed region as a cross-rank check).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on
-                                                             # the host cores (CPU oracle)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU
+                                                             # implementation, host cores
 
 One JSON line on stdout (rank 0).  `value`: device-resident SoA prior, CUDA-event time,
-max over ranks.  `e2e`: the reference-facing call CJokerHelper.batch_marginal_ln_likelihood
-on a pinned HOST chunk (n, 5), host->device and device->host copies inside the timed
-region.  `roofline`: algorithmic FP64 work / kernel time against the
-FP64 FMA-chain peak measured in this run.  `cpu_baseline`: the CPU oracle (restatement of
-the reference's Cython, same LAPACK) on this box's cores, on a bounded sample.
+max over ranks.  `e2e`: the reference-facing data path on HOST buffers, host->device and
+device->host copies inside the timed region -- page-locked prior columns in / ll out
+(`e2e.value`), the packed (n, 5) chunk of CJokerHelper.batch_marginal_ln_likelihood
+(`e2e.packed_chunk`), and ordinary pageable numpy columns (`e2e.pageable_columns`).
+`roofline`: algorithmic FP64 work / kernel time against the FP64
+FMA-chain peak measured in this run.  `cpu_baseline` and `--impl reference`: the
+reference's own Cython operator compiled from its sources (oracle/_ref, kind "reference";
+one process per core like its pool.map) when that build is present, else the C
+restatement (oracle/joker_oracle.c, kind "port"), on this box's cores, on a bounded
+sample of the same workload.
 """
 from __future__ import annotations
 
