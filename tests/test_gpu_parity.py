@@ -113,6 +113,36 @@ def test_reference_cython_golden_vectors(torch_cuda, path):
     assert np.max(np.abs(samples[:, 5:] - z["ref_samples"][:, 5:]) / scale) < 1e-6
 
 
+@pytest.mark.parametrize("N,pt,kw", [(16, 1, {}), (64, 1, {}), (33, 2, {"n_surveys": 2}),
+                                     (64, 3, {}), (20, 1, {"K": 1e-4})])
+def test_live_reference_cython(torch_cuda, N, pt, kw):
+    """The CUDA path against the reference's own compiled operator running on this box
+    (oracle/_ref travels with the repo; skipped when it was not built): fresh seeded
+    inputs, 4096 prior rows per star, ll within 1e-10, a / A of the posterior."""
+    from oracle import ref_cython
+
+    if not ref_cython.available():
+        pytest.skip("oracle/_ref not built")
+    import thejoker_b200 as tj
+
+    spec, _, _ = star_spec(N, pt, seed=11, **kw)
+    ref = ref_cython.RefCythonHelper(spec, poly_trend=spec["n_poly"], n_offsets=spec["n_offsets"])
+    spec_ref_mode = dict(spec, jitter_mode=0)  # the reference ignores the jitter column
+    helper = tj.CJokerHelper.from_spec(spec_ref_mode, device=0)
+    chunk = prior_chunk(4096, seed=77, s_lognormal=(-1.0, 1.0))
+    want = ref.batch_marginal_ln_likelihood(chunk)
+    got = helper.batch_marginal_ln_likelihood(chunk)
+    r = rel_err(got, want)
+    flat = "K" in kw  # chi2 cancels to ~1e-12 of its terms in the reference itself
+    assert r.max() < (1e-8 if flat else 1e-10), r.max()
+    lls, a, A = helper.posterior_aA(chunk[:8], clamp_K=False)
+    for i in range(8):
+        ll_ref, mats = ref.test_likelihood_worker(chunk[i])
+        assert abs(lls[i] - ll_ref) <= (1e-8 if flat else 1e-10) * abs(ll_ref)
+        assert np.allclose(a[i], mats["a"], rtol=1e-8, atol=1e-10)
+        assert np.allclose(A[i], mats["A"], rtol=1e-7, atol=1e-14)
+
+
 @pytest.mark.parametrize("path", REF_REJECTION,
                          ids=[os.path.basename(p)[14:-4] for p in REF_REJECTION])
 def test_reference_rejection_driver_vectors(torch_cuda, path):
