@@ -125,11 +125,15 @@ class RVData:
             return u.Quantity(np.linalg.inv(self.rv_err.value), u.one / self.rv_err.unit)
         return u.Quantity(1.0 / self.rv_err.value**2, u.one / self.rv_err.unit**2)
 
-    def phase(self, P, t0=None):
-        """Orbital phase of each observation for period P [day] (data.py phase())."""
-        t0 = self._t_ref_bmjd if t0 is None else t0
+    def phase(self, P, t_ref=None, t0=None):
+        """Orbital phase of each observation for period P [day], relative to ``t_ref``
+        [BMJD] (default: the data's reference epoch).  data.py:365-392; ``t0`` is the
+        reference's deprecated name for ``t_ref`` and is still accepted."""
+        if t_ref is None:
+            t_ref = t0
+        t_ref = self._t_ref_bmjd if t_ref is None else t_ref
         P = u.to_value(P, u.day, u.day)
-        return ((self._t_bmjd - t0) / P) % 1.0
+        return ((self._t_bmjd - t_ref) / P) % 1.0
 
     def __len__(self):
         return len(self._t_bmjd)

@@ -106,6 +106,12 @@ class JokerSamples:
         return self.meta["n_offsets"]
 
     @property
+    def isscalar(self):
+        """samples.py:263-268: True when the object holds a single, un-indexed sample (the
+        reference backs that case with an astropy ``Row``)."""
+        return bool(self.tbl) and all(np.ndim(v.value) == 0 for v in self.tbl.values())
+
+    @property
     def par_names(self):
         return [k for k in self.tbl.keys() if k not in ("ln_prior", "ln_likelihood", "ln_posterior")]
 
@@ -204,7 +210,9 @@ class JokerSamples:
             np.savez(f, **payload)
 
     @classmethod
-    def read(cls, filename):
+    def read(cls, filename, path=None):
+        """samples.py:565-609.  ``path`` names the HDF5 group in the reference's files; the
+        .npz container written by ``write`` has a single table, so it is ignored."""
         import ast
 
         with np.load(filename, allow_pickle=False) as z:
