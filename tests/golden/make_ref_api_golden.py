@@ -59,6 +59,23 @@ def main():
             if isinstance(node, ast.FunctionDef) and node.name in funcs:
                 rec["functions"][node.name] = {"file": fname, "args": signature(node),
                                                "line": node.lineno}
+    # the Cython operator: cpdef methods and public attributes of CJokerHelper
+    import re
+
+    pyx = open(os.path.join(REF, "src", "fast_likelihood.pyx")).read()
+    helper = {"methods": {}, "public_attributes": []}
+    for m in re.finditer(r"cpdef\s+(\w+)\(([^)]*)\)", pyx, re.S):
+        flat = re.sub(r"\[[^\]]*\]", "", m.group(2).replace("\n", " "))  # drop memoryview types
+        args = [a.split("=")[0].split()[-1] for a in flat.split(",")]
+        helper["methods"][m.group(1)] = args
+    m = re.search(r"def __init__\(([^)]*)\)", pyx, re.S)
+    helper["methods"]["__init__"] = [a.split()[-1]
+                                     for a in re.sub(r"\[[^\]]*\]", "", m.group(1)).split(",")]
+    helper["public_attributes"] = sorted(set(re.findall(r"public\s+[\w\[\]:, ]+?\s(\w+)\s*$",
+                                                        pyx, re.M)))
+    helper["module_names"] = sorted(set(re.findall(r"^(_nonlinear_\w+)\s*=", pyx, re.M)))
+    rec["CJokerHelper"] = helper
+    print("CJokerHelper", helper)
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_api_signatures.json")
     with open(path, "w") as f:
         json.dump(rec, f, indent=1, sort_keys=True)

@@ -101,3 +101,25 @@ def test_function_signature(name):
 def test_every_out_of_scope_entry_is_real():
     for cls, method in OUT_OF_SCOPE:
         assert method in REF["classes"][cls]["methods"], (cls, method)
+
+
+def test_cjokerhelper_surface():
+    """The operator boundary itself: the cpdef methods of the reference's CJokerHelper with
+    their argument names, its public attributes, and the two module-level names
+    samples.py imports from the extension (pyx:41-45)."""
+    from thejoker_b200 import helper as helper_mod
+
+    ref = REF["CJokerHelper"]
+    for name, args in ref["methods"].items():
+        fn = getattr(tj.CJokerHelper, name)
+        names = [p.name for p in inspect.signature(fn).parameters.values()]
+        assert names[:len(args)] == args, (name, names, args)
+    # B / Binv (N x N) are never formed on the GPU path (DESIGN.md section 3); the oracle has them
+    never_formed = {"B", "Binv"}
+    src = inspect.getsource(tj.CJokerHelper)
+    for attr in ref["public_attributes"]:
+        if attr in never_formed:
+            continue
+        assert f"self.{attr}" in src, attr
+    for name in ref["module_names"]:
+        assert hasattr(helper_mod, name), name

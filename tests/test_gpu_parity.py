@@ -141,6 +141,14 @@ def test_live_reference_cython(torch_cuda, N, pt, kw):
         assert abs(lls[i] - ll_ref) <= (1e-8 if flat else 1e-10) * abs(ll_ref)
         assert np.allclose(a[i], mats["a"], rtol=1e-8, atol=1e-10)
         assert np.allclose(A[i], mats["A"], rtol=1e-7, atol=1e-14)
+    # the single-row entry point leaves the reference's public attributes behind
+    ll1 = helper.test_likelihood_worker(chunk[0])
+    ll_ref, mats = ref.test_likelihood_worker(chunk[0])
+    assert abs(ll1 - ll_ref) <= (1e-8 if flat else 1e-10) * abs(ll_ref)
+    assert np.allclose(helper.a, mats["a"], rtol=1e-8, atol=1e-10)
+    assert np.allclose(helper.A, mats["A"], rtol=1e-7, atol=1e-14)
+    assert np.allclose(helper.Ainv, mats["Ainv"], rtol=1e-6)
+    assert np.allclose(helper.b, mats["b"], rtol=1e-12, atol=1e-12)
 
 
 @pytest.mark.parametrize("path", REF_REJECTION,

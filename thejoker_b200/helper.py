@@ -184,7 +184,7 @@ class CJokerHelper:
         self.n_pars = self.spec["n_pars"]
         if self.n_linear > _lib.TJB_MAX_LINEAR or len(spec["mu"]) < self.n_linear:
             raise ValueError("bad n_linear / mu length")
-        self.a = self.A = self.b = None
+        self.a = self.A = self.Ainv = self.b = None
         if device is None:
             import os
             device = int(os.environ.get("LOCAL_RANK", "0"))
@@ -219,7 +219,7 @@ class CJokerHelper:
         self.spec = spec
         self.internal_units = spec["internal_units"]
         self.n_times, self.n_linear, self.n_pars = spec["n_times"], spec["n_linear"], spec["n_pars"]
-        self.a = self.A = self.b = None
+        self.a = self.A = self.Ainv = self.b = None
         _lib.check(self._lib.tjb_update_star(self._h, ctypes.byref(self._c_spec(spec))))
 
     def __del__(self):
@@ -332,10 +332,12 @@ class CJokerHelper:
         return ll
 
     def test_likelihood_worker(self, chunk_row):
-        """pyx:547-576: ll for one row; leaves a, A, b readable."""
+        """pyx:547-576: ll for one row; leaves a, A, Ainv, b readable (the N x N B and
+        Binv of the reference are never formed here)."""
         row = np.ascontiguousarray(chunk_row, dtype=np.float64).reshape(5)
         ll, a, A = self.posterior_aA(row[None, :], clamp_K=False)
         self.a, self.A = a[0], A[0]
+        self.Ainv = np.linalg.inv(self.A)  # L x L; the kernel holds it only in factored form
         M = np.hstack((self.design_column(row)[:, None], self.spec["trend_M"]))
         self.b = M @ self.spec["mu"]  # pyx:306-309
         return float(ll[0])
