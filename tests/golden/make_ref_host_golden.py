@@ -39,6 +39,57 @@ def design_cases():
     return out
 
 
+class _Q:
+    """What the reference's samples_analysis functions read from sample['P']."""
+
+    def __init__(self, value):
+        self.value = np.asarray(value, float)
+
+    def to(self, unit):
+        return self
+
+    def to_value(self, unit):
+        return self.value
+
+
+class _T:
+    def __init__(self, mjd):
+        self.mjd = self.jd = np.asarray(mjd, float)
+        self.tcb = self
+
+
+class _Data:
+    def __init__(self, t, t_ref):
+        self._t, self._t_ref = np.asarray(t, float), float(t_ref)
+        self.t = _T(self._t)
+
+    def phase(self, P):
+        return ((self._t - self._t_ref) / np.asarray(getattr(P, "value", P), float)) % 1.0
+
+
+def samples_analysis_cases():
+    """samples_analysis.py:35-135 on plain arrays (P in days, t in BMJD)."""
+    ns = {"u": type("U", (), {"day": "day"})}
+    fns = {n: reference_function("thejoker/samples_analysis.py", n, ns)
+           for n in ("is_P_unimodal", "max_phase_gap", "phase_coverage", "periods_spanned")}
+    rng = np.random.default_rng(5)
+    out = []
+    for k in range(8):
+        n = int(rng.integers(4, 30))
+        t = np.sort(56000.0 + rng.uniform(0, 400, n))
+        t_ref = float(t.min())
+        P = float(np.exp(rng.uniform(np.log(2), np.log(300))))
+        Ps = P * (1 + 10 ** rng.uniform(-6, -1) * rng.normal(size=6))
+        data = _Data(t, t_ref)
+        one = {"P": _Q(P)}
+        out.append({"t": t.tolist(), "t_ref": t_ref, "P": P, "P_samples": Ps.tolist(),
+                    "is_P_unimodal": bool(fns["is_P_unimodal"]({"P": _Q(Ps)}, data)),
+                    "max_phase_gap": float(fns["max_phase_gap"](one, data)),
+                    "phase_coverage": float(fns["phase_coverage"](one, data)),
+                    "periods_spanned": float(fns["periods_spanned"](one, data))})
+    return out
+
+
 def main():
     batch_tasks = reference_function("thejoker/utils.py", "batch_tasks")
     lh = load_likelihood_helpers()
@@ -61,6 +112,7 @@ def main():
                               "trend_M": M.tolist(), "const_M": C.tolist()})
     for x, mu, var in [(0.3, 0.1, 2.0), (-5.0, 1.0, 0.01), (1e3, 0.0, 1e4)]:
         rec["ln_normal"].append({"x": x, "mu": mu, "var": var, "value": float(lh.ln_normal(x, mu, var))})
+    rec["samples_analysis"] = samples_analysis_cases()
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_host_logic.json")
     with open(path, "w") as f:
         json.dump(rec, f)

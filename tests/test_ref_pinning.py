@@ -216,3 +216,24 @@ def test_design_matrices_match_reference():
         assert np.array_equal(M, ref), (c["poly_trend"], np.max(np.abs(M - ref) / np.abs(ref)))
     for c in g["ln_normal"]:
         assert np.isclose(ln_normal(c["x"], c["mu"], c["var"]), c["value"], rtol=1e-15, atol=0)
+
+
+def test_samples_analysis_matches_reference():
+    """thejoker/samples_analysis.py:35-135 (is_P_unimodal, max_phase_gap, phase_coverage,
+    periods_spanned), outputs of the reference's own functions on seeded epochs."""
+    import thejoker_b200 as tj
+    from thejoker_b200 import samples_analysis as sa
+    from thejoker_b200 import units as u
+
+    for c in _host_golden()["samples_analysis"]:
+        t = np.array(c["t"])
+        data = tj.RVData(t, np.zeros(len(t)) * u.km / u.s, np.ones(len(t)) * u.km / u.s,
+                         t_ref=c["t_ref"])
+        many = tj.JokerSamples()
+        many["P"] = np.array(c["P_samples"]) * u.day
+        one = tj.JokerSamples()
+        one["P"] = np.array([c["P"]]) * u.day
+        assert bool(sa.is_P_unimodal(many, data)) == c["is_P_unimodal"]
+        assert np.isclose(sa.max_phase_gap(one, data), c["max_phase_gap"], rtol=1e-12, atol=1e-15)
+        assert np.isclose(sa.phase_coverage(one, data), c["phase_coverage"], rtol=0, atol=1e-15)
+        assert np.isclose(sa.periods_spanned(one, data), c["periods_spanned"], rtol=1e-13)

@@ -57,10 +57,12 @@ def is_P_Kmodal(samples, data, n_clusters=2, n_iter=50):
 
 
 def max_phase_gap(sample, data):
-    """Largest gap in orbital phase between consecutive observations, wrapping around
-    (samples_analysis.py:100-111)."""
+    """Largest gap in orbital phase between consecutive observations
+    (samples_analysis.py:96-107).  As in the reference the sorted phases are concatenated
+    with themselves unshifted, so the gap across phase 1 -> 0 is not counted."""
     phase = np.sort(data.phase(_P_days(sample)[0]))
-    return float(np.max(np.diff(np.concatenate((phase, phase + 1.0)))))
+    phase = np.concatenate((phase, phase))
+    return float((phase[1:] - phase[:-1]).max())
 
 
 def phase_coverage(sample, data, n_bins=10):
@@ -77,7 +79,6 @@ def periods_spanned(sample, data):
 def phase_coverage_per_period(sample, data):
     """Largest number of observations inside any single period window (:142-151)."""
     cycles = (data._t_bmjd - data._t_ref_bmjd) / _P_days(sample)[0]
-    top = cycles.max() + 1
-    H1, _ = np.histogram(cycles, bins=np.arange(0, top + 1, 1))
-    H2, _ = np.histogram(cycles, bins=np.arange(-0.5, top + 1, 1))
+    H1, _ = np.histogram(cycles, bins=np.arange(0, cycles.max() + 1, 1))
+    H2, _ = np.histogram(cycles, bins=np.arange(-0.5, cycles.max() + 1, 1))
     return int(max(H1.max(), H2.max()))
