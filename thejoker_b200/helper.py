@@ -305,7 +305,9 @@ class CJokerHelper:
             out = np.zeros((n, k, 5 + L))
             for i in range(n):
                 out[i, :, :5] = chunk[i]
-                out[i, :, 5:] = rng.multivariate_normal(a[i], A[i], size=k)
+                # same numbers as the reference's call (pyx:529-530); only numpy's
+                # positive-semidefiniteness warning pass (an allclose per row) is skipped
+                out[i, :, 5:] = rng.multivariate_normal(a[i], A[i], size=k, check_valid="ignore")
             return out.reshape(n * k, -1), np.repeat(lls, k)
         if draw != "device":
             raise ValueError("draw must be 'device' or 'numpy'")
