@@ -113,6 +113,43 @@ def test_reference_cython_golden_vectors(torch_cuda, path):
     assert np.max(np.abs(samples[:, 5:] - z["ref_samples"][:, 5:]) / scale) < 1e-6
 
 
+def test_kepler_function_reproduces_twobody_outputs(torch_cuda):
+    """tjb_design_column (the kernel's Kepler function) against radial velocities computed
+    by twobody itself: the noiseless example data of the reference repository
+    (tests/golden/ref_examples.npz, made by tests/golden/make_ref_examples_golden.py); and
+    the marginal likelihood evaluated at the true nonlinear elements sits at the chi2
+    floor (the stored rv are exact, so the residual is ~0 against the quoted errors)."""
+    import thejoker_b200 as tj
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_examples.npz"))
+    tol = 6e-10  # km/s: the float64 Julian dates of the files resolve 4.7e-10 d
+    for name in ("single", "survey"):
+        dt, rv, err = g[name + "_dt"], g[name + "_rv"], g[name + "_rv_err"]
+        P, e, om, M0, K, v0 = g[name + "_truth"]
+        n = len(dt)
+        if name == "survey":
+            n1 = int(g["survey_n1"])
+            T = np.stack([np.ones(n), (np.arange(n) >= n1).astype(float)], axis=1)
+            lin = np.array([v0, float(g["survey_offset"])])
+            mu, Lam = np.zeros(3), np.array([0.0, 1e4, 25.0])
+        else:
+            T, lin = np.ones((n, 1)), np.array([v0])
+            mu, Lam = np.zeros(2), np.array([0.0, 1e4])
+        spec = dict(t=dt, rv=rv, ivar=1.0 / err**2, t0=0.0, trend_M=T, mu=mu, Lambda=Lam,
+                    K_prior_kind=0, sigma_K0=30.0, P0=365.25, max_K=500.0, jitter_mode=1)
+        helper = tj.CJokerHelper.from_spec(spec, device=0)
+        z = helper.design_column(np.array([P, e, om, M0, 0.0]))
+        model = K * z + T @ lin
+        assert np.max(np.abs(model - rv)) < tol, (name, np.max(np.abs(model - rv)))
+        # at the truth the data are reproduced exactly, so a, the posterior mean of the
+        # linear parameters, is the truth itself up to the (weak) prior's pull
+        ll, a, A = helper.posterior_aA(np.array([[P, e, om, M0, 0.0]]))
+        assert np.allclose(a[0], np.concatenate([[K], lin]), rtol=1e-4, atol=1e-4)
+        # and a period 1 % off is astronomically less likely
+        ll_off = helper.batch_marginal_ln_likelihood(np.array([[P * 1.01, e, om, M0, 0.0]]))
+        assert ll[0] - ll_off[0] > 100
+
+
 @pytest.mark.parametrize("N,pt,kw", [(16, 1, {}), (64, 1, {}), (33, 2, {"n_surveys": 2}),
                                      (64, 3, {}), (20, 1, {"K": 1e-4})])
 def test_live_reference_cython(torch_cuda, N, pt, kw):

@@ -237,3 +237,73 @@ def test_samples_analysis_matches_reference():
         assert np.isclose(sa.max_phase_gap(one, data), c["max_phase_gap"], rtol=1e-12, atol=1e-15)
         assert np.isclose(sa.phase_coverage(one, data), c["phase_coverage"], rtol=0, atol=1e-15)
         assert np.isclose(sa.periods_spanned(one, data), c["periods_spanned"], rtol=1e-13)
+
+
+# -- the Kepler function against twobody's own outputs stored in the reference repository ----
+def _examples():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_examples.npz"))
+
+
+def _example_cases():
+    """(name, dt [TCB days since t0], stored rv, list of (P, e, omega, M0, K), constant
+    per-epoch term) for the three datasets of docs/examples/make-data.ipynb."""
+    g = _examples()
+    P, e, om, M0, K, v0 = g["single_truth"]
+    yield "single", g["single_dt"], g["single_rv"], [(P, e, om, M0, K)], np.full(257, v0)
+    P, e, om, M0, K, v0 = g["triple_truth1"]
+    yield ("triple", g["triple_dt"], g["triple_rv"],
+           [(P, e, om, M0, K), tuple(g["triple_truth2"])], np.full(257, v0))
+    P, e, om, M0, K, v0 = g["survey_truth"]
+    const = np.full(17, v0)
+    const[int(g["survey_n1"]):] += float(g["survey_offset"])
+    yield "survey", g["survey_dt"], g["survey_rv"], [(P, e, om, M0, K)], const
+
+
+# float64 Julian dates resolve 4.7e-10 d: 2 pi K dt_err / P ~ 5e-10 km/s at K ~ 7, P ~ 42 d
+TWOBODY_RV_TOL = 6e-10  # km/s
+
+
+def test_oracle_kepler_reproduces_twobody_outputs():
+    """oracle/joker_oracle.c::orc_rv_from_elements (the restatement of twobody's
+    c_rv_from_elements) against radial velocities that twobody itself computed:
+    docs/examples/*.ecsv hold noiseless `KeplerOrbit.radial_velocity(t)` values whose true
+    elements follow from the notebook's seed (tests/golden/make_ref_examples_golden.py)."""
+    import ctypes
+
+    from oracle.oracle import load
+
+    lib = load()
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.orc_rv_from_elements.restype = None
+    lib.orc_rv_from_elements.argtypes = ([dp, dp, ctypes.c_int] + [ctypes.c_double] * 7
+                                         + [ctypes.c_int, ctypes.c_int])
+    for name, dt, rv, orbits, const in _example_cases():
+        model = const.copy()
+        for P, e, om, M0, K in orbits:
+            t = np.ascontiguousarray(dt)
+            out = np.zeros_like(t)
+            lib.orc_rv_from_elements(t.ctypes.data_as(dp), out.ctypes.data_as(dp), len(t), P, K,
+                                     e, om, M0, 0.0, 1e-10, 128, 0)
+            model += out
+        assert np.max(np.abs(model - rv)) < TWOBODY_RV_TOL, (name, np.max(np.abs(model - rv)))
+
+
+def test_device_kepler_math_reproduces_twobody_outputs():
+    """The same for the device Kepler function (csrc/kepler.cuh) compiled for the host."""
+    import ctypes
+
+    from helpers import host_emulation
+
+    lib = host_emulation()
+    dp = ctypes.POINTER(ctypes.c_double)
+    st = (ctypes.c_int * 3)()
+    for name, dt, rv, orbits, const in _example_cases():
+        model = const.copy()
+        for P, e, om, M0, K in orbits:
+            t = np.ascontiguousarray(dt)
+            z = np.zeros_like(t)
+            lib.emu_design_column(P, e, om, M0, t.ctypes.data_as(dp), len(t),
+                                  z.ctypes.data_as(dp), st)
+            assert st[2] == 0
+            model += K * z
+        assert np.max(np.abs(model - rv)) < TWOBODY_RV_TOL, (name, np.max(np.abs(model - rv)))
