@@ -131,12 +131,12 @@ def test_kepler_function_reproduces_twobody_outputs(torch_cuda):
             n1 = int(g["survey_n1"])
             T = np.stack([np.ones(n), (np.arange(n) >= n1).astype(float)], axis=1)
             lin = np.array([v0, float(g["survey_offset"])])
-            mu, Lam = np.zeros(3), np.array([0.0, 1e4, 25.0])
+            mu, Lam = np.zeros(3), np.array([0.0, 1e6, 1e6])
         else:
             T, lin = np.ones((n, 1)), np.array([v0])
-            mu, Lam = np.zeros(2), np.array([0.0, 1e4])
+            mu, Lam = np.zeros(2), np.array([0.0, 1e6])
         spec = dict(t=dt, rv=rv, ivar=1.0 / err**2, t0=0.0, trend_M=T, mu=mu, Lambda=Lam,
-                    K_prior_kind=0, sigma_K0=30.0, P0=365.25, max_K=500.0, jitter_mode=1)
+                    K_prior_kind=0, sigma_K0=300.0, P0=365.25, max_K=5000.0, jitter_mode=1)
         helper = tj.CJokerHelper.from_spec(spec, device=0)
         z = helper.design_column(np.array([P, e, om, M0, 0.0]))
         model = K * z + T @ lin
@@ -144,7 +144,7 @@ def test_kepler_function_reproduces_twobody_outputs(torch_cuda):
         # at the truth the data are reproduced exactly, so a, the posterior mean of the
         # linear parameters, is the truth itself up to the (weak) prior's pull
         ll, a, A = helper.posterior_aA(np.array([[P, e, om, M0, 0.0]]))
-        assert np.allclose(a[0], np.concatenate([[K], lin]), rtol=1e-4, atol=1e-4)
+        assert np.allclose(a[0], np.concatenate([[K], lin]), rtol=1e-3, atol=1e-3), a[0]
         # and a period 1 % off is astronomically less likely
         ll_off = helper.batch_marginal_ln_likelihood(np.array([[P * 1.01, e, om, M0, 0.0]]))
         assert ll[0] - ll_off[0] > 100
