@@ -145,9 +145,10 @@ def test_kepler_function_reproduces_twobody_outputs(torch_cuda):
         # linear parameters, is the truth itself up to the (weak) prior's pull
         ll, a, A = helper.posterior_aA(np.array([[P, e, om, M0, 0.0]]))
         assert np.allclose(a[0], np.concatenate([[K], lin]), rtol=1e-3, atol=1e-3), a[0]
-        # and a period 1 % off is astronomically less likely
+        # and a period 1 % off is far less likely (oracle: 474.6 for the 257-epoch set,
+        # 10.3 for the 17 epochs of the two surveys)
         ll_off = helper.batch_marginal_ln_likelihood(np.array([[P * 1.01, e, om, M0, 0.0]]))
-        assert ll[0] - ll_off[0] > 100
+        assert ll[0] - ll_off[0] > (400 if name == "single" else 9)
 
 
 @pytest.mark.parametrize("N,pt,kw", [(16, 1, {}), (64, 1, {}), (33, 2, {"n_surveys": 2}),
