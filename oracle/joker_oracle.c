@@ -6,8 +6,9 @@
  * cpu_baseline / --impl reference legs use it, and only as the checker / the
  * timed CPU baseline.
  *
- * PARITY STATUS: pinned to the reference's own compiled Cython for everything except
- * the Kepler solve; "parity unpinned" only at that one third-party function.
+ * PARITY STATUS: pinned.  Everything the reference itself implements is pinned bit for
+ * bit to its own compiled Cython; the one function it takes from a third party is pinned
+ * to that third party's own outputs as stored in the reference repository.
  *   - thejoker/src/fast_likelihood.pyx is translated by Cython and compiled unmodified
  *     from /root/reference (oracle/ref_build/build_ref.py -> oracle/_ref/, git-ignored)
  *     and driven through its real CJokerHelper.__init__ and public methods
@@ -22,11 +23,17 @@
  *     links THIS file's orc_rv_from_elements in its place: Newton iteration on
  *     E - e sin E = M from a second-order series starter, tolerance and maxiter as
  *     passed by fast_likelihood.pyx:35-36, true anomaly by the half-angle atan2 formula,
- *     rv = K (cos(f + omega) + e cos omega).  The sign / phase conventions are pinned
- *     inside the reference (samples.py:228-229, thejoker.py:441,
- *     _keplerian_orbit.py:642-656); the converged E is defined by the equation to
- *     kepler_tol = 1e-10 whatever the iteration, and joker_truth.c (quad precision)
- *     bounds what that leaves.
+ *     rv = K (cos(f + omega) + e cos omega).  It is pinned to twobody's OWN OUTPUTS: the
+ *     reference's docs/examples/{data,data-triple,data-survey1,data-survey2}.ecsv hold
+ *     noiseless `twobody.KeplerOrbit.radial_velocity(t)` values (make-data.ipynb adds no
+ *     noise to rv) whose true elements follow from the notebook's seed; on all 531
+ *     epochs (e = 0.1, 0.13, 0.25, a two-orbit sum, a survey offset) this function
+ *     reproduces them to 2.8e-10 km/s = 4e-11 K, which is the resolution of the files'
+ *     float64 Julian dates (tests/golden/make_ref_examples_golden.py,
+ *     tests/test_ref_pinning.py::test_oracle_kepler_reproduces_twobody_outputs).  What
+ *     stays unpinned is only the last-ulp behaviour of twobody's loop exit; the two
+ *     plausible readings differ by <= 3e-11 relative in ll, and joker_truth.c (quad
+ *     precision) bounds both.
  * The linear-algebra part follows the pyx statement by statement and calls the same
  * LAPACK entry points (scipy.linalg.cython_lapack dgetrf/dgetri/dsysv, bound at run time
  * from Python through orc_set_lapack).

@@ -4,10 +4,12 @@ TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
 cpu_baseline / --impl reference legs of bench.py.  The product package
 (thejoker_b200/) never imports this module.
 
-PARITY STATUS: pinned bit-for-bit to the reference's own compiled Cython
+PARITY STATUS: pinned -- bit for bit to the reference's own compiled Cython
 (oracle/ref_cython.py, tests/test_ref_pinning.py, tests/golden/ref_*.npz) for everything
-but the Kepler solve, which restates the absent third-party `twobody` and is the one
-"parity unpinned" function -- see the header of joker_oracle.c.
+the reference implements, and to twobody's own stored outputs (the reference's noiseless
+docs/examples/*.ecsv, tests/golden/ref_examples.npz; 4e-11 K, the resolution of their
+time stamps) for the Kepler function it takes from that absent third party.  See the
+header of joker_oracle.c.
 
 `OracleHelper` mirrors the method surface of the reference's CJokerHelper
 (thejoker/src/fast_likelihood.pyx:70-576) on plain arrays.
