@@ -20,8 +20,7 @@ _ALL_NPZ = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*
 # the others by the oracle + quad truth (golden/make_golden.py)
 GOLDEN = [p for p in _ALL_NPZ if not os.path.basename(p).startswith("ref_")]
 REF_REJECTION = [p for p in _ALL_NPZ if os.path.basename(p).startswith("ref_rejection_")]
-REF_GOLDEN = [p for p in _ALL_NPZ if os.path.basename(p).startswith("ref_")
-              and p not in REF_REJECTION]
+REF_GOLDEN = [p for p in _ALL_NPZ if os.path.basename(p).startswith("ref_n")]  # ref_n<N>_...
 
 
 def _spec_from_npz(z):

@@ -24,7 +24,7 @@ from oracle.oracle import OracleHelper, iterative_rejection_indices, rejection_a
 
 _REF_ALL = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.npz")))
 REF_REJECTION = [p for p in _REF_ALL if os.path.basename(p).startswith("ref_rejection_")]
-REF_GOLDEN = [p for p in _REF_ALL if p not in REF_REJECTION]
+REF_GOLDEN = [p for p in _REF_ALL if os.path.basename(p).startswith("ref_n")]  # ref_n<N>_...
 SPEC_KEYS = ("t", "rv", "ivar", "t0", "trend_M", "mu", "Lambda", "K_prior_kind", "sigma_K0", "P0",
              "max_K")
 MATS = ("a", "A", "Ainv", "b", "B", "Binv")
