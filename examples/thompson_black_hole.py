@@ -8,14 +8,16 @@ e = 0.00476, f(M) = 0.766 +- 0.006 Msun.
 
     python examples/thompson_black_hole.py [log2_prior_samples]
 """
+import os
 import sys
 import time
 
 import numpy as np
 
-import thejoker_b200 as tj
-from thejoker_b200 import units as u
-from thejoker_b200.prior import LogNormal, Normal
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import thejoker_b200 as tj  # noqa: E402
+from thejoker_b200 import units as u  # noqa: E402
+from thejoker_b200.prior import LogNormal, Normal  # noqa: E402
 
 TRES = np.array([
     [8006.97517, 0.000, 0.075], [8023.98151, -43.313, 0.075], [8039.89955, -27.963, 0.045],
