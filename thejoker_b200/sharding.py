@@ -4,11 +4,14 @@ schwimmbad chunk pool (thejoker/multiproc_helpers.py:17-60, utils.py:22-72).
 The reference maps contiguous chunks of prior samples over pool workers, each of
 which re-reads its rows from a shared HDF5 file and returns a float64[n_i] array that
 the master concatenates; max / compare / where then run serially on the master
-(multiproc_helpers.py:256-258).  Here a shard is a contiguous index range resident on
-one GPU (same split rule, so concatenating shards in order reproduces the global
-index order); ll never leaves the device, the only exchange is the 8-byte max key
-(integer MAX all-reduce over NCCL when the shards live in different processes) and
-the accepted indices.
+(multiproc_helpers.py:256-258).  Here a shard is a contiguous index range owned by one
+GPU (same split rule, so concatenating shards in order reproduces the global index
+order).  Prior columns that live on the host (numpy arrays, memory-mapped cache files)
+are streamed through the GPU range by range as they are evaluated -- the counterpart of
+the workers' ``read_batch`` slices -- and columns drawn on the device stay resident; in
+both cases ll never leaves the device, and the only exchange is the 8-byte max key
+(integer MAX all-reduce over NCCL when the shards live in different processes) and the
+accepted indices.
 
 Two deployments share this code:
   * one process driving several GPUs (``DeviceEngine(devices=[0, 1, ...])``) -- keys

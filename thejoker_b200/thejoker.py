@@ -1,6 +1,6 @@
 """TheJoker: the orchestrator of thejoker/thejoker.py with the same public methods
 (``marginal_ln_likelihood``, ``rejection_sample``, ``iterative_rejection_sample``),
-driving device-resident shards instead of a schwimmbad pool.
+driving per-GPU shards (sharding.DeviceEngine) instead of a schwimmbad pool.
 
 RNG contract: ``self.rng`` is a numpy Generator and is
 consumed exactly as the reference consumes it --
