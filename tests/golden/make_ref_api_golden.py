@@ -16,7 +16,8 @@ TARGETS = {
     "samples.py": ["JokerSamples"],
 }
 FUNCTIONS = {
-    "utils.py": ["batch_tasks"],
+    "utils.py": ["batch_tasks", "read_batch", "read_batch_slice", "read_batch_idx",
+                 "read_random_batch"],
     "likelihood_helpers.py": ["get_constant_term_design_matrix", "get_trend_design_matrix",
                               "ln_normal"],
     "data_helpers.py": ["validate_prepare_data"],

@@ -14,7 +14,7 @@ import os
 import pytest
 
 import thejoker_b200 as tj
-from thejoker_b200 import data_helpers, likelihood_helpers, sharding
+from thejoker_b200 import cache, data_helpers, likelihood_helpers, sharding
 from thejoker_b200 import prior as prior_helpers  # the reference keeps these in prior_helpers.py
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -24,6 +24,8 @@ with open(os.path.join(HERE, "golden", "ref_api_signatures.json")) as f:
 CLASSES = {"TheJoker": tj.TheJoker, "JokerPrior": tj.JokerPrior, "RVData": tj.RVData,
            "JokerSamples": tj.JokerSamples}
 FUNCTIONS = {"batch_tasks": sharding.batch_tasks,
+             "read_batch": cache.read_batch, "read_batch_slice": cache.read_batch_slice,
+             "read_batch_idx": cache.read_batch_idx, "read_random_batch": cache.read_random_batch,
              "get_constant_term_design_matrix": likelihood_helpers.get_constant_term_design_matrix,
              "get_trend_design_matrix": likelihood_helpers.get_trend_design_matrix,
              "ln_normal": likelihood_helpers.ln_normal,

@@ -373,6 +373,47 @@ def test_prior_cache_roundtrip(tmp_path):
             read_reference_hdf5("nope.hdf5")
 
 
+@pytest.mark.parametrize("kind", ["cache_dir", "npz"])
+def test_read_batch_family(tmp_path, kind):
+    """thejoker/tests/test_utils.py::test_read_batch_slice / _idx / _random_batch on the
+    native cache directory and on a JokerSamples.write file."""
+    from thejoker_b200.cache import (read_batch, read_batch_idx, read_batch_slice,
+                                     read_random_batch, write_prior_cache)
+
+    prior = default_prior(1)
+    ps = prior.sample(size=100, rng=np.random.default_rng(3), return_logprobs=True)
+    ps["s"] = np.linspace(0.0, 1.0, 100) * u.km / u.s
+    ps._uniform_s = False
+    if kind == "cache_dir":
+        fn = write_prior_cache(ps, str(tmp_path / "cache"))
+    else:
+        fn = str(tmp_path / "samples.npz")
+        ps.write(fn)
+    P, om, sv = ps["P"].to_value(u.day), ps["omega"].to_value(u.rad), ps["s"].to_value(u.km / u.s)
+    for read_func in (read_batch_slice, read_batch):
+        batch = read_func(fn, ["P", "omega"], slice(10, 20))
+        assert batch.shape == (10, 2)
+        assert np.allclose(batch[:, 0], P[10:20]) and np.allclose(batch[:, 1], om[10:20])
+        batch = read_func(fn, ["s", "P"], slice(0, 100), units={"s": u.m / u.s})
+        assert batch.shape == (100, 2)
+        assert np.allclose(batch[:, 0], sv * 1e3) and np.allclose(batch[:, 1], P)
+        assert read_func(fn, ["P", "e"], slice(0, 100, 2)).shape == (50, 2)
+    assert np.array_equal(read_batch(fn, ["P"], (5, 9)), read_batch_slice(fn, ["P"], slice(5, 9)))
+    idx = np.arange(10, 20)
+    for read_func in (read_batch_idx, read_batch):
+        batch = read_func(fn, ["P", "omega"], idx, units=None)
+        assert batch.shape == (10, 2) and np.allclose(batch[:, 0], P[idx])
+        batch = read_func(fn, ["s", "P"], idx, units={"s": u.m / u.s})
+        assert np.allclose(batch[:, 0], sv[idx] * 1e3) and np.allclose(batch[:, 1], P[idx])
+    for read_func in (read_random_batch, read_batch):
+        assert read_func(fn, ["P", "e"], 10, units=None).shape == (10, 2)
+        full = read_func(fn, ["P", "e"], 100, units=None, rng=np.random.default_rng(1))
+        assert full.shape == (100, 2) and np.allclose(np.sort(full[:, 0]), np.sort(P))
+    with pytest.raises(ValueError):
+        read_batch(fn, ["P"], "nope")
+    assert np.allclose(read_batch(fn, ["ln_prior"], slice(0, 5))[:, 0], ps["ln_prior"].value[:5])
+
+
 def test_poly_trend_zero_is_rejected_like_the_reference():
     """poly_trend=0 still yields the constant column (likelihood_helpers.py:21, 34-37), so
     the reference's shape check (pyx:174-179) raises; same here."""

@@ -25,7 +25,8 @@ import numpy as np
 from . import units as u
 from .samples import JokerSamples
 
-__all__ = ["write_prior_cache", "PriorCache", "read_reference_hdf5"]
+__all__ = ["write_prior_cache", "PriorCache", "read_reference_hdf5", "read_batch",
+           "read_batch_slice", "read_batch_idx", "read_random_batch"]
 
 _COLS = ("P", "e", "omega", "M0", "s")
 _INTERNAL = {"P": u.day, "e": u.one, "omega": u.rad, "M0": u.rad}
@@ -108,6 +109,74 @@ class PriorCache:
         if self.has_ln_prior:
             out["ln_prior"] = np.array(self._mm["ln_prior"][lo:hi])
         return out
+
+
+# -- row-block readers with the reference's names and signatures (utils.py:106-245) ------
+def _open_columns(prior_samples_file):
+    """(getter(name) -> (array-like column, unit), n_rows) for a native cache directory or
+    a file written by JokerSamples.write."""
+    if os.path.isdir(prior_samples_file):
+        cache = PriorCache(prior_samples_file)
+
+        def get(name):
+            unit = _INTERNAL.get(name, cache.rv_unit)
+            if name == "ln_prior":
+                return cache._mm[name], u.one
+            if name == "s" and cache.s_const is not None:
+                return np.broadcast_to(np.float64(cache.s_const), (cache.n,)), unit
+            return cache._mm[name], unit
+
+        return get, cache.n
+    samples = JokerSamples.read(prior_samples_file)
+    return (lambda name: (samples[name].value, samples[name].unit)), len(samples)
+
+
+def _read_rows(prior_samples_file, columns, rows, units):
+    get, _ = _open_columns(prior_samples_file)
+    batch = None
+    for i, name in enumerate(columns):
+        col, unit = get(name)
+        arr = np.asarray(col[rows], dtype=np.float64)
+        if batch is None:
+            batch = np.zeros((len(arr), len(columns)))
+        batch[:, i] = arr
+        if units is not None and name in units:
+            batch[:, i] *= float(unit.to(u.as_unit(units[name])))
+    return np.zeros((0, len(columns))) if batch is None else batch
+
+
+def read_batch_slice(prior_samples_file, columns, slice, units=None):
+    """Rows ``slice`` of the named columns as a plain (n, len(columns)) float64 array,
+    converted to ``units`` where given (utils.py:168-198)."""
+    return _read_rows(prior_samples_file, columns, slice, units)
+
+
+def read_batch_idx(prior_samples_file, columns, idx, units=None):
+    """The same for an index array (utils.py:201-228)."""
+    return _read_rows(prior_samples_file, columns, np.asarray(idx), units)
+
+
+def read_random_batch(prior_samples_file, columns, size, units=None, rng=None):
+    """``size`` distinct random rows (utils.py:231-245)."""
+    if rng is None:
+        rng = np.random.default_rng()
+    _, n = _open_columns(prior_samples_file)
+    idx = rng.choice(n, size=size, replace=False)
+    return read_batch_idx(prior_samples_file, columns, idx=idx, units=units)
+
+
+def read_batch(prior_samples_file, columns, slice_or_idx, units=None, rng=None):
+    """Single entry point (utils.py:106-165): a slice or (start, stop) tuple reads a
+    contiguous block, an integer a random batch of that size, an array those rows."""
+    if isinstance(slice_or_idx, tuple):
+        slice_or_idx = slice(*slice_or_idx)
+    if isinstance(slice_or_idx, slice):
+        return read_batch_slice(prior_samples_file, columns, slice_or_idx, units=units)
+    if isinstance(slice_or_idx, (int, np.integer)):
+        return read_random_batch(prior_samples_file, columns, slice_or_idx, units=units, rng=rng)
+    if isinstance(slice_or_idx, np.ndarray):
+        return read_batch_idx(prior_samples_file, columns, slice_or_idx, units=units)
+    raise ValueError("Invalid input for slice_or_idx: must be a slice, int, or numpy array.")
 
 
 def read_reference_hdf5(filename):
