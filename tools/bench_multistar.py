@@ -33,19 +33,40 @@ for i in range(n_stars):
     stars.append([tj.RVData(full._t_bmjd[:cut], full.rv[:cut], full.rv_err[:cut]),
                   tj.RVData(full._t_bmjd[cut:], (full.rv.value[cut:] + off) * u.km / u.s,
                             full.rv_err[cut:])])
-ms = tj.MultiStarJoker(prior, ps, rng=np.random.default_rng(2), devices=[0],
-                       streams_per_device=streams)
+world = int(os.environ.get("WORLD_SIZE", "1"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+group = None
+if world > 1:  # torchrun: one rank per GPU, stars sharded over the ranks
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    group = dist.group.WORLD
+ms = tj.MultiStarJoker(prior, ps, rng=np.random.default_rng(2), devices=[local],
+                       streams_per_device=streams, group=group)
 ms.rejection_sample(stars[:4], max_posterior_samples=256)  # upload + warm-up
 torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
 t0 = time.perf_counter()
-out = ms.rejection_sample(stars, max_posterior_samples=256)
+out = ms.rejection_sample(stars, max_posterior_samples=256)  # includes the result gather
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
-rec = dict(streams_per_device=streams, n_stars=n_stars, n_prior=1 << log2_prior, seconds=dt, stars_per_s=n_stars / dt,
+if world > 1:
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    if dist.get_rank() != 0:
+        dist.destroy_process_group()
+        sys.exit(0)
+rec = dict(n_gpus=world, streams_per_device=streams, n_stars=n_stars, n_prior=1 << log2_prior, seconds=dt, stars_per_s=n_stars / dt,
            prior_evaluations_per_s=n_stars * (1 << log2_prior) / dt,
            mean_epochs=float(np.mean([len(s[0]) + len(s[1]) for s in stars])),
            mean_posterior_samples=float(np.mean([len(o) for o in out])),
            extrapolated_4096_stars_s=4096 * dt / n_stars)
 print(json.dumps(rec))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(rec, open(os.path.join(ROOT, "gpurun_out", f"multistar_s{streams}.json"), "w"), indent=1)
+json.dump(rec, open(os.path.join(ROOT, "gpurun_out", f"multistar_g{world}_s{streams}.json"), "w"),
+          indent=1)
+if world > 1:
+    dist.destroy_process_group()
