@@ -171,6 +171,41 @@ int tjb_design_column(TjbHandle *h, const double *h_row, double *h_z, int32_t *h
  * whatever jitter_mode says (the reference's samples.py does apply it). */
 int tjb_unmarginalized_ll(TjbHandle *h, const double *h_rows, int64_t k, double *h_ll);
 
+/* ---- many stars against one shared, device-resident prior cache ------------------
+ * The reference has no batched entry point: users loop over stars and every
+ * TheJoker.rejection_sample call re-creates the CJokerHelper and re-reads the prior
+ * cache (thejoker/thejoker.py:87-91, 213-257; rejection_sample_inmem,
+ * likelihood_helpers.py:91-127).  This runs that loop natively -- per star: point a
+ * handle at the star (tjb_update_star), marginal ll over the whole prior, accept with the
+ * star's own PCG64 stream, gather the accepted rows from the device columns, draw the
+ * linear parameters (batch_get_posterior_samples, pyx:471-545) -- on n_slots host
+ * threads, each with its own handle, CUDA stream and ll buffer, so the host side of one
+ * star overlaps the kernels of the others.  Stars are independent, so the results do not
+ * depend on n_slots or on which slot ran a star. */
+typedef struct TjbMultiStarJob {
+  int64_t n_stars;
+  const TjbSpec *specs;     /* [n_stars], all with the same n_linear L */
+  const TjbPcg64 *pcg;      /* [n_stars] generator state of each star's uniforms (see tjb_accept) */
+  /* shared prior cache: SoA device columns on `device`; d_s may be NULL (then s_const) */
+  const double *d_P, *d_e, *d_omega, *d_M0, *d_s;
+  double s_const;
+  int64_t n_prior;
+  int64_t max_keep;         /* accepted samples kept per star (max_posterior_samples) */
+  double near_tol;          /* as tjb_accept */
+  int32_t n_per;            /* linear-parameter draws per accepted sample; 0 = indices only */
+  int32_t clamp_K;          /* as tjb_posterior_draw */
+  int32_t n_slots;          /* stars in flight (host threads), 1..64 */
+  int32_t reserved;
+  const double *h_normals;  /* [n_stars, max_keep, n_per, L] standard normals (n_per > 0) */
+  /* outputs, HOST; star i writes only the first h_counts[3i+1] entries of its slices */
+  int64_t *h_idx;           /* [n_stars, max_keep] accepted prior indices, ascending */
+  int64_t *h_counts;        /* [n_stars, 3] as tjb_accept */
+  double *h_llmax;          /* [n_stars] max ll over the prior */
+  double *h_rows;           /* [n_stars, max_keep * n_per, 5 + L] packed samples (n_per > 0) */
+  double *h_ll;             /* [n_stars, max_keep] ll of the accepted samples (n_per > 0; may be NULL) */
+} TjbMultiStarJob;
+int tjb_multistar_rejection(int device, const TjbMultiStarJob *job);
+
 /* Solver statistics accumulated by every likelihood launch of this handle since the
  * last reset: h_stats[0] = extra FP64 Householder passes (lane-epochs that needed more
  * than one; high eccentricity near pericentre), h_stats[1] = epochs that did not

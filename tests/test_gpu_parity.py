@@ -812,8 +812,28 @@ def test_multistar_driver_matches_per_star(torch_cuda):
                       tj.RVData(full._t_bmjd[cut:], (full.rv.value[cut:] + 3.0) * u.km / u.s,
                                 full.rv_err[cut:])])
     ms = tj.MultiStarJoker(prior, ps, rng=np.random.default_rng(77), devices=[0])
-    out = ms.rejection_sample(stars, max_posterior_samples=64)
-    assert len(out) == 6
+    out = ms.rejection_sample(stars, max_posterior_samples=64, return_logprobs=True)
+    assert len(out) == 6 and ms.engine == "native"
+    # the Python-driven loop gives the same samples, likelihoods and statistics
+    mp = tj.MultiStarJoker(prior, ps, rng=np.random.default_rng(77), devices=[0], engine="python")
+    outp = mp.rejection_sample(stars, max_posterior_samples=64, return_logprobs=True)
+    for a, b, sa, sb in zip(out, outp, ms.last_stats, mp.last_stats):
+        assert sa == sb
+        for k in ("P", "e", "omega", "M0", "s", "K", "v0", "dv0_1", "ln_likelihood"):
+            va, vb = (np.asarray(getattr(x[k], "value", x[k])) for x in (a, b))
+            assert np.array_equal(va, vb), k
+    # several draws per accepted sample, one star in flight, more slots than stars
+    for slots in (1, 16):
+        m2 = tj.MultiStarJoker(prior, ps, rng=np.random.default_rng(5), devices=[0],
+                               streams_per_device=slots)
+        o2 = m2.rejection_sample(stars, max_posterior_samples=16, n_linear_samples=3)
+        p2 = tj.MultiStarJoker(prior, ps, rng=np.random.default_rng(5), devices=[0],
+                               engine="python").rejection_sample(
+            stars, max_posterior_samples=16, n_linear_samples=3)
+        for a, b in zip(o2, p2):
+            assert len(a) == len(b) and len(a) % 3 == 0
+            for k in ("P", "K", "v0", "dv0_1"):
+                assert np.array_equal(a[k].value, b[k].value), (slots, k)
     seqs = np.random.default_rng(77).bit_generator._seed_seq.spawn(6)
     for i, star in enumerate(stars):
         child = np.random.Generator(np.random.PCG64(seqs[i]))

@@ -203,6 +203,122 @@ def test_no_gpu_fails_loudly():
         tj.TheJoker(prior)._make_joker_helper(data)
 
 
+def test_multistar_job_validation():
+    """tjb_multistar_rejection checks its job before touching CUDA (no GPU here: a valid
+    job must fail with the no-device error, not crash)."""
+    import ctypes
+
+    import torch
+
+    lib = _lib.load()
+    spec, data, prior = star_spec(8, 1)
+    cs = (_lib.TjbSpec * 2)()
+    cs[0] = tj.CJokerHelper._c_spec(spec)
+    cs[1] = tj.CJokerHelper._c_spec(spec)
+    pcg = (_lib.TjbPcg64 * 2)()
+    counts = np.zeros((2, 3), dtype=np.int64)
+    idx = np.zeros((2, 4), dtype=np.int64)
+    dummy = ctypes.c_void_p(8)  # never dereferenced before the device check
+    vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+
+    def job(**kw):
+        base = dict(n_stars=2, specs=cs, pcg=pcg, d_P=dummy, d_e=dummy, d_omega=dummy,
+                    d_M0=dummy, d_s=None, s_const=0.0, n_prior=16, max_keep=4, near_tol=1e-12,
+                    n_per=0, clamp_K=0, n_slots=2, h_idx=vp(idx), h_counts=vp(counts))
+        base.update(kw)
+        return _lib.TjbMultiStarJob(**base)
+
+    def run(j):
+        return lib.tjb_multistar_rejection(0, ctypes.byref(j)), lib.tjb_last_error().decode()
+
+    assert lib.tjb_multistar_rejection(0, None) == -1
+    assert run(job(n_stars=0))[0] == 0  # nothing to do
+    for bad in (dict(n_prior=0), dict(n_slots=0), dict(n_slots=65), dict(max_keep=-1),
+                dict(d_P=None), dict(h_counts=None), dict(specs=None), dict(n_per=1)):
+        rc, msg = run(job(**bad))
+        assert rc == -1 and msg, bad
+    cs[1].n_linear = 3
+    rc, msg = run(job())
+    assert rc == -1 and "n_linear" in msg
+    cs[1].n_linear = cs[0].n_linear
+    if not torch.cuda.is_available():
+        rc, msg = run(job())
+        assert rc == -2 and "no CUDA device" in msg
+
+
+def test_multistar_native_pipeline_host_side(monkeypatch):
+    """The host side of the native multi-star engine -- chunking, per-star specs, child
+    generators, pre-drawn normals, unpacking -- with the library call replaced by a stand-in
+    that echoes what it was given (no GPU here; tests/test_gpu_parity.py runs the real one)."""
+    import ctypes
+    import types
+
+    from thejoker_b200.prior import Normal
+    from thejoker_b200.synthetic import make_noisy_data
+
+    prior = default_prior(1, sigma_K0=25.0, v0_offsets=[Normal("dv0_1", 0.0, 5.0, u.km / u.s)])
+    n_prior, n_stars, keep, n_per, L = 64, 45, 5, 2, 3
+    stars = []
+    for i in range(n_stars):
+        full, _ = make_noisy_data(10 + i % 7, seed=i)
+        stars.append([tj.RVData(full._t_bmjd[:4], full.rv[:4], full.rv_err[:4]),
+                      tj.RVData(full._t_bmjd[4:], full.rv[4:], full.rv_err[4:])])
+    calls = []
+
+    class FakeLib:
+        @staticmethod
+        def tjb_multistar_rejection(device, jobref):
+            job = jobref._obj
+            n = job.n_stars
+            calls.append(n)
+            assert job.n_prior == n_prior and job.max_keep == keep and job.n_per == n_per
+            shape = lambda p, sh, t: np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(t)), sh)
+            counts = shape(job.h_counts, (n, 3), ctypes.c_int64)
+            rows = shape(job.h_rows, (n, keep * n_per, 5 + L), ctypes.c_double)
+            nrm = shape(job.h_normals, (n, keep, n_per, L), ctypes.c_double)
+            ll = shape(job.h_ll, (n, keep), ctypes.c_double)
+            llmax = shape(job.h_llmax, (n,), ctypes.c_double)
+            for j in range(n):
+                sp = job.specs[j]
+                k = sp.n_times % (keep + 1)
+                counts[j] = (k + 10, k, 1)
+                rows[j, : k * n_per, :5] = sp.n_times
+                rows[j, : k * n_per, 5:] = nrm[j, :k].reshape(k * n_per, L)
+                ll[j, :k] = np.arange(k)
+                llmax[j] = job.pcg[j].state_lo % 1000
+            return 0
+
+    monkeypatch.setattr(_lib, "load", lambda: FakeLib)
+    ms = tj.MultiStarJoker(prior, None, rng=np.random.default_rng(9), devices=[0],
+                           streams_per_device=2)
+    col = types.SimpleNamespace(data_ptr=lambda: 8)
+    ms._dev = {0: dict(cols=[col] * 4, s=None, slots=[])}
+    ms._host_cols = [np.zeros(n_prior)] * 5
+    ms._s_const = 0.0
+    ms._helper0 = types.SimpleNamespace(n_linear=L)
+    out = ms.rejection_sample(stars, max_posterior_samples=keep, n_linear_samples=n_per,
+                              return_logprobs=True)
+    assert sum(calls) == n_stars and calls[0] == 8 and len(calls) > 2  # growing chunks
+    seqs = np.random.default_rng(9).bit_generator._seed_seq.spawn(n_stars)
+    for i, smp in enumerate(out):
+        n_t = 10 + i % 7
+        k = n_t % (keep + 1)
+        assert len(smp) == k * n_per
+        child = np.random.Generator(np.random.PCG64(seqs[i]))
+        assert ms.last_stats[i] == dict(n_accepted=k + 10, n_near_threshold=1,
+                                        ll_max=float((child.bit_generator.state["state"]["state"]
+                                                      & ((1 << 64) - 1)) % 1000))
+        child.bit_generator.advance(n_prior)
+        z = child.standard_normal((k, n_per, L)).reshape(-1, L)
+        assert np.array_equal(smp["P"].value, np.full(k * n_per, float(n_t)))
+        assert np.array_equal(smp["K"].value, z[:, 0]) and np.array_equal(smp["dv0_1"].value, z[:, 2])
+        assert np.array_equal(smp["ln_likelihood"], np.repeat(np.arange(k), n_per))
+    # settings the native loop does not cover fall back to the Python engine
+    assert tj.MultiStarJoker(prior, None, engine="python").engine == "python"
+    with pytest.raises(ValueError):
+        tj.MultiStarJoker(prior, None, engine="cpu")
+
+
 def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "thejoker_b200")
     for fn in os.listdir(pkg):

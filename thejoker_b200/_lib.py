@@ -48,6 +48,30 @@ class TjbPcg64(ctypes.Structure):
                 ("inc_hi", ctypes.c_uint64), ("inc_lo", ctypes.c_uint64)]
 
 
+class TjbMultiStarJob(ctypes.Structure):
+    _fields_ = [
+        ("n_stars", ctypes.c_int64),
+        ("specs", ctypes.POINTER(TjbSpec)),
+        ("pcg", ctypes.POINTER(TjbPcg64)),
+        ("d_P", ctypes.c_void_p), ("d_e", ctypes.c_void_p), ("d_omega", ctypes.c_void_p),
+        ("d_M0", ctypes.c_void_p), ("d_s", ctypes.c_void_p),
+        ("s_const", ctypes.c_double),
+        ("n_prior", ctypes.c_int64),
+        ("max_keep", ctypes.c_int64),
+        ("near_tol", ctypes.c_double),
+        ("n_per", ctypes.c_int32),
+        ("clamp_K", ctypes.c_int32),
+        ("n_slots", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("h_normals", ctypes.c_void_p),
+        ("h_idx", ctypes.c_void_p),
+        ("h_counts", ctypes.c_void_p),
+        ("h_llmax", ctypes.c_void_p),
+        ("h_rows", ctypes.c_void_p),
+        ("h_ll", ctypes.c_void_p),
+    ]
+
+
 # every symbol include/thejoker_b200.h declares: name -> (restype, argtypes)
 _vp = ctypes.c_void_p
 _H = ctypes.c_void_p  # TjbHandle*
@@ -83,6 +107,7 @@ SYMBOLS = {
     "tjb_posterior_aA": (ctypes.c_int, [_H, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp]),
     "tjb_posterior_draw": (ctypes.c_int, [_H, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _vp,
                                           _vp, _vp]),
+    "tjb_multistar_rejection": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(TjbMultiStarJob)]),
     "tjb_unmarginalized_ll": (ctypes.c_int, [_H, _vp, ctypes.c_int64, _vp]),
     "tjb_design_column": (ctypes.c_int, [_H, _vp, _vp, _vp]),
     "tjb_get_stats": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int]),

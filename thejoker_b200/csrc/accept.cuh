@@ -68,7 +68,17 @@ struct PcgParams {
 };
 
 constexpr int kAccThreads = 256;
-constexpr int kAccWordsPerCta = 2048;  // 65536 samples per CTA
+// Mask words (32 samples each) owned by one CTA of the flag and scatter kernels: a power
+// of two in [kAccMinWordsPerCta, kAccMaxWordsPerCta] chosen per call so that small arrays
+// (one star of a multi-star batch, an early round of the iterative sampler) still fill
+// the GPU, while large ones amortise the per-thread PCG jump over up to 256 samples.
+constexpr int kAccMaxWordsPerCta = 2048;  // 65536 samples per CTA
+constexpr int kAccMinWordsPerCta = 256;   // 8192 samples per CTA: one mask word per lane in the scatter
+inline int acc_words_per_cta(long long n_words, int n_sm) {
+  int w = kAccMaxWordsPerCta;
+  while (w > kAccMinWordsPerCta && n_words / w < 4LL * n_sm) w >>= 1;
+  return w;
+}
 
 // out[i] = the (offset+i)-th uniform; grid-stride leapfrog
 __global__ void __launch_bounds__(kAccThreads)
@@ -84,17 +94,18 @@ pcg64_uniform_kernel(const PcgParams pp, const long long n, double *__restrict__
   }
 }
 
-// CTA b owns mask words [b*W, (b+1)*W), W = kAccWordsPerCta; warp j of the CTA
+// CTA b owns mask words [b*W, (b+1)*W), W = words_per_cta; warp j of the CTA
 // visits words b*W + j, b*W + j + 8, ... so that a thread's samples are 256
 // apart: the PCG leapfrog stride inside a CTA is the constant blockDim.
 __global__ void __launch_bounds__(kAccThreads)
 accept_flag_kernel(const double *__restrict__ ll, const long long n,
                    const long long *__restrict__ llmax_key, const double *__restrict__ uniforms,
-                   const PcgParams pp, const double near_tol, unsigned *__restrict__ mask,
-                   unsigned *__restrict__ cta_counts, unsigned long long *__restrict__ totals) {
+                   const PcgParams pp, const double near_tol, const int words_per_cta,
+                   unsigned *__restrict__ mask, unsigned *__restrict__ cta_counts,
+                   unsigned long long *__restrict__ totals) {
   const double llmax = key_to_ll(*llmax_key);
-  const long long first = (long long)blockIdx.x * kAccWordsPerCta * 32 + threadIdx.x;
-  const long long cta_end = min(n, ((long long)blockIdx.x + 1) * kAccWordsPerCta * 32);
+  const long long first = (long long)blockIdx.x * words_per_cta * 32 + threadIdx.x;
+  const long long cta_end = min(n, ((long long)blockIdx.x + 1) * words_per_cta * 32);
   const long long n_words = (n + 31) / 32;
   u128 st = 0;
   if (pp.enabled && first < n) {
@@ -169,17 +180,17 @@ accept_scan_kernel(const unsigned *__restrict__ cta_counts, const int m,
 }
 
 // CTA b expands its mask words in ascending order.  Warp j takes the contiguous
-// word range [j*W/8, (j+1)*W/8) of the CTA, lane l word (range start + 32 it + l).
+// word range [j*W/8, (j+1)*W/8) of the CTA (W = words_per_cta), lane l word (range start + 32 it + l).
 __global__ void __launch_bounds__(kAccThreads)
 accept_scatter_kernel(const unsigned *__restrict__ mask, const long long n,
                       const unsigned long long *__restrict__ cta_offsets,
                       const long long index_base, const long long max_keep,
-                      long long *__restrict__ idx_out) {
+                      const int words_per_cta, long long *__restrict__ idx_out) {
   constexpr int kWarps = kAccThreads / 32;
-  constexpr int kWordsPerWarp = kAccWordsPerCta / kWarps;
+  const int kWordsPerWarp = words_per_cta / kWarps;  // a multiple of 32
   const long long n_words = (n + 31) / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long w0 = (long long)blockIdx.x * kAccWordsPerCta + (long long)warp * kWordsPerWarp;
+  const long long w0 = (long long)blockIdx.x * words_per_cta + (long long)warp * kWordsPerWarp;
   const unsigned long long cta_off = cta_offsets[blockIdx.x];
   if ((long long)cta_off >= max_keep) return;
 

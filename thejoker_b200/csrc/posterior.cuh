@@ -125,6 +125,25 @@ posterior_kernel(const StarParams sp, const double *__restrict__ rows, const int
   }
 }
 
+// rows[j] = [P, e, omega, M0, s][idx[j]]: the packed rows of the accepted samples, taken
+// from the device-resident prior columns (multiproc_helpers.py:261-263 does this on the
+// host with read_batch_idx).  s == null: every sample has jitter s_const.
+__global__ void gather_rows_kernel(const double *__restrict__ P, const double *__restrict__ e,
+                                   const double *__restrict__ omega, const double *__restrict__ M0,
+                                   const double *__restrict__ s, const double s_const,
+                                   const long long *__restrict__ idx, const int k,
+                                   double *__restrict__ rows) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= k) return;
+  const long long i = idx[j];
+  double *o = rows + 5 * (long long)j;
+  o[0] = P[i];
+  o[1] = e[i];
+  o[2] = omega[i];
+  o[3] = M0[i];
+  o[4] = s ? s[i] : s_const;
+}
+
 // z[n] for one sample, computed by every lane of one warp (lane 0 writes)
 __global__ void design_column_kernel(const double *__restrict__ dt, const int N, const double P,
                                      const double e, const double om, const double M0,

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <functional>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -786,7 +788,8 @@ int tjb_accept(TjbHandle *h, const double *d_ll, int64_t n, const int64_t *d_llm
   if (max_keep > 0 && !d_idx) return fail(TJB_E_INVALID, "null index buffer");
   CU(cudaSetDevice(h->device));
   const long long n_words = (n + 31) / 32;
-  const int n_cta = (int)((n_words + kAccWordsPerCta - 1) / kAccWordsPerCta);
+  const int wpc = acc_words_per_cta(n_words, h->n_sm);
+  const int n_cta = (int)((n_words + wpc - 1) / wpc);
   if (h->acc_mask.ensure((size_t)n_words * sizeof(unsigned)) ||
       h->acc_counts.ensure((size_t)n_cta * sizeof(unsigned)) ||
       h->acc_offsets.ensure((size_t)n_cta * sizeof(unsigned long long)) ||
@@ -795,8 +798,8 @@ int tjb_accept(TjbHandle *h, const double *d_ll, int64_t n, const int64_t *d_llm
   CU(cudaMemsetAsync(h->acc_totals.p, 0, 2 * sizeof(unsigned long long), h->stream));
   const PcgParams pp = make_pcg(pcg, pcg_offset, kAccThreads);
   accept_flag_kernel<<<n_cta, kAccThreads, 0, h->stream>>>(
-      d_ll, n, (const long long *)d_llmax_key, d_uniforms, pp, near_tol, (unsigned *)h->acc_mask.p,
-      (unsigned *)h->acc_counts.p, (unsigned long long *)h->acc_totals.p);
+      d_ll, n, (const long long *)d_llmax_key, d_uniforms, pp, near_tol, wpc,
+      (unsigned *)h->acc_mask.p, (unsigned *)h->acc_counts.p, (unsigned long long *)h->acc_totals.p);
   CU(cudaGetLastError());
   accept_scan_kernel<<<1, 1024, 0, h->stream>>>((const unsigned *)h->acc_counts.p, n_cta,
                                                (unsigned long long *)h->acc_offsets.p);
@@ -804,7 +807,7 @@ int tjb_accept(TjbHandle *h, const double *d_ll, int64_t n, const int64_t *d_llm
   if (max_keep > 0) {
     accept_scatter_kernel<<<n_cta, kAccThreads, 0, h->stream>>>(
         (const unsigned *)h->acc_mask.p, n, (const unsigned long long *)h->acc_offsets.p,
-        index_base, max_keep, (long long *)d_idx);
+        index_base, max_keep, wpc, (long long *)d_idx);
     CU(cudaGetLastError());
   }
   unsigned long long tot[2] = {0, 0};
@@ -852,6 +855,152 @@ static int posterior_common(TjbHandle *h, const double *h_rows, int64_t k, int c
   CU(cudaStreamSynchronize(h->stream));
   return TJB_OK;
 }
+
+// ---- multi-star loop ---------------------------------------------------------------
+
+namespace {
+
+// one star in flight: handle, stream and device buffers of a slot thread
+struct StarSlot {
+  TjbHandle *h = nullptr;
+  cudaStream_t st = nullptr;
+  DevBuf ll, key, idx, rows, nrm, out, oll;
+  int rc = TJB_OK;
+  std::string err;
+};
+
+// everything one star needs, on the slot's stream; one host synchronisation for the
+// accept counts and one at the end
+int run_star(StarSlot &sl, const TjbMultiStarJob &job, int64_t i, bool load) {
+  TjbHandle *h = sl.h;
+  const int L = job.specs[0].n_linear, W = 5 + L;
+  const int64_t keep = std::min(job.max_keep, job.n_prior);
+  int rc;
+  if (load && (rc = tjb_update_star(h, &job.specs[i]))) return rc;
+  static const long long kNegInf = ll_to_key(-INFINITY);
+  CU(cudaMemcpyAsync(sl.key.p, &kNegInf, sizeof(kNegInf), cudaMemcpyHostToDevice, sl.st));
+  rc = tjb_marginal_ll_soa(h, job.d_P, job.d_e, job.d_omega, job.d_M0, job.d_s, job.s_const,
+                           job.n_prior, (double *)sl.ll.p, (int64_t *)sl.key.p);
+  if (rc) return rc;
+  int64_t *counts = job.h_counts + 3 * i;
+  rc = tjb_accept(h, (const double *)sl.ll.p, job.n_prior, (const int64_t *)sl.key.p, nullptr,
+                  &job.pcg[i], 0, 0, keep, job.near_tol, (int64_t *)sl.idx.p, counts);
+  if (rc) return rc;
+  const int64_t k = counts[1];
+  long long key = 0;
+  CU(cudaMemcpyAsync(&key, sl.key.p, sizeof(key), cudaMemcpyDeviceToHost, sl.st));
+  if (k > 0 && job.h_idx)
+    CU(cudaMemcpyAsync(job.h_idx + i * job.max_keep, sl.idx.p, (size_t)k * sizeof(int64_t),
+                       cudaMemcpyDeviceToHost, sl.st));
+  if (k > 0 && job.n_per > 0) {
+    const size_t n_draw = (size_t)k * job.n_per;
+    gather_rows_kernel<<<(int)((k + 127) / 128), 128, 0, sl.st>>>(
+        job.d_P, job.d_e, job.d_omega, job.d_M0, job.d_s, job.s_const, (const long long *)sl.idx.p,
+        (int)k, (double *)sl.rows.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(sl.nrm.p, job.h_normals + (size_t)i * job.max_keep * job.n_per * L,
+                       n_draw * L * sizeof(double), cudaMemcpyHostToDevice, sl.st));
+    rc = dispatch_posterior(h, (const double *)sl.rows.p, (int)k, job.clamp_K, job.n_per,
+                            (const double *)sl.nrm.p, (double *)sl.oll.p, nullptr, nullptr,
+                            (double *)sl.out.p);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(job.h_rows + (size_t)i * job.max_keep * job.n_per * W, sl.out.p,
+                       n_draw * W * sizeof(double), cudaMemcpyDeviceToHost, sl.st));
+    if (job.h_ll)
+      CU(cudaMemcpyAsync(job.h_ll + i * job.max_keep, sl.oll.p, (size_t)k * sizeof(double),
+                         cudaMemcpyDeviceToHost, sl.st));
+  }
+  CU(cudaStreamSynchronize(sl.st));
+  if (job.h_llmax) job.h_llmax[i] = key_to_ll(key);
+  return TJB_OK;
+}
+
+// a slot thread: takes the next star off the shared counter until none is left or any
+// slot has failed
+void slot_main(StarSlot &sl, int device, const TjbMultiStarJob &job, std::atomic<int64_t> &next,
+               std::atomic<int> &failed) {
+  auto body = [&]() -> int {
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking));
+    const int L = job.specs[0].n_linear;
+    const size_t keep = (size_t)std::max<int64_t>(1, std::min(job.max_keep, job.n_prior));
+    const size_t n_draw = keep * (size_t)std::max(job.n_per, 1);
+    if (sl.ll.ensure((size_t)job.n_prior * sizeof(double)) || sl.key.ensure(sizeof(long long)) ||
+        sl.idx.ensure(keep * sizeof(int64_t)) || sl.rows.ensure(keep * 5 * sizeof(double)) ||
+        sl.nrm.ensure(n_draw * L * sizeof(double)) ||
+        sl.out.ensure(n_draw * (5 + L) * sizeof(double)) || sl.oll.ensure(keep * sizeof(double)))
+      return fail(TJB_E_NOMEM, "cudaMalloc multi-star slot");
+    bool first = true;
+    for (;;) {
+      const int64_t i = next.fetch_add(1);
+      if (i >= job.n_stars || failed.load()) break;
+      int rc;
+      if (first) {
+        if ((rc = tjb_create(&job.specs[i], device, &sl.h))) return rc;
+        if ((rc = tjb_set_stream(sl.h, sl.st))) return rc;
+      }
+      if ((rc = run_star(sl, job, i, !first))) return rc;
+      first = false;
+    }
+    return TJB_OK;
+  };
+  sl.rc = body();
+  if (sl.rc) {
+    sl.err = g_err;  // thread-local: hand the message to the calling thread
+    failed.store(1);
+  }
+  if (sl.st) cudaStreamSynchronize(sl.st);
+  sl.ll.release(); sl.key.release(); sl.idx.release(); sl.rows.release();
+  sl.nrm.release(); sl.out.release(); sl.oll.release();
+}
+
+}  // namespace
+
+int tjb_multistar_rejection(int device, const TjbMultiStarJob *job) {
+  if (!job) return fail(TJB_E_INVALID, "null job");
+  if (job->n_stars < 0 || job->n_prior < 1 || job->max_keep < 0 || job->n_per < 0)
+    return fail(TJB_E_INVALID, "bad sizes");
+  if (job->n_stars == 0) return TJB_OK;
+  if (job->n_slots < 1 || job->n_slots > 64) return fail(TJB_E_INVALID, "n_slots must be in 1..64");
+  if (!job->specs || !job->pcg || !job->h_counts) return fail(TJB_E_INVALID, "null argument");
+  if (!job->d_P || !job->d_e || !job->d_omega || !job->d_M0)
+    return fail(TJB_E_INVALID, "null device pointer");
+  if (job->max_keep > 0 && !job->h_idx && job->n_per == 0)
+    return fail(TJB_E_INVALID, "no output requested");
+  if (job->n_per > 0 && job->max_keep > 0 && (!job->h_normals || !job->h_rows))
+    return fail(TJB_E_INVALID, "null normals / rows");
+  for (int64_t i = 0; i < job->n_stars; i++) {
+    int rc = validate_spec(&job->specs[i]);
+    if (rc) return rc;
+    if (job->specs[i].n_linear != job->specs[0].n_linear)
+      return fail(TJB_E_INVALID, "all stars of a job must have the same n_linear");
+  }
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1)
+    return fail(TJB_E_CUDA, "no CUDA device available: libthejoker_b200 has no CPU path");
+  if (device < 0 || device >= n_dev) return fail(TJB_E_INVALID, "device index out of range");
+
+  const int n_slots = (int)std::min<int64_t>(job->n_slots, job->n_stars);
+  std::vector<StarSlot> slots(n_slots);
+  std::atomic<int64_t> next(0);
+  std::atomic<int> failed(0);
+  std::vector<std::thread> pool;
+  for (int k = 1; k < n_slots; k++)
+    pool.emplace_back(slot_main, std::ref(slots[k]), device, std::cref(*job), std::ref(next),
+                      std::ref(failed));
+  slot_main(slots[0], device, *job, next, failed);
+  for (auto &t : pool) t.join();
+  // handles and streams go last: tjb_destroy synchronises the whole device
+  for (auto &sl : slots) {
+    if (sl.h) tjb_destroy(sl.h);
+    if (sl.st) cudaStreamDestroy(sl.st);
+  }
+  for (auto &sl : slots)
+    if (sl.rc) return fail(sl.rc, sl.err);
+  return TJB_OK;
+}
+
+// ---- posterior (host rows) -----------------------------------------------------------
 
 int tjb_posterior_aA(TjbHandle *h, const double *h_rows, int64_t k, int clamp_K, double *h_ll,
                      double *h_a, double *h_A) {

@@ -9,6 +9,15 @@ GPU, one library handle per GPU is re-pointed at each star (``tjb_update_star``)
 stars are sharded over GPUs / ranks with the reference's ``batch_tasks`` rule -- no
 collective is needed (each star is an independent rejection-sampling problem).
 
+Two engines run the star loop.  ``engine="native"`` (default): the loop itself is C++
+(``tjb_multistar_rejection``: per-star handle update, ll, accept, row gather and linear
+draws on a few host threads with one CUDA stream each, no Python between the kernels);
+this process only prepares the stars of the next chunk (``validate_prepare_data``,
+``extract_spec``, the child generators) and unpacks the previous chunk's results while the
+current chunk runs with the GIL released.  ``engine="python"``: the same steps driven from
+Python threads, one library call at a time (needed for ``draw="numpy"`` and for
+``max_posterior_samples=None``).  Both give identical results.
+
 RNG: star i draws from its own child generator ``Generator(PCG64(seed_seq.spawn(n)[i]))``
 (the reference's own device for per-task streams, multiproc_helpers.py:49-54), consumed
 as ``rejection_sample(..., in_memory=True)`` consumes it: ``uniform(size=n_prior)`` then
@@ -16,10 +25,13 @@ the linear-parameter draws.  Results therefore do not depend on how stars are sh
 """
 from __future__ import annotations
 
+import ctypes
+
 import numpy as np
 
+from . import _lib
 from .data_helpers import validate_prepare_data
-from .helper import CJokerHelper
+from .helper import CJokerHelper, _pcg_struct, extract_spec
 from .samples import JokerSamples
 from .sharding import shard_ranges
 
@@ -41,10 +53,19 @@ class MultiStarJoker:
         CJokerHelper.batch_get_posterior_samples ("device" by default: with hundreds of
         accepted samples per star a Python call per row would dominate the star's time)
     streams_per_device : stars in flight per GPU (default 4); results do not depend on it
+    engine : "native" (default; the star loop runs inside the library) or "python"
     """
 
+    # the native engine pre-draws max_posterior_samples x n_linear_samples x L normals per
+    # star; beyond this many per star the Python engine (which draws exactly what is
+    # needed) is used instead
+    _NATIVE_MAX_NORMALS = 1 << 16
+
     def __init__(self, prior, prior_samples, rng=None, devices=(0,), jitter_mode="apply",
-                 group=None, draw="device", streams_per_device=4):
+                 group=None, draw="device", streams_per_device=4, engine="native"):
+        if engine not in ("native", "python"):
+            raise ValueError("engine must be 'native' or 'python'")
+        self.engine = engine
         self.prior = prior
         self.rng = np.random.default_rng() if rng is None else rng
         self.devices = list(devices)
@@ -76,20 +97,121 @@ class MultiStarJoker:
             uniform_s = True
         self._host_cols = cols
         self._s_const = float(cols[4][0]) if uniform_s and len(cols[4]) else 0.0
-        n = len(cols[0])
         for d in self.devices:
             with torch.cuda.device(d):
                 up = lambda a: torch.from_numpy(a).to(f"cuda:{d}")
-                slots = []
-                for k in range(self.streams_per_device):
-                    first = d == self.devices[0] and k == 0
-                    slots.append(dict(
-                        helper=helper0 if first else first_helper_factory(d),
-                        ll=torch.empty(n, dtype=torch.float64, device=f"cuda:{d}"),
-                        stream=torch.cuda.Stream(device=d)))
                 self._dev[d] = dict(cols=[up(c) for c in cols[:4]],
-                                    s=None if uniform_s else up(cols[4]), slots=slots)
+                                    s=None if uniform_s else up(cols[4]), slots=[])
                 torch.cuda.synchronize(d)  # the slots' streams read the uploaded columns
+        self._helper0 = helper0
+        self._factory = first_helper_factory
+
+    def _python_slots(self, d):
+        """The Python engine's per-slot helper, ll buffer and stream (created on first use)."""
+        import torch
+
+        st = self._dev[d]
+        n = len(self._host_cols[0])
+        with torch.cuda.device(d):
+            while len(st["slots"]) < self.streams_per_device:
+                first = d == self.devices[0] and not st["slots"]
+                st["slots"].append(dict(
+                    helper=self._helper0 if first else self._factory(d),
+                    ll=torch.empty(n, dtype=torch.float64, device=f"cuda:{d}"),
+                    stream=torch.cuda.Stream(device=d)))
+        return st["slots"]
+
+    # -- native engine --------------------------------------------------------------
+    def _build_chunk(self, d, star_ids, prepare, seqs, keep, n_per):
+        """Host side of one native call: the stars' specs, generator states and
+        pre-drawn normals, plus the output arrays."""
+        n, L = len(star_ids), self._helper0.n_linear
+        n_prior = len(self._host_cols[0])
+        specs = (_lib.TjbSpec * n)()
+        pcg = (_lib.TjbPcg64 * n)()
+        normals = np.empty((n, keep, n_per, L))
+        alive, meta = [], []
+        for j, i in enumerate(star_ids):
+            all_data, ids, trend_M = prepare(i)
+            sp = extract_spec(all_data, self.prior, trend_M, self.jitter_mode)
+            if sp["n_linear"] != L:
+                raise ValueError("all stars must have the same number of linear parameters")
+            specs[j] = CJokerHelper._c_spec(sp)
+            child = np.random.Generator(np.random.PCG64(seqs[i]))
+            pcg[j] = _pcg_struct(child)
+            # consumed as rejection_sample(in_memory=True) consumes it: uniform(size=n_prior),
+            # then the normals of the accepted rows (a prefix of what is drawn here)
+            child.bit_generator.advance(n_prior)
+            normals[j] = child.standard_normal((keep, n_per, L))
+            alive.append(sp)  # the spec's arrays are read by the native call
+            meta.append((sp["internal_units"], all_data.t_ref))
+        st = self._dev[d]
+        out = dict(idx=np.empty((n, keep), dtype=np.int64), counts=np.zeros((n, 3), dtype=np.int64),
+                   llmax=np.empty(n), rows=np.empty((n, keep * n_per, 5 + L)),
+                   ll=np.empty((n, keep)))
+        vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+        job = _lib.TjbMultiStarJob(
+            n_stars=n, specs=specs, pcg=pcg,
+            d_P=st["cols"][0].data_ptr(), d_e=st["cols"][1].data_ptr(),
+            d_omega=st["cols"][2].data_ptr(), d_M0=st["cols"][3].data_ptr(),
+            d_s=st["s"].data_ptr() if st["s"] is not None else None,
+            s_const=self._s_const, n_prior=n_prior, max_keep=keep, near_tol=1e-12,
+            n_per=n_per, clamp_K=0, n_slots=self.streams_per_device,
+            h_normals=vp(normals), h_idx=vp(out["idx"]), h_counts=vp(out["counts"]),
+            h_llmax=vp(out["llmax"]), h_rows=vp(out["rows"]), h_ll=vp(out["ll"]))
+        return dict(job=job, alive=(alive, specs, pcg, normals), meta=meta, out=out,
+                    star_ids=star_ids, device=d)
+
+    def _finish_chunk(self, chunk, n_per, return_logprobs, results, stats):
+        out = chunk["out"]
+        for j, i in enumerate(chunk["star_ids"]):
+            k = int(out["counts"][j, 1])
+            units, t_ref = chunk["meta"][j]
+            smp = JokerSamples.unpack(out["rows"][j, : k * n_per], units, t_ref=t_ref,
+                                      poly_trend=self.prior.poly_trend,
+                                      n_offsets=self.prior.n_offsets)
+            if return_logprobs:
+                smp["ln_likelihood"] = np.repeat(out["ll"][j, :k], n_per)
+            results[i] = smp
+            stats[i] = dict(n_accepted=int(out["counts"][j, 0]),
+                            n_near_threshold=int(out["counts"][j, 2]),
+                            ll_max=float(out["llmax"][j]))
+
+    def _run_native(self, prepare, seqs, r_lo, dev_ranges, keep, n_per, return_logprobs,
+                    results, stats):
+        """Chunks of stars through tjb_multistar_rejection, one call in flight per device;
+        this thread prepares the next chunk and unpacks the previous one meanwhile (ctypes
+        releases the GIL for the duration of the call)."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        lib = _lib.load()
+
+        def call(chunk):
+            rc = lib.tjb_multistar_rejection(chunk["device"], ctypes.byref(chunk["job"]))
+            _lib.check(rc)  # the error message is per thread: read it here
+            return chunk
+
+        # chunk sizes grow so that the GPU starts early and the tail of each call is short
+        # against its length
+        todo = {}
+        for d, (a, b) in zip(self.devices, dev_ranges):
+            ids, pos, size = list(range(r_lo + a, r_lo + b)), 0, 4 * self.streams_per_device
+            chunks = []
+            while pos < len(ids):
+                chunks.append(ids[pos:pos + size])
+                pos += size
+                size = min(4 * size, 512)
+            todo[d] = chunks
+        with ThreadPoolExecutor(max(1, len(self.devices))) as ex:
+            running = {d: None for d in self.devices}
+            while any(todo[d] for d in self.devices) or any(running.values()):
+                for d in self.devices:
+                    nxt = (self._build_chunk(d, todo[d].pop(0), prepare, seqs, keep, n_per)
+                           if todo[d] else None)
+                    done = running[d].result() if running[d] is not None else None
+                    running[d] = ex.submit(call, nxt) if nxt is not None else None
+                    if done is not None:
+                        self._finish_chunk(done, n_per, return_logprobs, results, stats)
 
     def rejection_sample(self, stars, max_posterior_samples=256, n_linear_samples=1,
                          return_logprobs=False):
@@ -125,6 +247,13 @@ class MultiStarJoker:
 
         results = {}
         stats = {}
+        n_lin = self._helper0.n_linear
+        native = (self.engine == "native" and self.draw == "device" and
+                  min(max_keep, n_prior) * int(n_linear_samples) * n_lin <= self._NATIVE_MAX_NORMALS)
+        if native:
+            self._run_native(prepare, seqs, r_lo, dev_ranges, min(max_keep, n_prior),
+                             int(n_linear_samples), return_logprobs, results, stats)
+            dev_ranges = [(0, 0)] * len(self.devices)  # nothing left for the Python engine
 
         def run_slot(d, slot, star_indices):
             """All the stars of one slot, in order, on the slot's own stream."""
@@ -158,6 +287,8 @@ class MultiStarJoker:
 
         work = []
         for d, (a, b) in zip(self.devices, dev_ranges):
+            if b > a:
+                self._python_slots(d)  # created here, not in the slot threads
             k = self.streams_per_device
             for slot in range(k):
                 mine = list(range(r_lo + a + slot, r_lo + b, k))

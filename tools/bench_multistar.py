@@ -21,6 +21,7 @@ from thejoker_b200.synthetic import make_noisy_data  # noqa: E402
 n_stars = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 log2_prior = int(sys.argv[2]) if len(sys.argv) > 2 else 22
 streams = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+engine = sys.argv[4] if len(sys.argv) > 4 else "native"  # or "python": the loop driven from Python
 rng = np.random.default_rng(0)
 prior = default_prior(1, sigma_K0=30.0, v0_offsets=[Normal("dv0_1", 0.0, 5.0, u.km / u.s)])
 ps = prior.sample(size=1 << log2_prior, rng=np.random.default_rng(1))
@@ -43,7 +44,7 @@ if world > 1:  # torchrun: one rank per GPU, stars sharded over the ranks
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     group = dist.group.WORLD
 ms = tj.MultiStarJoker(prior, ps, rng=np.random.default_rng(2), devices=[local],
-                       streams_per_device=streams, group=group)
+                       streams_per_device=streams, group=group, engine=engine)
 ms.rejection_sample(stars[:4], max_posterior_samples=256)  # upload + warm-up
 torch.cuda.synchronize()
 if world > 1:
@@ -59,14 +60,14 @@ if world > 1:
     if dist.get_rank() != 0:
         dist.destroy_process_group()
         sys.exit(0)
-rec = dict(n_gpus=world, streams_per_device=streams, n_stars=n_stars, n_prior=1 << log2_prior, seconds=dt, stars_per_s=n_stars / dt,
+rec = dict(n_gpus=world, engine=engine, streams_per_device=streams, n_stars=n_stars, n_prior=1 << log2_prior, seconds=dt, stars_per_s=n_stars / dt,
            prior_evaluations_per_s=n_stars * (1 << log2_prior) / dt,
            mean_epochs=float(np.mean([len(s[0]) + len(s[1]) for s in stars])),
            mean_posterior_samples=float(np.mean([len(o) for o in out])),
            extrapolated_4096_stars_s=4096 * dt / n_stars)
 print(json.dumps(rec))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(rec, open(os.path.join(ROOT, "gpurun_out", f"multistar_g{world}_s{streams}.json"), "w"),
+json.dump(rec, open(os.path.join(ROOT, "gpurun_out", f"multistar_g{world}_s{streams}_{engine}.json"), "w"),
           indent=1)
 if world > 1:
     dist.destroy_process_group()
