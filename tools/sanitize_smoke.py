@@ -47,4 +47,20 @@ joker = tj.TheJoker(prior, rng=np.random.default_rng(42))
 joker.rejection_sample(flat, ps, in_memory=True)
 joker.iterative_rejection_sample(flat, ps, n_requested_samples=8, in_memory=True, growth_factor=16)
 joker.rejection_sample(flat, 30_000)
+# native multi-star loop: several slot threads, ragged stars, two surveys each
+from thejoker_b200 import units as u  # noqa: E402
+from thejoker_b200.prior import Normal  # noqa: E402
+from thejoker_b200.synthetic import make_noisy_data  # noqa: E402
+
+prior2 = default_prior(1, sigma_K0=25.0, v0_offsets=[Normal("dv0_1", 0.0, 5.0, u.km / u.s)])
+ps2 = prior2.sample(size=9_001, rng=np.random.default_rng(1))
+stars = []
+for i in range(7):
+    full, _ = make_noisy_data(9 + 3 * i, seed=100 + i, K=[None, 1e-4][i % 2])
+    stars.append([tj.RVData(full._t_bmjd[:4], full.rv[:4], full.rv_err[:4]),
+                  tj.RVData(full._t_bmjd[4:], full.rv[4:], full.rv_err[4:])])
+out = tj.MultiStarJoker(prior2, ps2, rng=np.random.default_rng(3), devices=[0],
+                        streams_per_device=3).rejection_sample(stars, max_posterior_samples=32,
+                                                               n_linear_samples=2)
+assert len(out) == 7 and all(len(o) % 2 == 0 for o in out)
 print("sanitize smoke ok")
