@@ -1,5 +1,6 @@
 """Small end-to-end pass over every kernel, for compute-sanitizer (memcheck / racecheck /
-initcheck) on the GPU box:  compute-sanitizer --tool memcheck python tools/sanitize_smoke.py"""
+initcheck) on the GPU box:  compute-sanitizer --tool memcheck python tools/sanitize_smoke.py
+[multistar]   (with the argument: only the native multi-star loop)"""
 import os
 import sys
 
@@ -13,7 +14,8 @@ import thejoker_b200 as tj  # noqa: E402
 from helpers import default_prior, prior_chunk, star_spec  # noqa: E402
 from thejoker_b200.synthetic import make_data  # noqa: E402
 
-for N, pt, kw in ((7, 1, {}), (16, 2, {"n_surveys": 2}), (33, 3, {})):
+only_multistar = len(sys.argv) > 1 and sys.argv[1] == "multistar"
+for N, pt, kw in (() if only_multistar else ((7, 1, {}), (16, 2, {"n_surveys": 2}), (33, 3, {}))):
     spec, data, prior = star_spec(N, pt, **kw)
     helper = tj.CJokerHelper.from_spec(spec, device=0)
     for n, sl in ((1, None), (1000, None), (4097, (-2.0, 1.0))):
@@ -40,13 +42,15 @@ for N, pt, kw in ((7, 1, {}), (16, 2, {"n_surveys": 2}), (33, 3, {})):
         h_ll = helper.marginal_ln_likelihood_columns(*hc)
         assert np.array_equal(d_ll.cpu().numpy(), h_ll)
         assert np.array_equal(helper.batch_marginal_ln_likelihood(big), h_ll)
-prior = default_prior(1, sigma_K0=25.0, P_min=5.0, P_max=500.0)
-flat, _ = make_data(8, rng=np.random.default_rng(11), K=1e-4)
-ps = prior.sample(size=20_000, return_logprobs=True, rng=np.random.default_rng(1))
-joker = tj.TheJoker(prior, rng=np.random.default_rng(42))
-joker.rejection_sample(flat, ps, in_memory=True)
-joker.iterative_rejection_sample(flat, ps, n_requested_samples=8, in_memory=True, growth_factor=16)
-joker.rejection_sample(flat, 30_000)
+if not only_multistar:
+    prior = default_prior(1, sigma_K0=25.0, P_min=5.0, P_max=500.0)
+    flat, _ = make_data(8, rng=np.random.default_rng(11), K=1e-4)
+    ps = prior.sample(size=20_000, return_logprobs=True, rng=np.random.default_rng(1))
+    joker = tj.TheJoker(prior, rng=np.random.default_rng(42))
+    joker.rejection_sample(flat, ps, in_memory=True)
+    joker.iterative_rejection_sample(flat, ps, n_requested_samples=8, in_memory=True,
+                                     growth_factor=16)
+    joker.rejection_sample(flat, 30_000)
 # native multi-star loop: several slot threads, ragged stars, two surveys each
 from thejoker_b200 import units as u  # noqa: E402
 from thejoker_b200.prior import Normal  # noqa: E402
