@@ -130,3 +130,70 @@ def mode_chunk(spec, n=400, sigma=0.5, seed=0):
     chunk[:, 2] = 0.283 + rng.normal(0, 5e-3 * sc, n)
     chunk[:, 3] = M0p + rng.normal(0, 5e-3 * sc, n)
     return chunk
+
+
+# ---- stand-ins for the native multi-star call (host-side tests without a GPU) -----------
+def fake_multistar_stars(n_stars):
+    """(prior with one survey offset, n_stars two-survey stars with 10..16 epochs)."""
+    import thejoker_b200 as tj
+    from thejoker_b200 import units as u
+    from thejoker_b200.prior import Normal
+    from thejoker_b200.synthetic import make_noisy_data
+
+    prior = default_prior(1, sigma_K0=25.0, v0_offsets=[Normal("dv0_1", 0.0, 5.0, u.km / u.s)])
+    stars = []
+    for i in range(n_stars):
+        full, _ = make_noisy_data(10 + i % 7, seed=i)
+        stars.append([tj.RVData(full._t_bmjd[:4], full.rv[:4], full.rv_err[:4]),
+                      tj.RVData(full._t_bmjd[4:], full.rv[4:], full.rv_err[4:])])
+    return prior, stars
+
+
+def fake_multistar_lib(n_prior, keep, n_per, L):
+    """An object with a ``tjb_multistar_rejection`` that echoes what it is given: star j
+    'accepts' k = n_times % (keep + 1) samples whose rows carry n_times in the nonlinear
+    columns and the star's pre-drawn normals in the linear ones; ll = 0..k-1; ll_max is
+    derived from the star's generator state.  Returns (lib, list of stars per call)."""
+    import ctypes
+
+    calls = []
+
+    class FakeLib:
+        @staticmethod
+        def tjb_multistar_rejection(device, jobref):
+            job = jobref._obj
+            n = job.n_stars
+            calls.append(n)
+            assert job.n_prior == n_prior and job.max_keep == keep and job.n_per == n_per
+            shape = lambda p, sh, t: np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(t)), sh)
+            counts = shape(job.h_counts, (n, 3), ctypes.c_int64)
+            rows = shape(job.h_rows, (n, keep * n_per, 5 + L), ctypes.c_double)
+            nrm = shape(job.h_normals, (n, keep, n_per, L), ctypes.c_double)
+            ll = shape(job.h_ll, (n, keep), ctypes.c_double)
+            llmax = shape(job.h_llmax, (n,), ctypes.c_double)
+            for j in range(n):
+                sp = job.specs[j]
+                k = sp.n_times % (keep + 1)
+                counts[j] = (k + 10, k, 1)
+                rows[j, : k * n_per, :5] = sp.n_times
+                rows[j, : k * n_per, 5:] = nrm[j, :k].reshape(k * n_per, L)
+                ll[j, :k] = np.arange(k)
+                llmax[j] = job.pcg[j].state_lo % 1000
+            return 0
+
+    return FakeLib, calls
+
+
+def fake_multistar_joker(prior, n_prior, L, **kw):
+    """A MultiStarJoker whose device state is filled in by hand (no CUDA)."""
+    import types
+
+    import thejoker_b200 as tj
+
+    ms = tj.MultiStarJoker(prior, None, devices=[0], streams_per_device=2, **kw)
+    col = types.SimpleNamespace(data_ptr=lambda: 8)
+    ms._dev = {0: dict(cols=[col] * 4, s=None, slots=[])}
+    ms._host_cols = [np.zeros(n_prior)] * 5
+    ms._s_const = 0.0
+    ms._helper0 = types.SimpleNamespace(n_linear=L)
+    return ms

@@ -68,3 +68,77 @@ def test_two_rank_accept_matches_single_process(tmp_path, max_keep):
     for k in range(world):
         assert r[k]["total"] == len(want)
         assert np.array_equal(r[k]["idx"], want if max_keep is None else want[:max_keep])
+
+
+def _multistar_worker(rank, world, port, n_stars, out_dir):
+    """Two gloo ranks run the multi-star driver over the same star list (the native call
+    is replaced by the echoing stand-in of tests/helpers.py: no GPU here)."""
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import pickle
+
+    from helpers import fake_multistar_joker, fake_multistar_lib, fake_multistar_stars
+
+    from thejoker_b200 import _lib
+
+    n_prior, keep, n_per, L = 64, 5, 2, 3
+    prior, stars = fake_multistar_stars(n_stars)
+    lib, calls = fake_multistar_lib(n_prior, keep, n_per, L)
+    _lib.load = lambda: lib
+    res = {}
+    for gather in (True, False):
+        ms = fake_multistar_joker(prior, n_prior, L, rng=np.random.default_rng(9),
+                                  group=dist.group.WORLD)
+        out = ms.rejection_sample(stars, max_posterior_samples=keep, n_linear_samples=n_per,
+                                  return_logprobs=True, gather=gather)
+        res[gather] = ([None if o is None else
+                        {k: np.asarray(getattr(o[k], "value", o[k])) for k in ("P", "K", "dv0_1",
+                                                                                "ln_likelihood")}
+                        for o in out], ms.last_stats, [None if o is None else o.t_ref for o in out])
+    res["n_computed"] = sum(calls)
+    with open(os.path.join(out_dir, f"ms{rank}.pkl"), "wb") as f:
+        pickle.dump(res, f)
+    dist.destroy_process_group()
+
+
+def test_two_rank_multistar_sharding_and_exchange(tmp_path, monkeypatch):
+    """Stars are sharded over the ranks (batch_tasks rule), each star is computed exactly
+    once, and after the packed exchange every rank holds what a single process computes."""
+    import pickle
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import fake_multistar_joker, fake_multistar_lib, fake_multistar_stars
+
+    from thejoker_b200 import _lib
+    from thejoker_b200.sharding import shard_ranges
+
+    n_stars, world = 23, 2
+    mp.spawn(_multistar_worker, args=(world, _free_port(), n_stars, str(tmp_path)), nprocs=world,
+             join=True)
+    prior, stars = fake_multistar_stars(n_stars)
+    lib, _ = fake_multistar_lib(64, 5, 2, 3)
+    monkeypatch.setattr(_lib, "load", lambda: lib)
+    ms = fake_multistar_joker(prior, 64, 3, rng=np.random.default_rng(9))
+    want = ms.rejection_sample(stars, max_posterior_samples=5, n_linear_samples=2,
+                               return_logprobs=True)
+    r = [pickle.load(open(tmp_path / f"ms{k}.pkl", "rb")) for k in range(world)]
+    assert r[0]["n_computed"] + r[1]["n_computed"] == 2 * n_stars  # two passes, each star once
+    ranges = shard_ranges(n_stars, world)
+    for k in range(world):
+        full, stats, t_ref = r[k][True]
+        assert stats == ms.last_stats
+        for i in range(n_stars):
+            assert t_ref[i] == want[i].t_ref
+            for name in ("P", "K", "dv0_1", "ln_likelihood"):
+                assert np.array_equal(full[i][name],
+                                      np.asarray(getattr(want[i][name], "value", want[i][name])))
+        own, own_stats, _ = r[k][False]
+        lo, hi = ranges[k]
+        for i in range(n_stars):
+            assert (own[i] is not None) == (lo <= i < hi) == (own_stats[i] is not None)
+            if own[i] is not None:
+                assert np.array_equal(own[i]["K"], full[i]["K"])

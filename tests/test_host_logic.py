@@ -250,52 +250,15 @@ def test_multistar_native_pipeline_host_side(monkeypatch):
     """The host side of the native multi-star engine -- chunking, per-star specs, child
     generators, pre-drawn normals, unpacking -- with the library call replaced by a stand-in
     that echoes what it was given (no GPU here; tests/test_gpu_parity.py runs the real one)."""
-    import ctypes
-    import types
+    from helpers import fake_multistar_stars
 
-    from thejoker_b200.prior import Normal
-    from thejoker_b200.synthetic import make_noisy_data
-
-    prior = default_prior(1, sigma_K0=25.0, v0_offsets=[Normal("dv0_1", 0.0, 5.0, u.km / u.s)])
     n_prior, n_stars, keep, n_per, L = 64, 45, 5, 2, 3
-    stars = []
-    for i in range(n_stars):
-        full, _ = make_noisy_data(10 + i % 7, seed=i)
-        stars.append([tj.RVData(full._t_bmjd[:4], full.rv[:4], full.rv_err[:4]),
-                      tj.RVData(full._t_bmjd[4:], full.rv[4:], full.rv_err[4:])])
-    calls = []
+    prior, stars = fake_multistar_stars(n_stars)
+    from helpers import fake_multistar_lib, fake_multistar_joker
 
-    class FakeLib:
-        @staticmethod
-        def tjb_multistar_rejection(device, jobref):
-            job = jobref._obj
-            n = job.n_stars
-            calls.append(n)
-            assert job.n_prior == n_prior and job.max_keep == keep and job.n_per == n_per
-            shape = lambda p, sh, t: np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(t)), sh)
-            counts = shape(job.h_counts, (n, 3), ctypes.c_int64)
-            rows = shape(job.h_rows, (n, keep * n_per, 5 + L), ctypes.c_double)
-            nrm = shape(job.h_normals, (n, keep, n_per, L), ctypes.c_double)
-            ll = shape(job.h_ll, (n, keep), ctypes.c_double)
-            llmax = shape(job.h_llmax, (n,), ctypes.c_double)
-            for j in range(n):
-                sp = job.specs[j]
-                k = sp.n_times % (keep + 1)
-                counts[j] = (k + 10, k, 1)
-                rows[j, : k * n_per, :5] = sp.n_times
-                rows[j, : k * n_per, 5:] = nrm[j, :k].reshape(k * n_per, L)
-                ll[j, :k] = np.arange(k)
-                llmax[j] = job.pcg[j].state_lo % 1000
-            return 0
-
+    FakeLib, calls = fake_multistar_lib(n_prior, keep, n_per, L)
     monkeypatch.setattr(_lib, "load", lambda: FakeLib)
-    ms = tj.MultiStarJoker(prior, None, rng=np.random.default_rng(9), devices=[0],
-                           streams_per_device=2)
-    col = types.SimpleNamespace(data_ptr=lambda: 8)
-    ms._dev = {0: dict(cols=[col] * 4, s=None, slots=[])}
-    ms._host_cols = [np.zeros(n_prior)] * 5
-    ms._s_const = 0.0
-    ms._helper0 = types.SimpleNamespace(n_linear=L)
+    ms = fake_multistar_joker(prior, n_prior, L, rng=np.random.default_rng(9))
     out = ms.rejection_sample(stars, max_posterior_samples=keep, n_linear_samples=n_per,
                               return_logprobs=True)
     assert sum(calls) == n_stars and calls[0] == 8 and len(calls) > 2  # growing chunks

@@ -22,6 +22,7 @@ n_stars = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 log2_prior = int(sys.argv[2]) if len(sys.argv) > 2 else 22
 streams = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 engine = sys.argv[4] if len(sys.argv) > 4 else "native"  # or "python": the loop driven from Python
+gather = os.environ.get("TJB_MS_GATHER", "1") != "0"  # ranks exchange results (every rank returns all stars)
 rng = np.random.default_rng(0)
 prior = default_prior(1, sigma_K0=30.0, v0_offsets=[Normal("dv0_1", 0.0, 5.0, u.km / u.s)])
 ps = prior.sample(size=1 << log2_prior, rng=np.random.default_rng(1))
@@ -50,7 +51,7 @@ torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 t0 = time.perf_counter()
-out = ms.rejection_sample(stars, max_posterior_samples=256)  # includes the result gather
+out = ms.rejection_sample(stars, max_posterior_samples=256, gather=gather)  # includes the result exchange
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 if world > 1:
@@ -63,11 +64,12 @@ if world > 1:
 rec = dict(n_gpus=world, engine=engine, streams_per_device=streams, n_stars=n_stars, n_prior=1 << log2_prior, seconds=dt, stars_per_s=n_stars / dt,
            prior_evaluations_per_s=n_stars * (1 << log2_prior) / dt,
            mean_epochs=float(np.mean([len(s[0]) + len(s[1]) for s in stars])),
-           mean_posterior_samples=float(np.mean([len(o) for o in out])),
+           mean_posterior_samples=float(np.mean([len(o) for o in out if o is not None])),
+           gather=gather,
            extrapolated_4096_stars_s=4096 * dt / n_stars)
 print(json.dumps(rec))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(rec, open(os.path.join(ROOT, "gpurun_out", f"multistar_g{world}_s{streams}_{engine}.json"), "w"),
+json.dump(rec, open(os.path.join(ROOT, "gpurun_out", f"multistar_g{world}_s{streams}_{engine}{'' if gather else '_nogather'}.json"), "w"),
           indent=1)
 if world > 1:
     dist.destroy_process_group()
