@@ -3,6 +3,7 @@ the sharding rule, spec extraction, the C-ABI library's exported symbols, and th
 device math compiled for the host (tools/host_emulation.cpp) against the oracle."""
 import ctypes
 import os
+import sys
 import re
 
 import numpy as np
@@ -491,6 +492,143 @@ def test_read_batch_family(tmp_path, kind):
     with pytest.raises(ValueError):
         read_batch(fn, ["P"], "nope")
     assert np.allclose(read_batch(fn, ["ln_prior"], slice(0, 5))[:, 0], ps["ln_prior"].value[:5])
+
+
+def test_table_header_parser_on_astropy_headers():
+    """parse_table_column_meta on headers written by astropy's own table serialiser (the
+    reference's docs/examples/*.ecsv, same YAML as ``samples.__table_column_meta__``):
+    units come from the datatype entries, the ``!astropy...`` nodes of the serialised
+    Quantity columns must not leak into them, and a serialised Time becomes an MJD."""
+    import json
+
+    from thejoker_b200.cache import _meta_kwargs, parse_table_column_meta
+
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_table_headers.json")))
+    units, cols, meta = parse_table_column_meta(g["ecsv:data.ecsv"])
+    assert cols == ["bjd", "rv", "rv_err"]
+    assert units == {"bjd": "", "rv": "km / s", "rv_err": "km / s"}
+    assert abs(_meta_kwargs(meta)["t_ref"] - 58511.29511355243) < 1e-9
+    assert "__serialized_columns__" not in meta
+    units, _, meta = parse_table_column_meta(g["ecsv:data-triple.ecsv"])
+    assert units["rv"] == "km / s" and _meta_kwargs(meta) == {}
+    for key in ("prior_samples", "prior_samples_units_in_meta_only"):
+        lines = [ln.encode() for ln in g[key]]  # h5py hands back bytes
+        units, cols, meta = parse_table_column_meta(lines)
+        assert cols == ["P", "e", "omega", "M0", "s", "ln_prior"]
+        assert units == {"P": "d", "e": "", "omega": "rad", "M0": "rad", "s": "m / s",
+                         "ln_prior": ""}
+        assert _meta_kwargs(meta) == {"poly_trend": 1, "n_offsets": 0}
+    with pytest.raises(ValueError):
+        parse_table_column_meta(["meta: {a: 1}"])
+
+
+def _fake_h5py(monkeypatch, files):
+    """A module with h5py's read interface over in-memory arrays: File(name, 'r') is a
+    context manager mapping dataset names to objects with len / dtype / slicing / [()]."""
+    import types
+
+    class Dataset:
+        def __init__(self, arr):
+            self._a = arr
+            self.n_reads, self.max_rows = 0, 0
+
+        dtype = property(lambda self: self._a.dtype)
+
+        def __len__(self):
+            return len(self._a)
+
+        def __getitem__(self, key):
+            out = self._a[key]
+            self.n_reads += 1
+            self.max_rows = max(self.max_rows, np.size(out))
+            return out
+
+    class File(dict):
+        def __init__(self, name, mode="r"):
+            assert mode == "r"
+            super().__init__(files[name])
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    store = {name: {k: Dataset(v) for k, v in dsets.items()} for name, dsets in files.items()}
+    files.clear()
+    files.update(store)
+    mod = types.ModuleType("h5py")
+    mod.File = File
+    monkeypatch.setitem(sys.modules, "h5py", mod)
+    return store
+
+
+def test_reference_hdf5_cache_reader_and_converter(tmp_path, monkeypatch):
+    """The reference's prior-cache layout (compound-row dataset ``samples`` + YAML header
+    dataset, samples.py:535-563) through read_reference_hdf5 and the blockwise
+    convert_reference_hdf5, with h5py replaced by an in-memory stand-in (h5py is not in this
+    image) and the header in astropy's format."""
+    import json
+
+    from thejoker_b200.cache import (PriorCache, convert_reference_hdf5, read_reference_hdf5,
+                                     write_prior_cache)
+
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_table_headers.json")))
+    n = 1000
+    rng = np.random.default_rng(4)
+    rows = np.zeros(n, dtype=[(c, "<f8") for c in ("P", "e", "omega", "M0", "s", "ln_prior")])
+    rows["P"], rows["e"] = rng.uniform(2, 100, n), rng.uniform(0, 0.9, n)
+    rows["omega"], rows["M0"] = rng.uniform(0, 6, n), rng.uniform(0, 6, n)
+    rows["s"], rows["ln_prior"] = rng.uniform(0, 300, n), rng.normal(size=n)  # s in m/s
+    hdr = np.array([ln.encode() for ln in g["prior_samples"]])
+    const = rows.copy()
+    const["s"] = 125.0
+    files = {"prior.hdf5": {"samples": rows, "samples.__table_column_meta__": hdr},
+             "const.hdf5": {"samples": const, "samples.__table_column_meta__": hdr}}
+    store = _fake_h5py(monkeypatch, files)
+
+    smp = read_reference_hdf5("prior.hdf5")
+    assert len(smp) == n and smp.poly_trend == 1 and smp.n_offsets == 0
+    assert np.array_equal(smp["P"].to_value(u.day), rows["P"])
+    assert np.allclose(smp["s"].to_value(u.km / u.s), rows["s"] / 1e3, rtol=1e-15)
+    assert np.array_equal(smp["ln_prior"].value, rows["ln_prior"])
+    part = read_reference_hdf5("prior.hdf5", lo=100, hi=164)
+    assert np.array_equal(part["e"].value, rows["e"][100:164])
+
+    store["prior.hdf5"]["samples"].max_rows = 0
+    out = convert_reference_hdf5("prior.hdf5", str(tmp_path / "c1"), rows_per_block=128)
+    assert store["prior.hdf5"]["samples"].max_rows <= 128  # never the whole table at once
+    cache = PriorCache(out)
+    cols = cache.columns()
+    for i, c in enumerate(("P", "e", "omega", "M0")):
+        assert np.array_equal(cols[i], rows[c])
+    assert np.allclose(cols[4], rows["s"] / 1e3, rtol=1e-15) and cache.s_const is None
+    assert np.array_equal(cache.ln_prior(), rows["ln_prior"])
+    # the converted cache equals what write_prior_cache makes of the same samples
+    write_prior_cache(smp, str(tmp_path / "c2"))
+    for c in ("P", "e", "omega", "M0", "s", "ln_prior"):
+        assert np.allclose(np.load(tmp_path / "c1" / f"{c}.npy"), np.load(tmp_path / "c2" / f"{c}.npy"),
+                           rtol=1e-15, atol=0)
+    # a constant jitter column collapses to a scalar; rv_unit converts it
+    c3 = PriorCache(convert_reference_hdf5("const.hdf5", str(tmp_path / "c3"), rv_unit=u.m / u.s,
+                                           rows_per_block=300))
+    assert c3.s_const == 125.0 and not os.path.exists(tmp_path / "c3" / "s.npy")
+    assert c3.columns(rv_unit=u.km / u.s)[4] == pytest.approx(0.125)
+    with pytest.raises(OSError):
+        convert_reference_hdf5("prior.hdf5", str(tmp_path / "c1"))
+    # the reference's read_batch family over the converted cache (utils.py:106-245)
+    from thejoker_b200.cache import read_batch
+
+    b = read_batch(out, ["P", "e", "s"], (10, 20), units={"s": u.m / u.s})
+    assert np.array_equal(b[:, 0], rows["P"][10:20]) and np.allclose(b[:, 2], rows["s"][10:20])
+
+
+def test_reference_hdf5_reader_needs_h5py(monkeypatch):
+    from thejoker_b200.cache import read_reference_hdf5
+
+    monkeypatch.setitem(sys.modules, "h5py", None)  # import h5py -> ImportError
+    with pytest.raises(ImportError, match="h5py"):
+        read_reference_hdf5("nope.hdf5")
 
 
 def test_poly_trend_zero_is_rejected_like_the_reference():

@@ -12,8 +12,10 @@ Native format here: a directory with one little-endian float64 ``.npy`` file per
 ``[lo, hi)`` is read straight from the page cache / disk into the device upload without
 touching the rest of the file, and a constant jitter column is stored as a scalar.
 
-``read_reference_hdf5`` reads the reference's own HDF5 layout when ``h5py`` is
-importable (it is not in the build image, so that function is import-gated).
+``read_reference_hdf5`` / ``convert_reference_hdf5`` read the reference's own HDF5 layout
+through ``h5py`` (the reference's own dependency; it is not in the build image, so the
+tests drive these functions through a stand-in module with h5py's dataset interface and
+headers in astropy's serialisation format); the conversion is blockwise.
 """
 from __future__ import annotations
 
@@ -25,7 +27,8 @@ import numpy as np
 from . import units as u
 from .samples import JokerSamples
 
-__all__ = ["write_prior_cache", "PriorCache", "read_reference_hdf5", "read_batch",
+__all__ = ["write_prior_cache", "PriorCache", "read_reference_hdf5", "convert_reference_hdf5",
+           "parse_table_column_meta", "read_batch",
            "read_batch_slice", "read_batch_idx", "read_random_batch"]
 
 _COLS = ("P", "e", "omega", "M0", "s")
@@ -179,33 +182,149 @@ def read_batch(prior_samples_file, columns, slice_or_idx, units=None, rng=None):
     raise ValueError("Invalid input for slice_or_idx: must be a slice, int, or numpy array.")
 
 
-def read_reference_hdf5(filename):
-    """JokerSamples from a file written by the reference's ``JokerSamples.write``
-    (HDF5 dataset ``samples``; column units in the YAML header stored next to it,
-    thejoker/samples.py:480-545, utils.py:75-103).  Needs h5py."""
+# -- the reference's HDF5 prior cache ------------------------------------------------------
+def parse_table_column_meta(lines):
+    """The YAML header astropy stores next to a serialised table -- dataset
+    ``samples.__table_column_meta__`` of the reference's prior cache (written by
+    ``write_table_hdf5(..., serialize_meta=True)``, thejoker/samples.py:535-545; read back
+    by ``get_header_from_yaml`` in thejoker/utils.py:75-88 and samples.py:548-563), one
+    line per array element -- as ``(units, columns, meta)``: column name -> unit string
+    ('' = dimensionless), the column order, and the table's own meta (``poly_trend``,
+    ``n_offsets``, ``t_ref`` ...).
+
+    The header carries a column's unit twice when the table held Quantity columns: in its
+    ``datatype`` entry and in ``meta.__serialized_columns__.<name>.unit`` (an
+    ``!astropy.units.Unit`` node); the first wins, the second is the fallback.  astropy's
+    custom tags are read as plain mappings, so astropy itself is not needed."""
+    import yaml
+
+    class _Loader(yaml.SafeLoader):
+        pass
+
+    def _plain(loader, suffix, node):
+        if isinstance(node, yaml.MappingNode):
+            return loader.construct_mapping(node, deep=True)
+        if isinstance(node, yaml.SequenceNode):
+            return loader.construct_sequence(node, deep=True)
+        return loader.construct_scalar(node)
+
+    _Loader.add_multi_constructor("!", _plain)
+    text = "\n".join(ln.decode("utf-8") if isinstance(ln, bytes) else str(ln) for ln in lines)
+    header = yaml.load(text, Loader=_Loader)
+    if not isinstance(header, dict) or "datatype" not in header:
+        raise ValueError("not an astropy table header: no 'datatype' list")
+    meta = header.get("meta") or {}
+    if isinstance(meta, list):  # !!omap -> list of (key, value) pairs
+        meta = {k: v for k, v in meta}
+    serialized = meta.pop("__serialized_columns__", None) or {}
+    units, columns = {}, []
+    for row in header["datatype"]:
+        name = row["name"]
+        columns.append(name)
+        unit = row.get("unit")
+        if unit is None:
+            ser = serialized.get(name) or {}
+            unit = ser.get("unit")
+            if isinstance(unit, dict):
+                unit = unit.get("unit")
+        units[name] = "" if unit is None else str(unit)
+    return units, columns, meta
+
+
+def _meta_kwargs(meta):
+    """poly_trend / n_offsets / t_ref of the stored table, as JokerSamples takes them
+    (samples.py:68-73).  A serialised astropy Time comes back as its jd1 + jd2 pair."""
+    kw = {}
+    for k in ("poly_trend", "n_offsets"):
+        if meta.get(k) is not None:
+            kw[k] = int(meta[k])
+    t_ref = meta.get("t_ref")
+    if isinstance(t_ref, dict) and "jd1" in t_ref:
+        t_ref = (float(t_ref["jd1"]) - 2400000.5) + float(t_ref.get("jd2", 0.0))  # -> MJD
+    if isinstance(t_ref, (int, float)):
+        kw["t_ref"] = float(t_ref)
+    return kw
+
+
+def _open_reference_hdf5(filename):
     try:
         import h5py
-    except ImportError as e:  # pragma: no cover - h5py is absent from the build image
+    except ImportError as e:
         raise ImportError("reading the reference's HDF5 prior cache needs h5py; convert it "
-                          "once with thejoker_b200.cache.write_prior_cache on a machine that "
-                          "has it") from e
-    import re
+                          "once with thejoker_b200.cache.convert_reference_hdf5 on a machine "
+                          "that has it") from e
+    return h5py.File(filename, "r")
 
-    with h5py.File(filename, "r") as f:  # pragma: no cover
-        data = f[JokerSamples._hdf5_path][()]
-        header = "\n".join(h.decode("utf-8") for h in
-                           f[JokerSamples._hdf5_path + ".__table_column_meta__"][()])
-    units, name = {}, None  # pragma: no cover
-    for line in header.splitlines():  # pragma: no cover
-        m = re.match(r"\s*-?\s*\{?\s*name:\s*([\w]+)", line)
-        if m:
-            name = m.group(1)
-        m = re.search(r"unit:\s*([^,}\n]+)", line)
-        if m and name:
-            units[name] = m.group(1).strip()
-    out = JokerSamples()  # pragma: no cover
-    for col in data.dtype.names:  # pragma: no cover
-        if col in out._valid_units:
-            unit = u.as_unit(units.get(col, ""))
-            out[col] = u.Quantity(np.asarray(data[col], dtype=np.float64), unit)
-    return out  # pragma: no cover
+
+def read_reference_hdf5(filename, lo=0, hi=None):
+    """JokerSamples from rows [lo, hi) of a file written by the reference's
+    ``JokerSamples.write`` (HDF5 dataset ``samples`` of compound rows; column units in the
+    YAML header stored next to it, thejoker/samples.py:480-563, utils.py:75-103).  Needs
+    h5py (not PyTables: the reference's workers read the same dataset with ``tables``,
+    utils.py:168-198)."""
+    with _open_reference_hdf5(filename) as f:
+        dset = f[JokerSamples._hdf5_path]
+        units, columns, meta = parse_table_column_meta(
+            f[JokerSamples._hdf5_path + ".__table_column_meta__"][()])
+        hi = len(dset) if hi is None else hi
+        data = dset[lo:hi]
+    out = JokerSamples(**_meta_kwargs(meta))
+    for col in data.dtype.names:
+        if col in out._valid_units or col in ("ln_prior", "ln_likelihood"):
+            out[col] = u.Quantity(np.ascontiguousarray(data[col], dtype=np.float64),
+                                  u.as_unit(units.get(col, "")))
+    return out
+
+
+def convert_reference_hdf5(filename, path, rv_unit=None, overwrite=False, rows_per_block=1 << 22):
+    """Convert the reference's HDF5 prior cache into a native SoA cache directory, block by
+    block: the compound (AoS) rows are read ``rows_per_block`` at a time and scattered into
+    memory-mapped per-column files in internal units, so a 2^28-row cache (10.7 GB of rows)
+    needs ~170 MB of host memory at a time, not the whole table twice.  Returns ``path``."""
+    from numpy.lib.format import open_memmap
+
+    rv_unit = u.as_unit(u.km / u.s if rv_unit is None else rv_unit)
+    if os.path.exists(path) and not overwrite:
+        raise OSError(f"{path} exists: use overwrite=True")
+    os.makedirs(path, exist_ok=True)
+    with _open_reference_hdf5(filename) as f:
+        dset = f[JokerSamples._hdf5_path]
+        units, columns, tmeta = parse_table_column_meta(
+            f[JokerSamples._hdf5_path + ".__table_column_meta__"][()])
+        n = len(dset)
+        missing = [c for c in _COLS[:4] if c not in columns]
+        if missing:
+            raise ValueError(f"{filename}: prior cache lacks the columns {missing}")
+        names = [c for c in _COLS + ("ln_prior",) if c in columns]
+        factor = {c: (1.0 if c == "ln_prior" else
+                      float(u.as_unit(units.get(c, "")).to(_INTERNAL.get(c, rv_unit))))
+                  for c in names}
+        mm = {c: open_memmap(os.path.join(path, f"{c}.npy"), mode="w+", dtype="<f8", shape=(n,))
+              for c in names}
+        s_first, s_uniform = None, "s" in names
+        for lo in range(0, n, rows_per_block):
+            block = dset[lo:lo + rows_per_block]
+            for c in names:
+                col = np.asarray(block[c], dtype=np.float64)
+                if factor[c] != 1.0:
+                    col = col * factor[c]
+                mm[c][lo:lo + len(col)] = col
+                if c == "s" and s_uniform and len(col):
+                    s_first = col[0] if s_first is None else s_first
+                    s_uniform = bool(np.all(col == s_first))
+        for m in mm.values():
+            m.flush()
+        del mm
+    kw = _meta_kwargs(tmeta)
+    meta = {"n": n, "rv_unit_scale": rv_unit.scale, "rv_unit_dims": list(rv_unit.dims),
+            "poly_trend": kw.get("poly_trend", 1), "n_offsets": kw.get("n_offsets", 0),
+            "columns": list(names), "s_const": None}
+    if "s" not in names:
+        meta["s_const"] = 0.0
+    elif s_uniform and n:  # a constant jitter column is stored as a scalar, like write_prior_cache
+        meta["s_const"] = float(s_first)
+        meta["columns"].remove("s")
+        os.remove(os.path.join(path, "s.npy"))
+    with open(os.path.join(path, "meta.json"), "w") as f:
+        json.dump(meta, f)
+    return path
