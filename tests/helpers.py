@@ -31,7 +31,7 @@ def default_prior(poly_trend=1, sigma_K0=30.0, P_min=2.0, P_max=1024.0, v0_offse
 
 
 def star_spec(n_times=16, poly_trend=1, seed=42, K=None, sigma=0.5, jitter_mode="apply",
-              normal_K=None, n_surveys=1, v1=None):
+              normal_K=None, n_surveys=1, v1=None, t_span_periods=3.0):
     """(spec dict, data, prior) for a synthetic star."""
     pars = None
     if normal_K is not None:
@@ -40,10 +40,12 @@ def star_spec(n_times=16, poly_trend=1, seed=42, K=None, sigma=0.5, jitter_mode=
     prior = default_prior(poly_trend, sigma_K0=None if normal_K is not None else 30.0,
                           v0_offsets=offsets or None, pars=pars)
     if n_surveys == 1:
-        data, _ = make_noisy_data(n_times, seed=seed, K=K, sigma=sigma, v1=v1)
+        data, _ = make_noisy_data(n_times, seed=seed, K=K, sigma=sigma, v1=v1,
+                                  t_span_periods=t_span_periods)
     else:
         rng = np.random.default_rng(seed)
-        full, _ = make_noisy_data(n_times, seed=seed, K=K, sigma=sigma, v1=v1)
+        full, _ = make_noisy_data(n_times, seed=seed, K=K, sigma=sigma, v1=v1,
+                                  t_span_periods=t_span_periods)
         cuts = np.sort(rng.choice(np.arange(2, n_times - 1), size=n_surveys - 1, replace=False))
         data, lo = [], 0
         for k, hi in enumerate(list(cuts) + [n_times]):
@@ -62,21 +64,24 @@ def prior_chunk(n, seed=123, s_lognormal=None, s_const=None):
     return np.ascontiguousarray(np.stack(cols, axis=1))
 
 
-_emu = None
+_emu = {}
 
 
-def host_emulation():
-    """CPU build of the device math (tools/host_emulation.cpp); debug tooling only."""
-    global _emu
-    if _emu is None:
-        so = os.path.join(ROOT, "tools", "libhost_emulation.so")
+def host_emulation(variant=""):
+    """CPU build of the device math (tools/host_emulation.cpp); debug tooling only.
+    `variant` is a compile-time flag set of the kernel headers ("" = the shipped
+    configuration, "TJB_TRIM=1" = the instruction-trimmed epoch loop, ...)."""
+    if variant not in _emu:
+        tag = "".join(ch if ch.isalnum() else "_" for ch in variant)
+        so = os.path.join(ROOT, "tools", f"libhost_emulation{'_' + tag if tag else ''}.so")
+        defs = ["-D" + d for d in variant.split()] if variant else []
         src = os.path.join(ROOT, "tools", "host_emulation.cpp")
         deps = [src] + [os.path.join(ROOT, "thejoker_b200", "csrc", f) for f in
                         ("kepler.cuh", "linalg.cuh", "marginal_ll.cuh", "star_tables.hpp",
                          "accept.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared",
-                            "-ffp-contract=off", src, "-o", so], check=True)
+                            "-ffp-contract=off"] + defs + [src, "-o", so], check=True)
         lib = ctypes.CDLL(so)
         dp = ctypes.POINTER(ctypes.c_double)
         lib.emu_design_column.argtypes = [ctypes.c_double] * 4 + [dp, ctypes.c_int, dp,
@@ -92,12 +97,12 @@ def host_emulation():
         lib.emu_pcg64_double.restype = ctypes.c_double
         lib.emu_pcg64_double.argtypes = [ctypes.c_ulonglong] * 5
         lib.emu_sincos_rev.argtypes = [ctypes.c_double, dp, dp]
-        _emu = lib
-    return _emu
+        _emu[variant] = lib
+    return _emu[variant]
 
 
-def emu_marginal_ll(spec, chunk, force_jit=False):
-    lib = host_emulation()
+def emu_marginal_ll(spec, chunk, force_jit=False, variant=""):
+    lib = host_emulation(variant)
     dp = ctypes.POINTER(ctypes.c_double)
     p = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(dp)
     chunk = np.ascontiguousarray(chunk, dtype=np.float64)

@@ -361,6 +361,76 @@ def test_host_emulated_ll_matches_oracle(N, pt, sl, kw):
         assert np.max(r_truth) < 1e-10
 
 
+VARIANTS = ["TJB_TRIM=1", "TJB_PHASE_FIXED=1", "TJB_TRIM=1 TJB_PHASE_FIXED=1",
+            "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_TRIG_TABLE=0"]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_host_emulated_tuning_variants(variant):
+    """Compile-time variants of the epoch loop that are built for timing on the GPU
+    (tools/build_variants.sh) must keep the shipped configuration's numerics: same Kepler
+    column to a few ulp (also on the high-eccentricity rare path) and the same ll gate."""
+    from oracle.oracle import OracleHelper
+
+    base, var = host_emulation(), host_emulation(variant)
+    spec, _, _ = star_spec(64, 1)
+    chunk = prior_chunk(3000)
+    chunk[:300, 1] = np.random.default_rng(1).uniform(0.8, 0.999, 300)  # exercises extra passes
+    dt = np.ascontiguousarray(spec["t"] - spec["t0"])
+    dp = ctypes.POINTER(ctypes.c_double)
+    za, zb = np.zeros(64), np.zeros(64)
+    sa, sb = (ctypes.c_int * 3)(), (ctypes.c_int * 3)()
+    worst, worst_orc, extra = 0.0, 0.0, 0
+    orc = OracleHelper.from_spec(spec)
+    for row in chunk:
+        base.emu_design_column(*row[:4], dt.ctypes.data_as(dp), 64, za.ctypes.data_as(dp), sa)
+        var.emu_design_column(*row[:4], dt.ctypes.data_as(dp), 64, zb.ctypes.data_as(dp), sb)
+        assert sb[2] == 0
+        extra += sb[1]
+        worst = max(worst, np.max(np.abs(za - zb)) * (1.0 - row[1]) ** 2)
+        worst_orc = max(worst_orc, np.max(np.abs(zb - orc.design_column(row))) * (1.0 - row[1]) ** 2)
+    assert extra > 0          # the rare path ran
+    # both round the phase x4 + d4 (|x4| ~ 1e5 angle units: ulp ~ 9e-14 rad) differently
+    assert worst < 2e-13
+    assert worst_orc < 2e-12  # the gate of test_kepler_column_matches_oracle
+    for N, pt, sl in ((64, 1, None), (20, 2, (-2.0, 1.0))):
+        spec, _, _ = star_spec(N, pt)
+        chunk = prior_chunk(1500, s_lognormal=sl)
+        orc = OracleHelper.from_spec(spec)
+        truth, _ = orc.truth_ll(chunk)
+        got = emu_marginal_ll(spec, chunk, force_jit=sl is not None, variant=variant)
+        ref = emu_marginal_ll(spec, chunk, force_jit=sl is not None)
+        assert np.max(rel_err(got, ref)) < 1e-12
+        assert np.max(rel_err(got, truth)) < 1e-10
+
+
+def test_phase_reduction_variants():
+    """How often the one-pass FP64 step is not enough, against the time baseline of the data
+    (default prior, P >= 2 d): the shipped FP32 stage rounds the unreduced phase to float, so
+    its starter degrades with the number of revolutions; the fixed-point reduction
+    (TJB_PHASE_FIXED) does not.  Extra passes are the same code on the GPU, where one lane
+    that needs them sends its whole warp through the rare path."""
+    libs = {"": host_emulation(), "fixed": host_emulation("TJB_TRIM=1 TJB_PHASE_FIXED=1")}
+    chunk = prior_chunk(2048)
+    dp = ctypes.POINTER(ctypes.c_double)
+    z, st = np.zeros(64), (ctypes.c_int * 3)()
+    warp_rate = {}
+    for span in (155.0, 4000.0):
+        dt = np.sort(np.random.default_rng(0).uniform(0, span, 64))
+        for name, lib in libs.items():
+            extra = []
+            for row in chunk:
+                lib.emu_design_column(*row[:4], dt.ctypes.data_as(dp), 64, z.ctypes.data_as(dp), st)
+                assert st[2] == 0
+                extra.append(st[1])
+            # share of (warp, epoch) pairs in which some lane needs another pass, if the
+            # lanes' epochs were independent: an upper bound of the rare-path rate
+            warp_rate[name, span] = np.reshape(extra, (-1, 32)).sum(axis=1).mean() / 64
+    assert warp_rate["", 155.0] < 0.01 and warp_rate["fixed", 155.0] < 0.01
+    assert warp_rate["", 4000.0] > 3 * warp_rate["fixed", 4000.0]
+    assert warp_rate["fixed", 4000.0] < 1.5 * warp_rate["fixed", 155.0] + 1e-3
+
+
 def test_host_emulated_uniform_jitter_paths_agree():
     spec, _, _ = star_spec(32, 2)
     chunk = prior_chunk(500, s_const=0.37)

@@ -51,6 +51,33 @@ namespace tjb {
 #define TJB_TRIG_TABLE 1
 #endif
 
+// Instruction-trimmed variant of the epoch loop (default off until it has been timed on the
+// GPU; tools/build_variants.sh builds it, tests/test_host_logic.py checks its numerics):
+//   * e cosE / (6 f1) = (1/f1 - 1)/6: one FMA instead of two multiplies, FP64 and FP32 stage
+//   * FP32 stage: t/2 computed once
+//   * convergence vote on one max of the sign-stripped high words (per-epoch flags are
+//     recomputed on the rare path only)
+//   * 0.5 pinned in a register pair (ptxas otherwise materialises it per iteration)
+// Saves ~1 FP64 and ~4.5 other instructions per (sample, epoch).
+#ifndef TJB_TRIM
+#define TJB_TRIM 0
+#endif
+
+// Phase reduction of the FP32 stage in fixed point (default off until timed on the GPU).
+// The shipped loop rounds the unreduced phase x4 to float first, so its starter carries an
+// error of ulp_float(x4)/2 -- 3.8e-4 rad at 2000 revolutions (P = 2 d over a 4000 d
+// baseline), above the 2^-13 threshold of the one-pass FP64 step: such lanes send their
+// warp through the extra-pass path (64 % of the warps at least once over 64 epochs on a
+// 4000 d baseline, 5 % on the 155 d benchmark data; tests/test_host_logic.py::
+// test_phase_reduction_variants).  With TJB_PHASE_FIXED one FP64 add of 1.5 * 2^(20+U)
+// (2^U angle units per revolution) leaves x4 in 2^-(32-U) units in the low mantissa word;
+// read as a signed integer that word *is* x4 modulo one revolution, good to 1e-9 rad for
+// |x4| < 2^(19+U) units (2^19 revolutions).  Replaces F2F.F32.F64 + three FP32
+// instructions by DADD + I2F.
+#ifndef TJB_PHASE_FIXED
+#define TJB_PHASE_FIXED 0
+#endif
+
 // 1.5 * 2^52 (1.5 * 2^23): adding it rounds to the nearest integer and leaves
 // that integer in the low mantissa bits.
 constexpr double kMagic = 6755399441055744.0;
@@ -66,6 +93,9 @@ constexpr double kUnitsPerRev = (double)kTrigTableSize;
 constexpr int kTrigTableSize = 0;
 constexpr double kUnitsPerRev = 4.0;
 #endif
+// fixed-point phase (TJB_PHASE_FIXED): fraction bits that fit one revolution in 32 bits
+constexpr double kFixOne = 4294967296.0 / kUnitsPerRev;          // 2^(32-U)
+constexpr double kMagicFix = 6755399441055744.0 / kFixOne;       // 1.5 * 2^(52-(32-U))
 constexpr double kRadPerUnit = kTwoPi / kUnitsPerRev;
 constexpr double kUnitsPerRad = kUnitsPerRev / kTwoPi;
 
@@ -107,8 +137,9 @@ TJB_COEF double kCosC[8] = {1.0,
                             0.0000004710641505803501879438872,
                             -6.324746678866069891109223e-9};
 #endif
-// 1/6, angle units per radian, radians per angle unit
-TJB_COEF double kMisc[3] = {1.0 / 6.0, kUnitsPerRad, kRadPerUnit};
+// 1/6, angle units per radian, radians per angle unit, 1/2 (TJB_TRIM only)
+constexpr int kNMisc = TJB_TRIM ? 4 : 3;
+TJB_COEF double kMisc[4] = {1.0 / 6.0, kUnitsPerRad, kRadPerUnit, 0.5};
 
 // ---- bit helpers / pipe-specific primitives -------------------------------
 #if defined(__CUDA_ARCH__)
@@ -158,7 +189,7 @@ inline double rcp_pos(double x) { return 1.0 / x; }
 // re-loads (LDC) or re-materialises (MOV) each of them on every epoch, which costs issue
 // slots; measured: pinned 2.75e9 samples/s, LDC per use 2.61e9, literals 2.57e9.
 struct TrigCoef {
-  double s[kNSin], c[kNCos], m[3];
+  double s[kNSin], c[kNCos], m[kNMisc];
   const SinCos *table;  // kTrigTableSize nodes, sin/cos(2 pi j / size); null without a table
   // `zero` must be a run-time 0.0 (a kernel parameter): coefficient + zero is an
   // FP64 result ptxas will not rematerialise, so the values stay in registers.
@@ -169,7 +200,7 @@ struct TrigCoef {
 #pragma unroll
     for (int i = 0; i < kNCos; i++) c[i] = kCosC[i] + zero;
 #pragma unroll
-    for (int i = 0; i < 3; i++) m[i] = kMisc[i] + zero;
+    for (int i = 0; i < kNMisc; i++) m[i] = kMisc[i] + zero;
   }
 };
 
@@ -275,12 +306,19 @@ TJB_HD void count_event(unsigned long long *gstats, int which) {
 // One third-order Householder step from (D, sE, cE): returns delta.
 //   f = D - e sinE, f1 = 1 - e cosE, f2 = e sinE, f3 = e cosE
 //   u = -f/f1, t = f2/f1, b6 = f3/(6 f1), delta = u (1 + u (-t/2 + u (t^2/2 - b6)))
-TJB_HD double householder3(const OrbitConsts &oc, double D, double sE, double cE) {
+TJB_HD double householder3(const OrbitConsts &oc, const TrigCoef &tc, double D, double sE,
+                           double cE) {
   const double es = oc.e * sE;
   const double r = rcp_pos(fma(-oc.e, cE, 1.0));
   const double t = es * r;
   const double u = fma(-D, r, t);
+#if TJB_TRIM
+  // e cosE / f1 = (1 - f1)/f1 = r - 1; the 2e-16 r absolute error enters delta times u^3
+  const double b6 = fma(r, TJB_MC(0), -TJB_MC(0));
+#else
+  (void)tc;
   const double b6 = (oc.e6 * cE) * r;
+#endif
   const double th = 0.5 * t;
   const double q = fma(th, t, -b6);
   return u * fma(u, fma(u, q, -th), 1.0);
@@ -291,7 +329,11 @@ TJB_HD double householder3(const OrbitConsts &oc, double D, double sE, double cE
 TJB_HD void rotate_small(const TrigCoef &tc, double del, double &sE, double &cE) {
   const double d2 = del * del;
   const double sd = del * fma(d2, -TJB_MC(0), 1.0);
+#if TJB_TRIM
+  const double cd = fma(d2, -TJB_MC(3), 1.0);
+#else
   const double cd = fma(d2, -0.5, 1.0);
+#endif
   const double sN = fma(cE, sd, sE * cd);
   cE = fma(-sE, sd, cE * cd);
   sE = sN;
@@ -314,9 +356,18 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
 #pragma unroll
   for (int k = 0; k < K; k++) {
     x4[k] = fma(dt[k], oc.nu, -oc.ph);
+#if TJB_PHASE_FIXED
+    const float Mf = (float)lo32(x4[k] + kMagicFix) * (float)(kRadPerUnit / kFixOne);  // [-pi, pi)
+#elif TJB_TRIM
+    const float x4f = (float)x4[k];
+    // adding 1.5 * 2^23 * (units per revolution) rounds to whole revolutions, in angle units
+    const float rev = (x4f + kMagicF * (float)kUnitsPerRev) - kMagicF * (float)kUnitsPerRev;
+    const float Mf = (x4f - rev) * (float)kRadPerUnit;  // M in [-pi, pi]
+#else
     const float x4f = (float)x4[k];
     const float r4 = (x4f * (float)(1.0 / kUnitsPerRev) + kMagicF) - kMagicF;  // whole revolutions
     const float Mf = fmaf(r4, -(float)kUnitsPerRev, x4f) * (float)kRadPerUnit;  // M in [-pi, pi]
+#endif
     const float sM = fsin_approx(Mf), cM = fcos_approx(Mf);
     const float D0 = ef * sM * frsqrt_approx(fmaf(-2.0f * ef, cM, oc.g0f));
     const float Ef = Mf + D0;
@@ -324,27 +375,51 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
     const float r = frcp_approx(1.0f - ec);
     const float t = es * r;           // f2/f1
     const float u = fmaf(-D0, r, t);  // -f/f1
+#if TJB_TRIM
+    const float th = 0.5f * t;
+    const float q = fmaf(th, t, fmaf(r, -1.0f / 6.0f, 1.0f / 6.0f));  // -ec r/6 = (1 - r)/6
+    const float del = u * fmaf(u, fmaf(u, q, -th), 1.0f);
+    Df[k] = D0 + del;  // not clamped here: a wild or NaN estimate is caught by the FP64 test
+#else
     const float q = fmaf(0.5f * t, t, ec * r * (-1.0f / 6.0f));
     const float del = u * fmaf(u, fmaf(u, q, -0.5f * t), 1.0f);
     Df[k] = fminf(fmaxf(D0 + del, -ef), ef);  // |E - M| <= e holds for the root
+#endif
   }
 
   // ---- FP64: exact reduction of E0 = M + D0, one full sincos, one Householder step
   double del[K];
   bool need[K];
   bool any_need = false;
+#if TJB_TRIM
+  unsigned top = 0;  // max over the epochs of the high word without its sign bit
+#endif
 #pragma unroll
   for (int k = 0; k < K; k++) {
+#if TJB_TRIM
+    D[k] = (double)Df[k];                // E0 - M [rad]
+    const double d4 = D[k] * TJB_MC(1);  // in angle units (1-ulp rounding: < 2e-16 rad)
+    sincos_units(tc, x4[k] + d4, sE[k], cE[k]);
+#else
     const double d4 = (double)(Df[k] * (float)kUnitsPerRad);  // D0 in angle units
     sincos_units(tc, x4[k] + d4, sE[k], cE[k]);
     D[k] = d4 * TJB_MC(2);  // E0 - M [rad]
-    del[k] = householder3(oc, D[k], sE[k], cE[k]);
+#endif
+    del[k] = householder3(oc, tc, D[k], sE[k], cE[k]);
     // error map of the step: eps -> ~C eps^4 (tools/kepler_solver_study.py); a lane
     // that moved by 2^-13 (1.2e-4) or more, or produced a NaN, takes further passes.
     // The test reads the exponent field on the integer pipe instead of a DSETP.
+#if TJB_TRIM
+    const unsigned hk = (unsigned)hi32(del[k]) << 1;
+    top = hk > top ? hk : top;
+#else
     need[k] = (unsigned)(hi32(del[k]) & 0x7fffffff) >= 0x3f200000u;
     any_need = any_need || need[k];
+#endif
   }
+#if TJB_TRIM
+  any_need = top >= (0x3f200000u << 1);
+#endif
   if (!any_lane(any_need)) {
     // the normal case: every lane of the warp converged in one pass
 #pragma unroll
@@ -357,12 +432,20 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
     for (int k = 0; k < K; k++) {
       double sR = sE[k], cR = cE[k];
       rotate_small(tc, del[k], sR, cR);
+#if TJB_TRIM
+      need[k] = ((unsigned)hi32(del[k]) << 1) >= (0x3f200000u << 1);
+#endif
       bool nd = need[k];
       double Dk = D[k] + del[k];
+#if TJB_TRIM
+      // the FP32 estimate is not clamped on the main path: |E - M| <= e holds for the
+      // root, and fmin / fmax also replace a NaN estimate
+      if (nd) Dk = fmin(fmax(Dk, -oc.e), oc.e);
+#endif
       for (int it = 1; it < kF64MaxIter && any_lane(nd); ++it) {
         double s2, c2;
         sincos_units(tc, fma(Dk, TJB_MC(1), x4[k]), s2, c2);
-        const double d2 = householder3(oc, Dk, s2, c2);
+        const double d2 = householder3(oc, tc, Dk, s2, c2);
         if (nd) {
           if (kCountStats) st->extra_f64++;
           count_event(gstats, 0);

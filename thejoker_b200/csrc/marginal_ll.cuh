@@ -41,6 +41,18 @@ TJB_HD constexpr int row_stride(int L) { return (L + 2 + 1) & ~1; }
 #endif
 constexpr int kEpochsPerIter = TJB_EPOCHS_PER_ITER;
 
+// header of the loop over groups of kEpochsPerIter epochs; leaves n at the first epoch of
+// the remainder.  The TJB_TRIM form counts groups down (one add + compare against zero per
+// iteration instead of re-loading N and comparing n + kEpochsPerIter against it).
+#if TJB_TRIM
+#define TJB_EPOCH_GROUPS(n, N, row, RS)                                                  \
+  n = (N / kEpochsPerIter) * kEpochsPerIter;                                            \
+  for (int grp_ = N / kEpochsPerIter; grp_ > 0; --grp_, row += kEpochsPerIter * RS)
+#else
+#define TJB_EPOCH_GROUPS(n, N, row, RS) \
+  for (; n + kEpochsPerIter <= N; n += kEpochsPerIter, row += kEpochsPerIter * RS)
+#endif
+
 struct StarParams {
   int n_times;
   const double *table;              // device, [N, row_stride(L)]
@@ -134,7 +146,7 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab,
     const double *row = tab;
     int n = 0;
     // kEpochsPerIter epochs per iteration: independent Kepler chains for ILP
-    for (; n + kEpochsPerIter <= N; n += kEpochsPerIter, row += kEpochsPerIter * RS) {
+    TJB_EPOCH_GROUPS(n, N, row, RS) {
       double dt[kEpochsPerIter], z[kEpochsPerIter];
 #pragma unroll
       for (int j = 0; j < kEpochsPerIter; j++) dt[j] = row[j * RS];
@@ -197,7 +209,7 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab,
         for (int j = i; j < L; j++) G[tri<L>(i, j)] = fma(wm, m[j], G[tri<L>(i, j)]);
       }
     };
-    for (; n + kEpochsPerIter <= N; n += kEpochsPerIter, row += kEpochsPerIter * RS) {
+    TJB_EPOCH_GROUPS(n, N, row, RS) {
       double dt[kEpochsPerIter], z[kEpochsPerIter];
 #pragma unroll
       for (int j = 0; j < kEpochsPerIter; j++) dt[j] = row[j * RS];

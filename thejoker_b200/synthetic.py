@@ -49,10 +49,11 @@ def make_data(n_times=8, rng=None, v1=None, K=None, sigma=0.5, t_span_periods=3.
     return RVData(t, rv * u.km / u.s, rv_err=err * u.km / u.s), truth
 
 
-def make_noisy_data(n_times=64, seed=42, K=None, sigma=0.5, v1=None):
+def make_noisy_data(n_times=64, seed=42, K=None, sigma=0.5, v1=None, t_span_periods=3.0):
     """BASELINE.md section 5 data: the fixture above plus Gaussian noise of sigma."""
     rng = np.random.default_rng(seed)
-    data, truth = make_data(n_times, rng=rng, K=K, sigma=sigma, v1=v1)
+    data, truth = make_data(n_times, rng=rng, K=K, sigma=sigma, v1=v1,
+                            t_span_periods=t_span_periods)
     noisy = data.rv.value + rng.normal(0, sigma, size=len(data))
     return RVData(data._t_bmjd, noisy * u.km / u.s, rv_err=data.rv_err), truth
 

@@ -6,10 +6,10 @@ so=$1; pat=$2
 cuobjdump -sass "$so" | awk -v pat="$pat" '/Function : /{f=index($0,pat)>0} f' > /tmp/_k.sass
 python3 - << 'PY'
 import re
-lines=[l for l in open('/tmp/_k.sass') if re.match(r'\s+/\*[0-9a-f]{4}\*/',l)]
+lines=[l for l in open('/tmp/_k.sass') if re.match(r'\s+/\*[0-9a-f]{4,6}\*/',l)]
 ins=[]
 for l in lines:
-    m=re.match(r'\s+/\*([0-9a-f]{4})\*/\s+(.*?);',l)
+    m=re.match(r'\s+/\*([0-9a-f]{4,6})\*/\s+(.*?);',l)
     if m: ins.append((int(m.group(1),16),m.group(2).strip()))
 # find backward branches
 best=None

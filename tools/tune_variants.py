@@ -27,8 +27,12 @@ om = (torch.rand(n, dtype=torch.float64, device="cuda", generator=g) * 2 - 1) * 
 M0 = (torch.rand(n, dtype=torch.float64, device="cuda", generator=g) * 2 - 1) * np.pi
 s = torch.exp(torch.randn(n, dtype=torch.float64, device="cuda", generator=g) - 2)
 ll = torch.empty(n, dtype=torch.float64, device="cuda")
-for N, pt, jit in ((64, 1, False), (64, 2, True), (256, 1, False), (16, 1, False)):
-    spec, data, prior = star_spec(N, pt)
+# span: time baseline in units of the 51.8 d fixture period (3 = the benchmark data, 155 d;
+# 77 = 4000 d, where the float phase reduction of the shipped loop starts to send warps
+# through the extra-pass path: tests/test_host_logic.py::test_phase_reduction_variants)
+for N, pt, jit, span in ((64, 1, False, 3.0), (64, 2, True, 3.0), (256, 1, False, 3.0),
+                         (16, 1, False, 3.0), (64, 1, False, 77.0), (64, 1, False, 193.0)):
+    spec, data, prior = star_spec(N, pt, t_span_periods=span)
     all_data, ids, trend_M = validate_prepare_data(data, prior.poly_trend, prior.n_offsets)
     h = tj.CJokerHelper(all_data, prior, trend_M, device=0)
     m = n if N <= 64 else n // 4
@@ -42,9 +46,11 @@ for N, pt, jit in ((64, 1, False), (64, 2, True), (256, 1, False), (16, 1, False
         h.marginal_ll_soa(*args, s=s[:m] if jit else None, out=ll[:m])
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
-    out[f"N{N}_L{1+pt}_{'jit' if jit else 'const'}"] = round(m / ms * 1e3 / 1e9, 4)
+    tag = f"N{N}_L{1+pt}_{'jit' if jit else 'const'}" + ("" if span == 3.0 else f"_span{int(span * 51.8239)}d")
+    out[tag] = round(m / ms * 1e3 / 1e9, 4)
     out["ctas_per_sm"] = h.device_info()["ctas_per_sm"]
-    out[f"chk{N}{jit}"] = float(ll[:1000].sum().item())
+    out["chk_" + tag] = float(ll[:1000].sum().item())
+    out["extra_passes_" + tag] = h.solver_stats(reset=True)["extra_fp64_passes"] // 7  # per launch
 print(json.dumps(out))
 ''' % (ROOT, ROOT)
 
