@@ -442,6 +442,35 @@ def test_design_column_and_solver_tail(torch_cuda, oracle_lib):
     print(f"\nextra FP64 Householder passes over {len(chunk) * 64} epochs: {extra}")
 
 
+def test_extreme_eccentricity_and_phase_stay_finite(torch_cuda):
+    """e -> 1 (down to 1 - 1e-7) with mean anomalies down to 1e-9 rad, and phases beyond the
+    FP32 stage's range (P = 0.05 d over a 10 000 d baseline): the safeguarded extra passes
+    (kepler.cuh::solve_extra_passes) converge for every epoch and every ll is finite -- a
+    single NaN would poison the max of the prior cache and nothing would be accepted.  The
+    same sweep runs on the host build of the device code in
+    tests/test_host_logic.py::test_kepler_solver_extreme_cases (there also against mpmath)."""
+    rng = np.random.default_rng(3)
+    for span_periods, P_min in ((3.0, 2.0), (193.0, 0.05)):
+        helper, spec, _, _ = make_helper((64, 1), t_span_periods=span_periods)
+        n = 600
+        chunk = prior_chunk(n)
+        chunk[:, 0] = np.exp(rng.uniform(np.log(P_min), np.log(1000), n))
+        chunk[:, 1] = 1 - 10 ** rng.uniform(-7, -1, n)
+        # a tiny mean anomaly at the first epoch for half of the rows
+        dt0 = spec["t"][0] - spec["t0"]
+        tiny = 10 ** rng.uniform(-9, -2, n // 2) * rng.choice([-1, 1], n // 2)
+        chunk[: n // 2, 3] = 2 * np.pi * dt0 / chunk[: n // 2, 0] - tiny
+        not_conv = 0
+        for row in chunk[:200]:
+            z, st = helper.design_column(row, return_stats=True)
+            assert np.isfinite(z).all(), row
+            not_conv += st[2]
+        assert not_conv == 0
+        ll = helper.batch_marginal_ln_likelihood(chunk)
+        assert np.isfinite(ll).all()
+        assert helper.solver_stats(reset=True)["not_converged"] == 0
+
+
 def test_posterior_aA_and_draws(torch_cuda, oracle_lib):
     """(a, A) vs oracle (dsysv / inverse of Ainv) as in
     test_fast_likelihood.py::test_likelihood_helpers; draws: same RNG consumption as

@@ -404,6 +404,56 @@ def test_host_emulated_tuning_variants(variant):
         assert np.max(rel_err(got, truth)) < 1e-10
 
 
+@pytest.mark.parametrize("variant", ["", "TJB_TRIM=1 TJB_PHASE_FIXED=1"])
+def test_kepler_solver_extreme_cases(variant):
+    """e -> 1 at M -> 0, phases beyond the FP32 stage's range (P = 0.05 d over 10 000 d):
+    the safeguarded extra passes (kepler.cuh::solve_extra_passes) always converge to a
+    finite value -- one NaN ll would poison the max of the whole prior cache and the
+    rejection step would accept nothing -- and the value is right (50-digit mpmath)."""
+    import mpmath as mp
+
+    lib = host_emulation(variant)
+    dp = ctypes.POINTER(ctypes.c_double)
+    rng = np.random.default_rng(3)
+    z, st = np.zeros(64), (ctypes.c_int * 3)()
+    n = 3000
+    for span, P_min in ((155.0, 2.0), (10000.0, 0.05)):
+        dt = np.sort(rng.uniform(0, span, 64))
+        P = np.exp(rng.uniform(np.log(P_min), np.log(1000), n))
+        e = 1 - 10 ** rng.uniform(-7, -1, n)
+        om, M0 = rng.uniform(-np.pi, np.pi, (2, n))
+        for i in range(n):
+            lib.emu_design_column(P[i], e[i], om[i], M0[i], dt.ctypes.data_as(dp), 64,
+                                  z.ctypes.data_as(dp), st)
+            assert st[2] == 0 and np.isfinite(z).all(), (P[i], e[i], om[i], M0[i])
+    # accuracy at the hard corner, scaled by the conditioning d z / d M ~ 1 / (1 - e cosE)^2
+    mp.mp.dps = 50
+    worst, one, zz = 0.0, np.zeros(1), np.zeros(1)
+    for trial in range(120):
+        e = 1 - 10 ** rng.uniform(-7, -2)
+        P = float(np.exp(rng.uniform(np.log(2), np.log(1000))))
+        om, M0 = rng.uniform(-np.pi, np.pi, 2)
+        Mt = 10 ** rng.uniform(-9, -1) * rng.choice([-1, 1])   # a tiny mean anomaly
+        one[0] = (Mt + M0) * P / (2 * np.pi) + P * rng.integers(0, 3)
+        lib.emu_design_column(P, e, om, M0, one.ctypes.data_as(dp), 1, zz.ctypes.data_as(dp), st)
+        assert st[2] == 0
+        M = 2 * mp.pi * mp.mpf(float(one[0])) / mp.mpf(P) - mp.mpf(float(M0))
+        M -= 2 * mp.pi * mp.nint(M / (2 * mp.pi))
+        lo, hi = M - mp.mpf(e), M + mp.mpf(e)
+        for _ in range(180):
+            mid = (lo + hi) / 2
+            if mid - mp.mpf(e) * mp.sin(mid) - M > 0:
+                hi = mid
+            else:
+                lo = mid
+        E = (lo + hi) / 2
+        a, b = mp.cos(mp.mpf(float(om))), -mp.sqrt(1 - mp.mpf(e) ** 2) * mp.sin(mp.mpf(float(om)))
+        f1 = 1 - mp.mpf(e) * mp.cos(E)
+        zt = (a * (mp.cos(E) - mp.mpf(e)) + b * mp.sin(E)) / f1 + mp.mpf(e) * a
+        worst = max(worst, float(abs(mp.mpf(float(zz[0])) - zt) * f1 ** 2))
+    assert worst < 1e-14
+
+
 def test_phase_reduction_variants():
     """How often the one-pass FP64 step is not enough, against the time baseline of the data
     (default prior, P >= 2 d): the shipped FP32 stage rounds the unreduced phase to float, so

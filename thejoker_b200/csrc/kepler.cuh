@@ -34,9 +34,11 @@
 #if defined(__CUDACC__)
 #define TJB_HD __host__ __device__ __forceinline__
 #define TJB_D __device__ __forceinline__
+#define TJB_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define TJB_HD inline
 #define TJB_D inline
+#define TJB_HD_NOINLINE inline
 #endif
 
 namespace tjb {
@@ -290,8 +292,9 @@ struct SolveStats {
 
 // A third-order Householder step maps an error eps to ~C eps^4 with C = O(1) for
 // e <~ 0.95 (tools/kepler_solver_study.py): a lane repeats the pass while it moved by
-// 2^-13 (1.2e-4) or more, at most kF64MaxIter times.
-constexpr int kF64MaxIter = 16;
+// 2^-13 (1.2e-4) or more, at most kF64MaxIter times (bisection steps of the safeguard
+// included: e = 1 - 1e-5 at M = 1e-5 takes ~25).
+constexpr int kF64MaxIter = 64;
 
 // run-wide solver statistics (device counters, touched only on the rare path):
 // [0] extra FP64 passes (lane-epochs), [1] epochs that hit kF64MaxIter
@@ -337,6 +340,60 @@ TJB_HD void rotate_small(const TrigCoef &tc, double del, double &sE, double &cE)
   const double sN = fma(cE, sd, sE * cd);
   cE = fma(-sE, sd, cE * cd);
   sE = sN;
+}
+
+// The rare path of the solver: lanes whose first FP64 step moved by 2^-13 or more
+// (e >~ 0.8 near pericentre, a phase beyond the FP32 stage's range) re-evaluate sincos in
+// full at the updated E and repeat the step until it is small; lanes that had converged
+// (`nd` false) return `frozen`, exactly the values of the normal path.  All lanes of the
+// warp call together (the loop votes).  A function of its own, not inlined: its registers
+// and code stay out of the epoch loop's allocation and instruction stream, and it takes
+// scalars only so that the caller's constants stay in registers.
+//
+// Safeguard: the root obeys |E - M| <= e and g(D) = D - e sin(M + D) increases with D, so
+// [-e, e] brackets it.  Every pass narrows the bracket by the sign of g; a start or a
+// Householder step that leaves it (or is NaN: wild FP32 estimate, e -> 1 at M -> 0) is
+// replaced by the clamp / the midpoint, so the iteration cannot diverge and the result is
+// finite for every e < 1 (tests/test_host_logic.py::test_kepler_solver_extreme_cases).
+template <bool kCountStats>
+TJB_HD_NOINLINE SinCos solve_extra_passes(double e, const SinCos *table, double x4, double Dstart,
+                                          SinCos frozen, bool nd, SolveStats *st,
+                                          unsigned long long *gstats) {
+  TrigCoef tc;
+  tc.load(0.0, table);
+  OrbitConsts oc;
+  oc.e = e;
+  oc.e6 = e * (1.0 / 6.0);
+  double Dlo = -e, Dhi = e;
+  double Dk = fmin(fmax(Dstart, Dlo), Dhi);
+  SinCos out = frozen;
+#pragma unroll 1
+  for (int it = 1; it < kF64MaxIter && any_lane(nd); ++it) {
+    double s2, c2;
+    sincos_units(tc, fma(Dk, TJB_MC(1), x4), s2, c2);
+    const double d2 = householder3(oc, tc, Dk, s2, c2);
+    if (nd) {
+      if (kCountStats) st->extra_f64++;
+      count_event(gstats, 0);
+      if ((unsigned)(hi32(d2) & 0x7fffffff) < 0x3f200000u) {
+        rotate_small(tc, d2, s2, c2);
+        out.s = s2;
+        out.c = c2;
+        nd = false;
+      } else {
+        // |g| >> rounding here, so its sign is reliable
+        if (fma(-e, s2, Dk) > 0.0) Dhi = Dk; else Dlo = Dk;
+        const double Dn = Dk + d2;
+        Dk = (Dn > Dlo && Dn < Dhi) ? Dn : 0.5 * (Dlo + Dhi);  // a NaN step bisects
+      }
+    }
+  }
+  if (nd) {  // did not converge within kF64MaxIter passes: best estimate, counted
+    if (kCountStats) st->not_converged++;
+    count_event(gstats, 1);
+    sincos_units(tc, fma(Dk, TJB_MC(1), x4), out.s, out.c);
+  }
+  return out;
 }
 
 // K epochs of one sample at once (K independent dependency chains interleaved by
@@ -425,46 +482,18 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
 #pragma unroll
     for (int k = 0; k < K; k++) rotate_small(tc, del[k], sE[k], cE[k]);
   } else {
-    // rare (e >~ 0.8 near pericentre, or |x4| beyond float range): lanes that need it
-    // re-evaluate sincos in full at the updated E and repeat the step; converged lanes
-    // are frozen at exactly the values the normal case gives them.
+    // rare: see solve_extra_passes
 #pragma unroll
     for (int k = 0; k < K; k++) {
-      double sR = sE[k], cR = cE[k];
-      rotate_small(tc, del[k], sR, cR);
+      SinCos fr = {sE[k], cE[k]};
+      rotate_small(tc, del[k], fr.s, fr.c);
 #if TJB_TRIM
       need[k] = ((unsigned)hi32(del[k]) << 1) >= (0x3f200000u << 1);
 #endif
-      bool nd = need[k];
-      double Dk = D[k] + del[k];
-#if TJB_TRIM
-      // the FP32 estimate is not clamped on the main path: |E - M| <= e holds for the
-      // root, and fmin / fmax also replace a NaN estimate
-      if (nd) Dk = fmin(fmax(Dk, -oc.e), oc.e);
-#endif
-      for (int it = 1; it < kF64MaxIter && any_lane(nd); ++it) {
-        double s2, c2;
-        sincos_units(tc, fma(Dk, TJB_MC(1), x4[k]), s2, c2);
-        const double d2 = householder3(oc, tc, Dk, s2, c2);
-        if (nd) {
-          if (kCountStats) st->extra_f64++;
-          count_event(gstats, 0);
-          Dk += d2;
-          if ((unsigned)(hi32(d2) & 0x7fffffff) < 0x3f200000u) {
-            rotate_small(tc, d2, s2, c2);
-            sR = s2;
-            cR = c2;
-            nd = false;
-          }
-        }
-      }
-      if (nd) {  // did not converge within kF64MaxIter passes: best estimate, counted
-        if (kCountStats) st->not_converged++;
-        count_event(gstats, 1);
-        sincos_units(tc, fma(Dk, TJB_MC(1), x4[k]), sR, cR);
-      }
-      sE[k] = sR;
-      cE[k] = cR;
+      const SinCos r = solve_extra_passes<kCountStats>(oc.e, tc.table, x4[k], D[k] + del[k], fr,
+                                                       need[k], st, gstats);
+      sE[k] = r.s;
+      cE[k] = r.c;
     }
   }
 
