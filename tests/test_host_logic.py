@@ -362,7 +362,8 @@ def test_host_emulated_ll_matches_oracle(N, pt, sl, kw):
 
 
 VARIANTS = ["TJB_TRIM=1", "TJB_PHASE_FIXED=1", "TJB_TRIM=1 TJB_PHASE_FIXED=1",
-            "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_TRIG_TABLE=0"]
+            "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_TRIG_TABLE=0",
+            "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_HALLEY=1"]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
@@ -404,7 +405,8 @@ def test_host_emulated_tuning_variants(variant):
         assert np.max(rel_err(got, truth)) < 1e-10
 
 
-@pytest.mark.parametrize("variant", ["", "TJB_TRIM=1 TJB_PHASE_FIXED=1"])
+@pytest.mark.parametrize("variant", ["", "TJB_TRIM=1 TJB_PHASE_FIXED=1",
+                                     "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_HALLEY=1"])
 def test_kepler_solver_extreme_cases(variant):
     """e -> 1 at M -> 0, phases beyond the FP32 stage's range (P = 0.05 d over 10 000 d):
     the safeguarded extra passes (kepler.cuh::solve_extra_passes) always converge to a

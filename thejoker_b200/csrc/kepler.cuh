@@ -80,6 +80,19 @@ namespace tjb {
 #define TJB_PHASE_FIXED 0
 #endif
 
+// Second-order (Halley) FP64 step on the main path instead of the third-order one (default
+// off until timed on the GPU).  The FP32 stage leaves an error of a few 1e-7 / (1 - e cosE);
+// a cubically convergent step takes that below 1e-16 as long as the step itself is below
+// 2^-17 (7.6e-6: error <= 4.4e-16 (t^2/2 - e cosE/(6 f1)), i.e. 1e-15 at e = 0.9 and 1e-13
+// at e = 0.999 in the worst case), and for such a step sin(delta) = delta to 7e-17.  Saves
+// 5 FP64 instructions per epoch; 2 % instead of 0.4 % of the (warp, two-epoch) groups take
+// the extra-pass path on the benchmark data (host build of the device code), which keeps
+// the third-order step.  Meant to be combined with TJB_PHASE_FIXED (a float-rounded phase
+// alone exceeds the tighter threshold beyond ~100 revolutions).
+#ifndef TJB_HALLEY
+#define TJB_HALLEY 0
+#endif
+
 // 1.5 * 2^52 (1.5 * 2^23): adding it rounds to the nearest integer and leaves
 // that integer in the low mantissa bits.
 constexpr double kMagic = 6755399441055744.0;
@@ -295,6 +308,11 @@ struct SolveStats {
 // 2^-13 (1.2e-4) or more, at most kF64MaxIter times (bisection steps of the safeguard
 // included: e = 1 - 1e-5 at M = 1e-5 takes ~25).
 constexpr int kF64MaxIter = 64;
+// high word of the threshold 2^-TJB_NEED_LOG2 (exponent field only)
+#ifndef TJB_NEED_LOG2
+#define TJB_NEED_LOG2 (TJB_HALLEY ? 17 : 13)
+#endif
+constexpr unsigned kNeedHi = (unsigned)(1023 - TJB_NEED_LOG2) << 20;
 
 // run-wide solver statistics (device counters, touched only on the rare path):
 // [0] extra FP64 passes (lane-epochs), [1] epochs that hit kF64MaxIter
@@ -342,6 +360,34 @@ TJB_HD void rotate_small(const TrigCoef &tc, double del, double &sE, double &cE)
   sE = sN;
 }
 
+// Main-path step and rotation of the TJB_HALLEY variant: delta = u (1 - u t / 2) with
+// u = -f/f1, t = f2/f1; rotation by |delta| < 2^-17 with sin d = d, cos d = 1 - d^2/2.
+TJB_HD double halley2(const OrbitConsts &oc, double D, double sE, double cE) {
+  const double es = oc.e * sE;
+  const double r = rcp_pos(fma(-oc.e, cE, 1.0));
+  const double t = es * r;
+  const double u = fma(-D, r, t);
+  return u * fma(u * -0.5, t, 1.0);
+}
+TJB_HD void rotate_tiny(const TrigCoef &tc, double del, double &sE, double &cE) {
+  (void)tc;
+#if TJB_TRIM
+  const double cd = fma(del * del, -TJB_MC(3), 1.0);
+#else
+  const double cd = fma(del * del, -0.5, 1.0);
+#endif
+  const double sN = fma(cE, del, sE * cd);
+  cE = fma(-sE, del, cE * cd);
+  sE = sN;
+}
+#if TJB_HALLEY
+#define TJB_MAIN_STEP(oc, tc, D, s, c) halley2(oc, D, s, c)
+#define TJB_MAIN_ROTATE rotate_tiny
+#else
+#define TJB_MAIN_STEP(oc, tc, D, s, c) householder3(oc, tc, D, s, c)
+#define TJB_MAIN_ROTATE rotate_small
+#endif
+
 // The rare path of the solver: lanes whose first FP64 step moved by 2^-13 or more
 // (e >~ 0.8 near pericentre, a phase beyond the FP32 stage's range) re-evaluate sincos in
 // full at the updated E and repeat the step until it is small; lanes that had converged
@@ -375,7 +421,7 @@ TJB_HD_NOINLINE SinCos solve_extra_passes(double e, const SinCos *table, double 
     if (nd) {
       if (kCountStats) st->extra_f64++;
       count_event(gstats, 0);
-      if ((unsigned)(hi32(d2) & 0x7fffffff) < 0x3f200000u) {
+      if ((unsigned)(hi32(d2) & 0x7fffffff) < kNeedHi) {
         rotate_small(tc, d2, s2, c2);
         out.s = s2;
         out.c = c2;
@@ -462,7 +508,7 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
     sincos_units(tc, x4[k] + d4, sE[k], cE[k]);
     D[k] = d4 * TJB_MC(2);  // E0 - M [rad]
 #endif
-    del[k] = householder3(oc, tc, D[k], sE[k], cE[k]);
+    del[k] = TJB_MAIN_STEP(oc, tc, D[k], sE[k], cE[k]);
     // error map of the step: eps -> ~C eps^4 (tools/kepler_solver_study.py); a lane
     // that moved by 2^-13 (1.2e-4) or more, or produced a NaN, takes further passes.
     // The test reads the exponent field on the integer pipe instead of a DSETP.
@@ -470,25 +516,25 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
     const unsigned hk = (unsigned)hi32(del[k]) << 1;
     top = hk > top ? hk : top;
 #else
-    need[k] = (unsigned)(hi32(del[k]) & 0x7fffffff) >= 0x3f200000u;
+    need[k] = (unsigned)(hi32(del[k]) & 0x7fffffff) >= kNeedHi;
     any_need = any_need || need[k];
 #endif
   }
 #if TJB_TRIM
-  any_need = top >= (0x3f200000u << 1);
+  any_need = top >= (kNeedHi << 1);
 #endif
   if (!any_lane(any_need)) {
     // the normal case: every lane of the warp converged in one pass
 #pragma unroll
-    for (int k = 0; k < K; k++) rotate_small(tc, del[k], sE[k], cE[k]);
+    for (int k = 0; k < K; k++) TJB_MAIN_ROTATE(tc, del[k], sE[k], cE[k]);
   } else {
     // rare: see solve_extra_passes
 #pragma unroll
     for (int k = 0; k < K; k++) {
       SinCos fr = {sE[k], cE[k]};
-      rotate_small(tc, del[k], fr.s, fr.c);
+      TJB_MAIN_ROTATE(tc, del[k], fr.s, fr.c);
 #if TJB_TRIM
-      need[k] = ((unsigned)hi32(del[k]) << 1) >= (0x3f200000u << 1);
+      need[k] = ((unsigned)hi32(del[k]) << 1) >= (kNeedHi << 1);
 #endif
       const SinCos r = solve_extra_passes<kCountStats>(oc.e, tc.table, x4[k], D[k] + del[k], fr,
                                                        need[k], st, gstats);

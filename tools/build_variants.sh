@@ -22,4 +22,9 @@ build trim_fixed_e4 -DTJB_TRIM=1 -DTJB_PHASE_FIXED=1 -DTJB_EPOCHS_PER_ITER=4
 build trim_fixed_192x3 -DTJB_TRIM=1 -DTJB_PHASE_FIXED=1 -DTJB_LL_THREADS=192 -DTJB_LL_MIN_CTAS=3
 build trim_fixed_t2048 -DTJB_TRIM=1 -DTJB_PHASE_FIXED=1 -DTJB_TRIG_TABLE_LOG2=11
 wait
+build trim_fixed_halley -DTJB_TRIM=1 -DTJB_PHASE_FIXED=1 -DTJB_HALLEY=1
+build trim_fixed_halley_e3 -DTJB_TRIM=1 -DTJB_PHASE_FIXED=1 -DTJB_HALLEY=1 -DTJB_EPOCHS_PER_ITER=3
+build trim_fixed_halley_16 -DTJB_TRIM=1 -DTJB_PHASE_FIXED=1 -DTJB_HALLEY=1 -DTJB_NEED_LOG2=16
+build trim_fixed_halley_18 -DTJB_TRIM=1 -DTJB_PHASE_FIXED=1 -DTJB_HALLEY=1 -DTJB_NEED_LOG2=18
+wait
 ls -la build/variants
