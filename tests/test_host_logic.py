@@ -292,12 +292,13 @@ def test_product_does_not_import_oracle():
 
 
 # ---- device math on the host ---------------------------------------------------------
-def test_sincos_units():
+@pytest.mark.parametrize("variant", ["", "TJB_TRIG_TABLE=0", "TJB_TRIM=1 TJB_TRIG_TABLE_LOG2=11"])
+def test_sincos_units(variant):
     """The FP64 sin/cos of the epoch loop (table node + short polynomial, or the minimax
     polynomial back-end) against 40-digit mpmath, over many revolutions."""
     import mpmath as mp
 
-    lib = host_emulation()
+    lib = host_emulation(variant)
     rng = np.random.default_rng(0)
     s, c = ctypes.c_double(), ctypes.c_double()
     worst = 0.0
@@ -363,7 +364,8 @@ def test_host_emulated_ll_matches_oracle(N, pt, sl, kw):
 
 VARIANTS = ["TJB_TRIM=1", "TJB_PHASE_FIXED=1", "TJB_TRIM=1 TJB_PHASE_FIXED=1",
             "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_TRIG_TABLE=0",
-            "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_HALLEY=1"]
+            "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_HALLEY=1",
+            "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_HALLEY=1 TJB_TRIG_TABLE_LOG2=11"]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
@@ -406,7 +408,8 @@ def test_host_emulated_tuning_variants(variant):
 
 
 @pytest.mark.parametrize("variant", ["", "TJB_TRIM=1 TJB_PHASE_FIXED=1",
-                                     "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_HALLEY=1"])
+                                     "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_HALLEY=1",
+            "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_HALLEY=1 TJB_TRIG_TABLE_LOG2=11"])
 def test_kepler_solver_extreme_cases(variant):
     """e -> 1 at M -> 0, phases beyond the FP32 stage's range (P = 0.05 d over 10 000 d):
     the safeguarded extra passes (kepler.cuh::solve_extra_passes) always converge to a

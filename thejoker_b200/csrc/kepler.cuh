@@ -127,7 +127,8 @@ struct alignas(16) SinCos {
 // sin(r h) = r (S0 + S1 r^2 + S2 r^4), cos(r h) = 1 + C1 r^2 + C2 r^4 for |r| <= 1/2,
 // h = 2 pi / table size (Taylor; truncation 5e-22 and 1.2e-18 at 1024 nodes).  From 4096
 // nodes on the r^5 term of the sine is below 3e-18 and is dropped.
-constexpr bool kSinQuintic = kTrigTableSize < 4096;
+// (TJB_TRIM drops it from 2048 nodes on: 7e-17 at most, below one ulp of the result.)
+constexpr bool kSinQuintic = kTrigTableSize < (TJB_TRIM ? 2048 : 4096);
 constexpr int kNSin = 3, kNCos = 3;
 TJB_COEF double kSinC[3] = {kRadPerUnit, -(kRadPerUnit * kRadPerUnit * kRadPerUnit) / 6.0,
                             (kRadPerUnit * kRadPerUnit * kRadPerUnit * kRadPerUnit * kRadPerUnit) /
@@ -183,7 +184,15 @@ TJB_D double rcp_pos(double x) {
   const double t = fma(-x, r, 1.0);
   return fma(r, fma(t, t, t), r);
 }
+// the same with one Newton step: relative error <= 1e-12, for factors that multiply a
+// step of at most 2^-17
+TJB_D double rcp_pos_newton(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return fma(r, fma(-x, r, 1.0), r);
+}
 #else
+inline double rcp_pos_newton(double x) { return 1.0 / x; }
 inline int lo32(double x) { int64_t b; memcpy(&b, &x, 8); return (int)(uint32_t)(b & 0xffffffff); }
 inline int hi32(double x) { int64_t b; memcpy(&b, &x, 8); return (int)(uint32_t)((uint64_t)b >> 32); }
 inline double mk64(int hi, int lo) {
@@ -364,7 +373,8 @@ TJB_HD void rotate_small(const TrigCoef &tc, double del, double &sE, double &cE)
 // u = -f/f1, t = f2/f1; rotation by |delta| < 2^-17 with sin d = d, cos d = 1 - d^2/2.
 TJB_HD double halley2(const OrbitConsts &oc, double D, double sE, double cE) {
   const double es = oc.e * sE;
-  const double r = rcp_pos(fma(-oc.e, cE, 1.0));
+  // 1/f1 to 1e-12 is enough: its error enters delta times |u| <= 2^-17
+  const double r = rcp_pos_newton(fma(-oc.e, cE, 1.0));
   const double t = es * r;
   const double u = fma(-D, r, t);
   return u * fma(u * -0.5, t, 1.0);

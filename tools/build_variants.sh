@@ -27,4 +27,7 @@ build trim_fixed_halley_e3 -DTJB_TRIM=1 -DTJB_PHASE_FIXED=1 -DTJB_HALLEY=1 -DTJB
 build trim_fixed_halley_16 -DTJB_TRIM=1 -DTJB_PHASE_FIXED=1 -DTJB_HALLEY=1 -DTJB_NEED_LOG2=16
 build trim_fixed_halley_18 -DTJB_TRIM=1 -DTJB_PHASE_FIXED=1 -DTJB_HALLEY=1 -DTJB_NEED_LOG2=18
 wait
+build trim_fixed_halley_t2048 -DTJB_TRIM=1 -DTJB_PHASE_FIXED=1 -DTJB_HALLEY=1 -DTJB_TRIG_TABLE_LOG2=11
+build trim_fixed_halley_t2048_e3 -DTJB_TRIM=1 -DTJB_PHASE_FIXED=1 -DTJB_HALLEY=1 -DTJB_TRIG_TABLE_LOG2=11 -DTJB_EPOCHS_PER_ITER=3
+wait
 ls -la build/variants
