@@ -13,7 +13,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TJB_LIB_PATH", os.path.join(_HERE, "libthejoker_b200.so"))  # override: tuning builds
 _SRC = [os.path.join(_HERE, "csrc", f) for f in
-        ("tjb_api.cu", "kepler.cuh", "linalg.cuh", "marginal_ll.cuh", "accept.cuh", "posterior.cuh")]
+        ("tjb_api.cu", "kepler.cuh", "linalg.cuh", "marginal_ll.cuh", "accept.cuh", "posterior.cuh",
+         "star_tables.hpp")]
 _HDR = os.path.join(os.path.dirname(_HERE), "include", "thejoker_b200.h")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

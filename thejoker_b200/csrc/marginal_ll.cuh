@@ -148,13 +148,28 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab,
     // kEpochsPerIter epochs per iteration: independent Kepler chains for ILP
     TJB_EPOCH_GROUPS(n, N, row, RS) {
       double dt[kEpochsPerIter], z[kEpochsPerIter];
+#if TJB_TRIM && defined(__CUDA_ARCH__)
+      // dt and w in one 16-byte shared-memory load (rows are 16-byte aligned)
+      double wj[kEpochsPerIter];
+#pragma unroll
+      for (int j = 0; j < kEpochsPerIter; j++) {
+        const double2 dw = *reinterpret_cast<const double2 *>(row + j * RS);
+        dt[j] = dw.x;
+        wj[j] = dw.y;
+      }
+#else
 #pragma unroll
       for (int j = 0; j < kEpochsPerIter; j++) dt[j] = row[j * RS];
+#endif
       rv_unit_columns<kEpochsPerIter, false>(oc, tc, dt, z, nullptr, sp.stats);
 #pragma unroll
       for (int j = 0; j < kEpochsPerIter; j++) {
         const double *rj = row + j * RS;
+#if TJB_TRIM && defined(__CUDA_ARCH__)
+        Szz = fma(z[j] * z[j], wj[j], Szz);
+#else
         Szz = fma(z[j] * z[j], rj[1], Szz);
+#endif
         Szy = fma(z[j], rj[2], Szy);
 #pragma unroll
         for (int k = 1; k < L; k++) SzT[k] = fma(z[j], rj[2 + k], SzT[k]);
