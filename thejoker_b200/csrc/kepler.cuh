@@ -198,8 +198,21 @@ inline int hi32(double x) { int64_t b; memcpy(&b, &x, 8); return (int)(uint32_t)
 inline double mk64(int hi, int lo) {
   uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double x; memcpy(&x, &b, 8); return x;
 }
+#if defined(TJB_EMU_MUFU_NOISE)
+// host emulation only: the documented absolute error of sin.approx / cos.approx on
+// [-pi, pi] (2^-21.41) as a deterministic pseudo-random perturbation, to estimate how often
+// the device's FP32 stage misses the extra-pass threshold
+inline float emu_mufu_noise(float x) {
+  uint32_t b; memcpy(&b, &x, 4);
+  b = b * 2654435761u; b ^= b >> 15; b *= 2246822519u; b ^= b >> 13;
+  return ((float)(b >> 8) * (1.0f / 8388608.0f) - 1.0f) * 3.6e-7f;
+}
+inline float fsin_approx(float x) { return sinf(x) + emu_mufu_noise(x); }
+inline float fcos_approx(float x) { return cosf(x) + emu_mufu_noise(-x); }
+#else
 inline float fsin_approx(float x) { return sinf(x); }
 inline float fcos_approx(float x) { return cosf(x); }
+#endif
 inline float frsqrt_approx(float x) { return 1.0f / sqrtf(x); }
 inline float frcp_approx(float x) { return 1.0f / x; }
 inline double rcp_pos(double x) { return 1.0 / x; }
