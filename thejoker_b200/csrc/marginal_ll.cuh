@@ -203,8 +203,8 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab,
     lp.init();
     const double *row = tab;
     int n = 0;
-    auto accumulate = [&](const double *rj, double z) {
-      const double var = rj[1] + s2;
+    auto accumulate = [&](const double *rj, double z, double var_n) {
+      const double var = var_n + s2;
       // positive and normal unless ivar == 0 (var = inf): then the epoch has zero weight
       const double w = var < 1.0e300 ? rcp_pos(var) : 0.0;
       lp.mul(var);
@@ -226,15 +226,28 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab,
     };
     TJB_EPOCH_GROUPS(n, N, row, RS) {
       double dt[kEpochsPerIter], z[kEpochsPerIter];
+#if TJB_TRIM && defined(__CUDA_ARCH__)
+      double vn[kEpochsPerIter];
+#pragma unroll
+      for (int j = 0; j < kEpochsPerIter; j++) {  // dt and var in one 16-byte load
+        const double2 dv = *reinterpret_cast<const double2 *>(row + j * RS);
+        dt[j] = dv.x;
+        vn[j] = dv.y;
+      }
+      rv_unit_columns<kEpochsPerIter, false>(oc, tc, dt, z, nullptr, sp.stats);
+#pragma unroll
+      for (int j = 0; j < kEpochsPerIter; j++) accumulate(row + j * RS, z[j], vn[j]);
+#else
 #pragma unroll
       for (int j = 0; j < kEpochsPerIter; j++) dt[j] = row[j * RS];
       rv_unit_columns<kEpochsPerIter, false>(oc, tc, dt, z, nullptr, sp.stats);
 #pragma unroll
-      for (int j = 0; j < kEpochsPerIter; j++) accumulate(row + j * RS, z[j]);
+      for (int j = 0; j < kEpochsPerIter; j++) accumulate(row + j * RS, z[j], row[j * RS + 1]);
+#endif
       lp.renorm();  // at most kEpochsPerIter factors between renormalisations
     }
     for (; n < N; n++, row += RS) {
-      accumulate(row, rv_unit_column<false>(oc, tc, row[0], nullptr));
+      accumulate(row, rv_unit_column<false>(oc, tc, row[0], nullptr), row[1]);
       lp.renorm();
     }
     lp.renorm();
