@@ -228,6 +228,16 @@ inline double rcp_pos(double x) { return 1.0 / x; }
 struct TrigCoef {
   double s[kNSin], c[kNCos], m[kNMisc];
   const SinCos *table;  // kTrigTableSize nodes, sin/cos(2 pi j / size); null without a table
+#if TJB_TRIM && defined(__CUDA_ARCH__)
+  // 32-bit shared-window address of the table where it is staged in shared memory (the
+  // likelihood kernel; sincos_units<true>): ptxas otherwise re-derives the window base of
+  // the generic pointer inside the epoch loop (S2UR / UIADD3 / ULEA / moves)
+  unsigned table_s;
+  TJB_D void use_shared_table() {
+    table_s = (unsigned)__cvta_generic_to_shared(table);
+    asm volatile("" : "+r"(table_s));  // opaque: keep it in a register
+  }
+#endif
   // `zero` must be a run-time 0.0 (a kernel parameter): coefficient + zero is an
   // FP64 result ptxas will not rematerialise, so the values stay in registers.
   TJB_HD void load(double zero, const SinCos *tab) {
@@ -243,13 +253,25 @@ struct TrigCoef {
 
 // sin and cos of an angle v given in angle units (1/kUnitsPerRev revolution), any size
 // up to 2^51: exact reduction by magic-number rounding.
+template <bool kSharedTable = false>
 TJB_HD void sincos_units(const TrigCoef &tc, double v, double &s, double &c) {
   const double tv = v + kMagic;
   const double r = v - (tv - kMagic);  // in [-0.5, 0.5]
   const int k = lo32(tv);              // nearest node / quadrant (mod 2^32)
   const double r2 = r * r;
 #if TJB_TRIG_TABLE
+#if TJB_TRIM && defined(__CUDA_ARCH__)
+  SinCos node;
+  if (kSharedTable) {
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];"
+        : "=d"(node.s), "=d"(node.c)
+        : "r"(tc.table_s + ((unsigned)(k & (kTrigTableSize - 1)) << 4)));
+  } else {
+    node = tc.table[k & (kTrigTableSize - 1)];
+  }
+#else
   const SinCos node = tc.table[k & (kTrigTableSize - 1)];
+#endif
   const double sr = kSinQuintic ? r * fma(r2, fma(r2, TJB_SC(2), TJB_SC(1)), TJB_SC(0))
                                 : r * fma(r2, TJB_SC(1), TJB_SC(0));
   const double cr = fma(r2, fma(r2, TJB_CC(2), TJB_CC(1)), 1.0);
@@ -469,7 +491,7 @@ TJB_HD_NOINLINE SinCos solve_extra_passes(double e, const SinCos *table, double 
 // the compiler).  dt[k] = t_n - t_ref [day]; z[k] receives z_n.  All lanes of a warp
 // must call together.  The result of a lane depends only on that lane's inputs (not
 // on its warp-mates): lanes that need extra passes iterate under a per-lane flag.
-template <int K, bool kCountStats>
+template <int K, bool kCountStats, bool kSharedTable = false>
 TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const double *dt, double *z,
                             SolveStats *st, unsigned long long *gstats = nullptr) {
   double x4[K], D[K], sE[K], cE[K];  // x4: mean anomaly in angle units (unreduced)
@@ -525,10 +547,10 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
 #if TJB_TRIM
     D[k] = (double)Df[k];                // E0 - M [rad]
     const double d4 = D[k] * TJB_MC(1);  // in angle units (1-ulp rounding: < 2e-16 rad)
-    sincos_units(tc, x4[k] + d4, sE[k], cE[k]);
+    sincos_units<kSharedTable>(tc, x4[k] + d4, sE[k], cE[k]);
 #else
     const double d4 = (double)(Df[k] * (float)kUnitsPerRad);  // D0 in angle units
-    sincos_units(tc, x4[k] + d4, sE[k], cE[k]);
+    sincos_units<kSharedTable>(tc, x4[k] + d4, sE[k], cE[k]);
     D[k] = d4 * TJB_MC(2);  // E0 - M [rad]
 #endif
     del[k] = TJB_MAIN_STEP(oc, tc, D[k], sE[k], cE[k]);
@@ -576,10 +598,10 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
 }
 
 // One epoch.
-template <bool kCountStats>
+template <bool kCountStats, bool kSharedTable = false>
 TJB_HD double rv_unit_column(const OrbitConsts &oc, const TrigCoef &tc, double dt, SolveStats *st) {
   double z;
-  rv_unit_columns<1, kCountStats>(oc, tc, &dt, &z, st);
+  rv_unit_columns<1, kCountStats, kSharedTable>(oc, tc, &dt, &z, st);
   return z;
 }
 

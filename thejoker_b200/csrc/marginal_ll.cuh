@@ -130,6 +130,12 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab,
   constexpr int RS = row_stride(L);
   TrigCoef tc;
   tc.load(sp.zero, trig);
+#if TJB_TRIM && defined(__CUDA_ARCH__)
+  tc.use_shared_table();  // `trig` is the kernel's shared-memory copy of the table
+  constexpr bool kSh = true;
+#else
+  constexpr bool kSh = false;
+#endif
   const OrbitConsts oc = make_orbit_consts(tc, P, e, omega, M0);
   const int N = sp.n_times;
 
@@ -161,7 +167,7 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab,
 #pragma unroll
       for (int j = 0; j < kEpochsPerIter; j++) dt[j] = row[j * RS];
 #endif
-      rv_unit_columns<kEpochsPerIter, false>(oc, tc, dt, z, nullptr, sp.stats);
+      rv_unit_columns<kEpochsPerIter, false, kSh>(oc, tc, dt, z, nullptr, sp.stats);
 #pragma unroll
       for (int j = 0; j < kEpochsPerIter; j++) {
         const double *rj = row + j * RS;
@@ -176,7 +182,7 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab,
       }
     }
     for (; n < N; n++, row += RS) {
-      const double z = rv_unit_column<false>(oc, tc, row[0], nullptr);
+      const double z = rv_unit_column<false, kSh>(oc, tc, row[0], nullptr);
       Szz = fma(z * z, row[1], Szz);
       Szy = fma(z, row[2], Szy);
 #pragma unroll
@@ -234,20 +240,20 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab,
         dt[j] = dv.x;
         vn[j] = dv.y;
       }
-      rv_unit_columns<kEpochsPerIter, false>(oc, tc, dt, z, nullptr, sp.stats);
+      rv_unit_columns<kEpochsPerIter, false, kSh>(oc, tc, dt, z, nullptr, sp.stats);
 #pragma unroll
       for (int j = 0; j < kEpochsPerIter; j++) accumulate(row + j * RS, z[j], vn[j]);
 #else
 #pragma unroll
       for (int j = 0; j < kEpochsPerIter; j++) dt[j] = row[j * RS];
-      rv_unit_columns<kEpochsPerIter, false>(oc, tc, dt, z, nullptr, sp.stats);
+      rv_unit_columns<kEpochsPerIter, false, kSh>(oc, tc, dt, z, nullptr, sp.stats);
 #pragma unroll
       for (int j = 0; j < kEpochsPerIter; j++) accumulate(row + j * RS, z[j], row[j * RS + 1]);
 #endif
       lp.renorm();  // at most kEpochsPerIter factors between renormalisations
     }
     for (; n < N; n++, row += RS) {
-      accumulate(row, rv_unit_column<false>(oc, tc, row[0], nullptr), row[1]);
+      accumulate(row, rv_unit_column<false, kSh>(oc, tc, row[0], nullptr), row[1]);
       lp.renorm();
     }
     lp.renorm();
