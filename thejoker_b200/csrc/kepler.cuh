@@ -263,9 +263,9 @@ TJB_HD void sincos_units(const TrigCoef &tc, double v, double &s, double &c) {
 #if TJB_TRIM && defined(__CUDA_ARCH__)
   SinCos node;
   if (kSharedTable) {
-    asm("ld.shared.v2.f64 {%0, %1}, [%2];"
-        : "=d"(node.s), "=d"(node.c)
-        : "r"(tc.table_s + ((unsigned)(k & (kTrigTableSize - 1)) << 4)));
+    unsigned addr;  // mask, then one multiply-add (the compiler's shift / mask / add is three)
+    asm("mad.lo.u32 %0, %1, 16, %2;" : "=r"(addr) : "r"(k & (kTrigTableSize - 1)), "r"(tc.table_s));
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(node.s), "=d"(node.c) : "r"(addr));
   } else {
     node = tc.table[k & (kTrigTableSize - 1)];
   }
