@@ -365,7 +365,9 @@ def test_host_emulated_ll_matches_oracle(N, pt, sl, kw):
 VARIANTS = ["TJB_TRIM=1", "TJB_PHASE_FIXED=1", "TJB_TRIM=1 TJB_PHASE_FIXED=1",
             "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_TRIG_TABLE=0",
             "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_HALLEY=1",
-            "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_HALLEY=1 TJB_TRIG_TABLE_LOG2=11"]
+            "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_HALLEY=1 TJB_TRIG_TABLE_LOG2=11",
+            "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_HALLEY=1 TJB_TRIG_TABLE_LOG2=11 TJB_EPOCHS_PER_ITER=3",
+            "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_EPOCHS_PER_ITER=4"]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
@@ -396,20 +398,25 @@ def test_host_emulated_tuning_variants(variant):
     # both round the phase x4 + d4 (|x4| ~ 1e5 angle units: ulp ~ 9e-14 rad) differently
     assert worst < 2e-13
     assert worst_orc < 2e-12  # the gate of test_kepler_column_matches_oracle
-    for N, pt, sl in ((64, 1, None), (20, 2, (-2.0, 1.0))):
+    # even / odd epoch counts (the remainder loop after the groups of kEpochsPerIter), L up to 5
+    for N, pt, sl in ((64, 1, None), (20, 2, (-2.0, 1.0)), (33, 1, None), (3, 1, None),
+                      (17, 4, (-2.0, 1.0))):
         spec, _, _ = star_spec(N, pt)
         chunk = prior_chunk(1500, s_lognormal=sl)
         orc = OracleHelper.from_spec(spec)
         truth, _ = orc.truth_ll(chunk)
         got = emu_marginal_ll(spec, chunk, force_jit=sl is not None, variant=variant)
         ref = emu_marginal_ll(spec, chunk, force_jit=sl is not None)
-        assert np.max(rel_err(got, ref)) < 1e-12
-        assert np.max(rel_err(got, truth)) < 1e-10
+        # (differently rounded phases: ~1e-13 rad, times the conditioning of ll)
+        assert np.max(rel_err(got, ref)) < 2e-11, (N, pt)
+        assert np.max(rel_err(got, truth)) < 1e-10, (N, pt)
 
 
 @pytest.mark.parametrize("variant", ["", "TJB_TRIM=1 TJB_PHASE_FIXED=1",
                                      "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_HALLEY=1",
-            "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_HALLEY=1 TJB_TRIG_TABLE_LOG2=11"])
+            "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_HALLEY=1 TJB_TRIG_TABLE_LOG2=11",
+            "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_HALLEY=1 TJB_TRIG_TABLE_LOG2=11 TJB_EPOCHS_PER_ITER=3",
+            "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_EPOCHS_PER_ITER=4"])
 def test_kepler_solver_extreme_cases(variant):
     """e -> 1 at M -> 0, phases beyond the FP32 stage's range (P = 0.05 d over 10 000 d):
     the safeguarded extra passes (kepler.cuh::solve_extra_passes) always converge to a
