@@ -144,6 +144,33 @@ def test_kepler_solver_residual():
         assert abs(E - e * np.sin(E) - M) < 1e-13 * max(1, abs(M))
 
 
+def test_reference_newton_at_extreme_eccentricity():
+    """Where parity with the reference algorithm stops being the right gate: the Newton
+    iteration restated from twobody (start M + e sin M, |dM| < 1e-10, at most 128 steps)
+    does not converge for e -> 1 near pericentre, so the reference's ll is off from the exact
+    value there (by percents), while for e <= 0.999 it is within the 1e-10 gate.  The CUDA
+    path is gated on the quad-precision truth in that corner
+    (test_host_logic.py::test_kepler_solver_extreme_cases, DESIGN.md section 4.1)."""
+    from oracle.oracle import load
+
+    lib = load()
+    rng = np.random.default_rng(0)
+    worst_lo, worst_hi = 0.0, 0.0
+    for _ in range(4000):
+        M = 10 ** rng.uniform(-5, -1) * rng.choice([-1, 1])
+        e_lo, e_hi = rng.uniform(0.9, 0.999), 1 - 10 ** rng.uniform(-7, -4)
+        for e, which in ((e_lo, 0), (e_hi, 1)):
+            E = lib.orc_eccentric_anomaly(M, e, 1e-10, 128, 0)
+            res = abs(E - e * np.sin(E) - M) / (1 - e * np.cos(E))  # ~ distance to the root
+            if which == 0:
+                worst_lo = max(worst_lo, res)
+            else:
+                worst_hi = max(worst_hi, res)
+    assert worst_lo < 1e-9
+    print(f"\nreference Newton, distance to the root: e <= 0.999 {worst_lo:.1e}, e -> 1 {worst_hi:.1e}")
+    assert worst_hi > 1e-6   # documents the failure; the kernel does not share it
+
+
 def test_accept_rule_and_iterative_logic():
     rng = np.random.default_rng(3)
     lls = rng.normal(-50, 3, size=5000)
