@@ -122,6 +122,48 @@ int tjb_marginal_ll_host_soa_resident(TjbHandle *h, const double *h_P, const dou
                                       const double *h_s, double s_const, int64_t n, double *d_ll,
                                       int64_t *d_llmax_key);
 
+/* ---- drawn priors: JokerPrior.sample for the nonlinear parameters (prior.py:297-407) ----
+ * rejection_sample(data, <int>) draws its prior samples first (thejoker.py:215-218).  Here
+ * sample i of the prior is a pure function of (seed, i): a Philox4x32-10 stream per sample,
+ * consumed in the order P, e, omega, M0, s.  The likelihood kernel can therefore generate
+ * the samples in registers (tjb_marginal_ll_generated: the prior never exists in HBM), the
+ * accepted rows are re-generated from their indices (tjb_prior_rows), and any sharding of
+ * the index range over GPUs / ranks yields the same prior.  Distribution kinds: the
+ * families of the reference's default prior and its documented variants --
+ * UniformLog (distributions.py:17-51), Beta (Kipping13*, distributions.py:155-176),
+ * uniform angles (prior.py:437, 469-472), constant / LogNormal / Normal jitter. */
+enum {
+  TJB_PRIOR_CONSTANT = 0,   /* p0 */
+  TJB_PRIOR_UNIFORM = 1,    /* U(p0, p1) */
+  TJB_PRIOR_UNIFORMLOG = 2, /* exp(U(ln p0, ln p1)) */
+  TJB_PRIOR_BETA = 3,       /* Beta(p0, p1) */
+  TJB_PRIOR_LOGNORMAL = 4,  /* exp(N(p0, p1)) */
+  TJB_PRIOR_NORMAL = 5      /* N(p0, p1) */
+};
+typedef struct TjbPriorDist {
+  int32_t kind;
+  int32_t reserved;
+  double p0, p1;
+  double scale; /* multiplies the draw: unit conversion into [day, -, rad, rad, rv unit] */
+} TjbPriorDist;
+typedef struct TjbPriorGen {
+  TjbPriorDist par[5]; /* P, e, omega, M0, s */
+  uint64_t seed;
+} TjbPriorGen;
+/* columns of the samples with global indices [index0, index0 + n) into device arrays on
+ * `device` (any may be NULL); asynchronous on `cuda_stream`; needs no handle */
+int tjb_prior_sample(int device, void *cuda_stream, const TjbPriorGen *gen, int64_t index0,
+                     int64_t n, double *d_P, double *d_e, double *d_omega, double *d_M0,
+                     double *d_s);
+/* packed rows h_rows[k, 5] = [P, e, omega, M0, s] of the samples with the given global
+ * indices (host in, host out) */
+int tjb_prior_rows(TjbHandle *h, const TjbPriorGen *gen, const int64_t *h_idx, int64_t k,
+                   double *h_rows);
+/* batch_marginal_ln_likelihood (pyx:428-469) over the generated samples
+ * [index0, index0 + n): as tjb_marginal_ll_soa, without any prior array */
+int tjb_marginal_ll_generated(TjbHandle *h, const TjbPriorGen *gen, int64_t index0, int64_t n,
+                              double *d_ll, int64_t *d_llmax_key);
+
 /* ---- accept step (likelihood_helpers.py:107-109; multiproc_helpers.py:256-258) */
 int tjb_llmax_reset(TjbHandle *h, int64_t *d_llmax_key);
 /* max-update *d_llmax_key with d_ll[0..n) (for ll arrays not produced above) */

@@ -78,7 +78,7 @@ def host_emulation(variant=""):
         src = os.path.join(ROOT, "tools", "host_emulation.cpp")
         deps = [src] + [os.path.join(ROOT, "thejoker_b200", "csrc", f) for f in
                         ("kepler.cuh", "linalg.cuh", "marginal_ll.cuh", "star_tables.hpp",
-                         "accept.cuh")]
+                         "accept.cuh", "prior_gen.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared",
                             "-ffp-contract=off"] + defs + [src, "-o", so], check=True)
@@ -97,6 +97,11 @@ def host_emulation(variant=""):
         lib.emu_pcg64_double.restype = ctypes.c_double
         lib.emu_pcg64_double.argtypes = [ctypes.c_ulonglong] * 5
         lib.emu_sincos_rev.argtypes = [ctypes.c_double, dp, dp]
+        up = ctypes.POINTER(ctypes.c_uint)
+        lib.emu_philox4x32_10.argtypes = [up, up, up]
+        lib.emu_prior_rows.argtypes = [ctypes.POINTER(ctypes.c_int), dp, dp, dp, ctypes.c_ulonglong,
+                                       ctypes.c_longlong, ctypes.c_long, dp]
+        lib.emu_prior_uniforms.argtypes = [ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.c_int, dp]
         _emu[variant] = lib
     return _emu[variant]
 
@@ -116,6 +121,18 @@ def emu_marginal_ll(spec, chunk, force_jit=False, variant=""):
                              int(force_jit), p(chunk), len(chunk), ll.ctypes.data_as(dp))
     assert rc == 0
     return ll
+
+
+def emu_prior_rows(gen, index0, n):
+    """Host build of csrc/prior_gen.cuh: rows [P, e, omega, M0, s] of the generated prior
+    samples index0 .. index0 + n for a ``_lib.TjbPriorGen`` (JokerPrior.device_generator)."""
+    lib = host_emulation()
+    kind = (ctypes.c_int * 5)(*[gen.par[k].kind for k in range(5)])
+    arr = lambda f: (ctypes.c_double * 5)(*[getattr(gen.par[k], f) for k in range(5)])
+    rows = np.zeros((int(n), 5))
+    lib.emu_prior_rows(kind, arr("p0"), arr("p1"), arr("scale"), gen.seed, int(index0), int(n),
+                       rows.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    return rows
 
 
 def rel_err(a, b):

@@ -775,32 +775,64 @@ def test_large_n_properties(torch_cuda):
 
 
 def test_device_prior_sampling(torch_cuda):
-    """rejection_sample(data, prior_samples=<int>): the prior is drawn on the GPU
-    (SURVEY.md section 8 f2).  Distribution checks against the host sampler, determinism,
-    logprobs, and a jitter prior that is not constant."""
+    """rejection_sample(data, prior_samples=<int>): the prior is drawn on the GPU by the
+    library's counter-based sampler (csrc/prior_gen.cuh).  The
+    CUDA sampler against its host build and against scipy's distributions; the likelihood
+    kernel that generates the samples in registers against the same kernel reading the
+    materialised columns (bit-equal); determinism; logprobs; a non-constant jitter prior."""
+    from scipy import stats
+
     import thejoker_b200 as tj
-    from helpers import default_prior
+    from helpers import default_prior, emu_prior_rows
     from thejoker_b200 import units as u
     from thejoker_b200.prior import LogNormal
     from thejoker_b200.synthetic import make_data
 
+    torch = torch_cuda
     prior = default_prior(1, sigma_K0=25.0, P_min=5.0, P_max=500.0)
-    cols, s, lp = prior.sample_device(400_000, "cuda:0", 1234, u.km / u.s, return_logprobs=True)
-    host = prior.sample(size=400_000, rng=np.random.default_rng(0), return_logprobs=True)
-    P, e = cols[0].cpu().numpy(), cols[1].cpu().numpy()
+    n = 400_000
+    cols, s, lp = prior.sample_device(n, "cuda:0", 1234, u.km / u.s, return_logprobs=True)
+    dev = np.stack([c.cpu().numpy() for c in cols], axis=1)
+    P, e = dev[:, 0], dev[:, 1]
     assert s == 0.0 and P.min() >= 5 and P.max() <= 500 and e.min() > 0 and e.max() < 1
-    for dev, hst in ((np.log(P), np.log(host["P"].value)), (e, host["e"].value),
-                     (cols[2].cpu().numpy(), host["omega"].value)):
-        q = [0.01, 0.1, 0.25, 0.5, 0.75, 0.9, 0.99]
-        assert np.allclose(np.quantile(dev, q), np.quantile(hst, q), rtol=0.03, atol=0.02)
-    # ln_prior on the device equals the host formula at the same points
-    dev_samples = tj.JokerSamples()
-    lp_host = (prior.pars["P"].logp(P) + prior.pars["e"].logp(e)
-               + prior.pars["omega"].logp(cols[2].cpu().numpy())
-               + prior.pars["M0"].logp(cols[3].cpu().numpy()))
-    assert np.allclose(lp.cpu().numpy(), lp_host, rtol=1e-12, atol=1e-12)
+    # the same (seed, index) -> the same sample as the host build of the sampler (libm vs
+    # CUDA log / exp / sincospi differ by ulps; an accept decision of the gamma sampler
+    # can flip on such a difference once in ~1e15 draws)
+    host = emu_prior_rows(prior.device_generator(1234, u.km / u.s), 0, n)
+    assert np.max(np.abs(dev - host[:, :4]) / np.maximum(np.abs(host[:, :4]), 1e-300)) < 1e-12
+    assert stats.kstest(np.log(P), stats.uniform(np.log(5), np.log(100)).cdf).pvalue > 1e-3
+    assert stats.kstest(e, stats.beta(0.867, 3.03).cdf).pvalue > 1e-3
+    for j in (2, 3):
+        assert stats.kstest(dev[:, j], stats.uniform(-np.pi, 2 * np.pi).cdf).pvalue > 1e-3
+    # a window of the index range is the same samples
+    cols2, _, _ = prior.sample_device(1000, "cuda:0", 1234, u.km / u.s, index0=77_000)
+    assert np.array_equal(cols2[1].cpu().numpy(), e[77_000:78_000])
+    lp_host = (prior.pars["P"].logp(P) + prior.pars["e"].logp(e) + prior.pars["omega"].logp(dev[:, 2])
+               + prior.pars["M0"].logp(dev[:, 3]))
+    assert np.allclose(lp, lp_host, rtol=1e-12, atol=1e-12)
 
+    # generated-in-kernel ll == ll over the materialised columns, bit for bit; constant
+    # jitter (folded into the table) and a LogNormal jitter in m/s (per-sample kernel)
     flat, _ = make_data(8, rng=np.random.default_rng(11), K=1e-4)
+    prior_s = default_prior(1, sigma_K0=25.0, P_min=5.0, P_max=500.0,
+                            s=LogNormal("s", np.log(200.0), 0.5, u.m / u.s))
+    for pr in (prior, prior_s):
+        helper = tj.TheJoker(pr, devices=[0])._make_joker_helper(flat)
+        gen = pr.device_generator(99, helper.internal_units["s"])
+        m, i0 = 100_003, 5_000_000_000  # a window beyond 2^32: the counter is 64-bit
+        c, sv, _ = pr.sample_device(m, "cuda:0", 99, helper.internal_units["s"], index0=i0)
+        key_a, key_b = helper.new_llmax_key(), helper.new_llmax_key()
+        ll_a = helper.marginal_ll_generated(gen, i0, m, llmax_key=key_a)
+        ll_b = helper.marginal_ll_soa(*c, s=None if not hasattr(sv, "shape") else sv,
+                                      s_const=sv if not hasattr(sv, "shape") else 0.0,
+                                      llmax_key=key_b)
+        assert torch.equal(ll_a, ll_b) and torch.equal(key_a, key_b)
+        idx = np.array([0, 17, m - 1], dtype=np.int64) + i0
+        rows = helper.prior_rows(gen, idx)
+        assert np.array_equal(rows[:, 1], c[1].cpu().numpy()[idx - i0])
+        if hasattr(sv, "shape"):
+            assert np.array_equal(rows[:, 4], sv.cpu().numpy()[idx - i0])
+
     runs = []
     for _ in range(2):
         joker = tj.TheJoker(prior, rng=np.random.default_rng(5))
@@ -808,11 +840,20 @@ def test_device_prior_sampling(torch_cuda):
                                      return_logprobs=True)
         runs.append(smp)
         assert 10 < len(smp) <= 128 and np.isfinite(smp["ln_prior"].value).all()
+        assert np.isfinite(smp["ln_likelihood"].value).all()
     assert np.array_equal(runs[0]["P"].value, runs[1]["P"].value)
     assert np.array_equal(runs[0]["K"].value, runs[1]["K"].value)
+    # the accepted set is what the materialised path accepts with the same uniforms
+    joker = tj.TheJoker(prior, rng=np.random.default_rng(5))
+    seed = int(np.random.default_rng(5).integers(0, 2**62))
+    c, sv, _ = prior.sample_device(1 << 18, "cuda:0", seed, u.km / u.s)
+    chunk = np.stack([t.cpu().numpy() for t in c] + [np.zeros(1 << 18)], axis=1)
+    rng = np.random.default_rng(5)
+    rng.integers(0, 2**62)
+    smp_b = tj.TheJoker(prior, rng=rng).rejection_sample(flat, chunk, max_posterior_samples=128,
+                                                         in_memory=True)
+    assert np.array_equal(runs[0]["P"].value, smp_b["P"].value)
     # non-constant jitter prior, in m/s, through the per-sample-jitter kernel
-    prior_s = default_prior(1, sigma_K0=25.0, P_min=5.0, P_max=500.0,
-                            s=LogNormal("s", np.log(200.0), 0.5, u.m / u.s))
     smp = tj.TheJoker(prior_s, rng=np.random.default_rng(5)).rejection_sample(flat, 1 << 16)
     sv = smp["s"].to_value(u.km / u.s)
     assert len(smp) > 10 and 0.02 < np.median(sv) < 2.0

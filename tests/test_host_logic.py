@@ -838,3 +838,78 @@ def test_conditioning_at_the_posterior_mode(sigma):
     assert np.median(e_emu) <= 3 * np.median(e_ref) + 1e-14
     assert e_emu.max() <= 5 * e_ref.max() + 1e-13
     assert e_emu.max() < 3e-16 * np.median(kappa)
+
+
+# ---- counter-based prior sampler (csrc/prior_gen.cuh, host build) ---------------------------
+def test_philox_known_answers():
+    """Philox4x32-10 against the known-answer vectors of the Random123 distribution
+    (kat_vectors: zero, all-ones and the digits-of-pi counter / key)."""
+    lib = host_emulation()
+    kat = [([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+           ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+           ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+            [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for ctr, key, want in kat:
+        out = (ctypes.c_uint * 4)()
+        lib.emu_philox4x32_10((ctypes.c_uint * 4)(*ctr), (ctypes.c_uint * 2)(*key), out)
+        assert list(out) == want
+
+
+def test_prior_generator_distributions():
+    """The generated prior against scipy's distributions (KS), for the reference's default
+    prior (UniformLog P, Kipping13Global e, uniform angles; distributions.py:17-51, 171-176;
+    prior.py:437-479) and a LogNormal jitter in m/s converted to km/s; independence of
+    the columns; and the contract that sample g depends only on (seed, g)."""
+    from scipy import stats
+
+    from helpers import emu_prior_rows
+    from thejoker_b200.prior import LogNormal
+
+    prior = default_prior(1, sigma_K0=25.0, P_min=2.0, P_max=1024.0,
+                          s=LogNormal("s", np.log(200.0), 0.5, u.m / u.s))
+    gen = prior.device_generator(987654321, u.km / u.s)
+    n = 200_000
+    rows = emu_prior_rows(gen, 0, n)
+    assert rows[:, 0].min() >= 2 and rows[:, 0].max() <= 1024
+    assert rows[:, 1].min() > 0 and rows[:, 1].max() < 1
+    assert np.abs(rows[:, 2:4]).max() <= np.pi
+    pv = [stats.kstest(np.log(rows[:, 0]), stats.uniform(np.log(2), np.log(512)).cdf).pvalue,
+          stats.kstest(rows[:, 1], stats.beta(0.867, 3.03).cdf).pvalue,
+          stats.kstest(rows[:, 2], stats.uniform(-np.pi, 2 * np.pi).cdf).pvalue,
+          stats.kstest(rows[:, 3], stats.uniform(-np.pi, 2 * np.pi).cdf).pvalue,
+          stats.kstest(np.log(rows[:, 4] * 1e3), stats.norm(np.log(200.0), 0.5).cdf).pvalue]
+    assert min(pv) > 1e-3, pv
+    cc = np.corrcoef(rows.T)
+    assert np.abs(cc - np.eye(5)).max() < 0.01
+    # any window of the index range reproduces the same samples; another seed does not
+    assert np.array_equal(emu_prior_rows(gen, 12345, 100), rows[12345:12445])
+    gen2 = prior.device_generator(987654322, u.km / u.s)
+    assert not np.any(emu_prior_rows(gen2, 0, 100) == rows[:100])
+    # the other Beta shapes of the reference (a >= 1 takes the unboosted gamma)
+    from thejoker_b200.prior import Kipping13Long, Kipping13Short
+
+    for cls, (a, b) in ((Kipping13Long, (1.12, 3.09)), (Kipping13Short, (0.697, 3.27))):
+        pr = default_prior(1, sigma_K0=25.0, pars={"e": cls("e")})
+        e = emu_prior_rows(pr.device_generator(5, u.km / u.s), 0, 100_000)[:, 1]
+        assert stats.kstest(e, stats.beta(a, b).cdf).pvalue > 1e-3
+    # a family without a device sampler -> no generator (the caller samples on the host)
+    from thejoker_b200.prior import Distribution
+
+    class Odd(Distribution):
+        def draw(self, rng, size, **ctx):
+            return rng.uniform(size=size)
+
+    assert default_prior(1, sigma_K0=25.0, pars={"e": Odd("e", u.one)}).device_generator(1, u.km / u.s) is None
+
+
+def test_prior_generator_ln_prior_rows():
+    """ln_prior_rows (prior.py:388-400 restated for packed rows in internal units) equals
+    the per-parameter logp sum of JokerPrior.sample(return_logprobs=True)."""
+    from thejoker_b200.prior import LogNormal
+
+    prior = default_prior(1, sigma_K0=25.0, s=LogNormal("s", np.log(200.0), 0.5, u.m / u.s))
+    smp = prior.sample(size=1000, rng=np.random.default_rng(3), return_logprobs=True)
+    rows = np.stack([smp["P"].to_value(u.day), smp["e"].value, smp["omega"].to_value(u.rad),
+                     smp["M0"].to_value(u.rad), smp["s"].to_value(u.km / u.s)], axis=1)
+    assert np.allclose(prior.ln_prior_rows(rows, u.km / u.s), smp["ln_prior"].value, rtol=1e-12,
+                       atol=1e-12)

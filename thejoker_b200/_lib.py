@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TJB_LIB_PATH", os.path.join(_HERE, "libthejoker_b200.so"))  # override: tuning builds
 _SRC = [os.path.join(_HERE, "csrc", f) for f in
         ("tjb_api.cu", "kepler.cuh", "linalg.cuh", "marginal_ll.cuh", "accept.cuh", "posterior.cuh",
-         "star_tables.hpp")]
+         "prior_gen.cuh", "star_tables.hpp")]
 _HDR = os.path.join(os.path.dirname(_HERE), "include", "thejoker_b200.h")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -47,6 +47,15 @@ class TjbSpec(ctypes.Structure):
 class TjbPcg64(ctypes.Structure):
     _fields_ = [("state_hi", ctypes.c_uint64), ("state_lo", ctypes.c_uint64),
                 ("inc_hi", ctypes.c_uint64), ("inc_lo", ctypes.c_uint64)]
+
+
+class TjbPriorDist(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("reserved", ctypes.c_int32), ("p0", ctypes.c_double),
+                ("p1", ctypes.c_double), ("scale", ctypes.c_double)]
+
+
+class TjbPriorGen(ctypes.Structure):
+    _fields_ = [("par", TjbPriorDist * 5), ("seed", ctypes.c_uint64)]
 
 
 class TjbMultiStarJob(ctypes.Structure):
@@ -95,6 +104,11 @@ SYMBOLS = {
     "tjb_marginal_ll_host_soa_resident": (ctypes.c_int, [_H, _vp, _vp, _vp, _vp, _vp,
                                                          ctypes.c_double, ctypes.c_int64, _vp,
                                                          _vp]),
+    "tjb_prior_sample": (ctypes.c_int, [ctypes.c_int, _vp, ctypes.POINTER(TjbPriorGen),
+                                        ctypes.c_int64, ctypes.c_int64, _vp, _vp, _vp, _vp, _vp]),
+    "tjb_prior_rows": (ctypes.c_int, [_H, ctypes.POINTER(TjbPriorGen), _vp, ctypes.c_int64, _vp]),
+    "tjb_marginal_ll_generated": (ctypes.c_int, [_H, ctypes.POINTER(TjbPriorGen), ctypes.c_int64,
+                                                 ctypes.c_int64, _vp, _vp]),
     "tjb_llmax_reset": (ctypes.c_int, [_H, _vp]),
     "tjb_llmax_update": (ctypes.c_int, [_H, _vp, ctypes.c_int64, _vp]),
     "tjb_llmax_get": (ctypes.c_int, [_H, _vp, _dp]),

@@ -8,6 +8,7 @@
 #pragma once
 
 #include "linalg.cuh"
+#include "prior_gen.cuh"
 
 namespace tjb {
 
@@ -20,6 +21,15 @@ struct PriorView {
   // *nonuniform (optimistic execution; the caller then reruns per-sample jitter)
   double s_expect;
   int *nonuniform;
+};
+
+// The third source of prior samples: none in memory at all.  Sample i of a launch is
+// generated in registers from (gen.seed, index0 + i) by the counter-based sampler of
+// prior_gen.cuh (kGen kernels), so a prior that is drawn -- rejection_sample(data, <int>),
+// thejoker.py:215-218 -- costs no HBM traffic and no HBM capacity.
+struct PriorGenView {
+  PriorGenSpec gen;
+  long long index0;
 };
 
 // Per-star constants.  Passed by value as a kernel parameter (constant bank).
@@ -294,10 +304,32 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab,
 #endif
 constexpr int kLLThreads = TJB_LL_THREADS;
 
-template <int L, bool kJit>
+// what varies between the two kernels below: where a sample's parameters come from
+template <bool kJit>
+TJB_D void load_sample(const PriorView &pv, long long ii, double &P, double &e, double &om,
+                       double &M0, double &s) {
+  if (pv.aos) {
+    const double *r = pv.aos + 5 * ii;
+    P = r[0]; e = r[1]; om = r[2]; M0 = r[3]; s = r[4];
+    if (!kJit && pv.nonuniform && s != pv.s_expect) atomicOr(pv.nonuniform, 1);
+  } else {
+    P = pv.P[ii]; e = pv.e[ii]; om = pv.omega[ii]; M0 = pv.M0[ii];
+    s = (kJit && pv.s) ? pv.s[ii] : 0.0;
+  }
+}
+template <bool kJit>
+TJB_D void load_sample(const PriorGenView &pv, long long ii, double &P, double &e, double &om,
+                       double &M0, double &s) {
+  double row[5];
+  prior_row(pv.gen, (unsigned long long)(pv.index0 + ii), row);
+  P = row[0]; e = row[1]; om = row[2]; M0 = row[3];
+  s = kJit ? row[4] : 0.0;
+}
+
+template <int L, bool kJit, typename View>
 __global__ void __launch_bounds__(kLLThreads, TJB_LL_MIN_CTAS)
-marginal_ll_kernel(const __grid_constant__ StarParams sp, const PriorView pv, const long long n,
-                   double *__restrict__ ll_out, const MaxKeys mk) {
+marginal_ll_kernel(const __grid_constant__ StarParams sp, const View pv,
+                   const long long n, double *__restrict__ ll_out, const MaxKeys mk) {
   // dynamic shared memory: [trig table (16 KB, 16-byte aligned) | epoch table]
   extern __shared__ SinCos smem_trig[];
   double *tab = reinterpret_cast<double *>(smem_trig + kTrigTableSize);
@@ -314,14 +346,7 @@ marginal_ll_kernel(const __grid_constant__ StarParams sp, const PriorView pv, co
     const bool valid = i < n;
     const long long ii = valid ? i : n - 1;
     double P, e, om, M0, s;
-    if (pv.aos) {
-      const double *r = pv.aos + 5 * ii;
-      P = r[0]; e = r[1]; om = r[2]; M0 = r[3]; s = r[4];
-      if (!kJit && pv.nonuniform && s != pv.s_expect) atomicOr(pv.nonuniform, 1);
-    } else {
-      P = pv.P[ii]; e = pv.e[ii]; om = pv.omega[ii]; M0 = pv.M0[ii];
-      s = (kJit && pv.s) ? pv.s[ii] : 0.0;
-    }
+    load_sample<kJit>(pv, ii, P, e, om, M0, s);
     const double v = sample_ll<L, kJit>(sp, tab, smem_trig, P, e, om, M0, s);
     if (valid) {
       ll_out[i] = v;

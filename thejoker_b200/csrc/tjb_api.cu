@@ -200,10 +200,10 @@ int build_jit_table(TjbHandle *h) {
 
 // ---- kernel dispatch ---------------------------------------------------------
 
-template <int L, bool J>
-int launch_ll(TjbHandle *h, const StarParams &sp, const PriorView &pv, long long n, double *d_ll,
+template <int L, bool J, typename View>
+int launch_ll(TjbHandle *h, const StarParams &sp, const View &pv, long long n, double *d_ll,
               long long *d_key, cudaStream_t stream) {
-  auto kern = marginal_ll_kernel<L, J>;
+  auto kern = marginal_ll_kernel<L, J, View>;
   const size_t smem = (size_t)kTrigTableSize * sizeof(SinCos) +
                       (size_t)h->N * row_stride(L) * sizeof(double);
   if (smem > 227 * 1024)
@@ -227,8 +227,8 @@ int launch_ll(TjbHandle *h, const StarParams &sp, const PriorView &pv, long long
   return TJB_OK;
 }
 
-template <bool J>
-int dispatch_ll(TjbHandle *h, const StarParams &sp, const PriorView &pv, long long n, double *d_ll,
+template <bool J, typename View>
+int dispatch_ll(TjbHandle *h, const StarParams &sp, const View &pv, long long n, double *d_ll,
                 long long *d_key, cudaStream_t stream) {
   switch (h->L) {
     case 1: return launch_ll<1, J>(h, sp, pv, n, d_ll, d_key, stream);
@@ -245,7 +245,8 @@ int dispatch_ll(TjbHandle *h, const StarParams &sp, const PriorView &pv, long lo
 
 // choose the kernel: a single jitter value for the whole call is folded into the
 // table (constant-jitter kernel); otherwise the per-sample-jitter kernel runs.
-int run_ll(TjbHandle *h, const PriorView &pv, bool uniform_s, double s_const, long long n,
+template <typename View>
+int run_ll(TjbHandle *h, const View &pv, bool uniform_s, double s_const, long long n,
            double *d_ll, long long *d_key, cudaStream_t stream) {
   if (n <= 0) return TJB_OK;
   CU(cudaSetDevice(h->device));
@@ -726,6 +727,91 @@ int tjb_marginal_ll_host_soa_resident(TjbHandle *h, const double *h_P, const dou
   if (!d_ll) return fail(TJB_E_INVALID, "null device pointer");
   const double *cols[5] = {h_P, h_e, h_omega, h_M0, h_s};
   return host_soa_stream(h, cols, h_s ? 5 : 4, s_const, n, nullptr, d_ll, d_llmax_key);
+}
+
+// ---- drawn priors (prior_gen.cuh) ---------------------------------------------------
+
+namespace {
+
+int make_gen(const TjbPriorGen *gen, PriorGenSpec &ps) {
+  if (!gen) return fail(TJB_E_INVALID, "null prior generator");
+  for (int k = 0; k < 5; k++) {
+    const TjbPriorDist &d = gen->par[k];
+    if (d.kind < kPriorConstant || d.kind > kPriorNormal)
+      return fail(TJB_E_INVALID, "unknown prior distribution kind");
+    if (d.kind == kPriorUniformLog && !(d.p0 > 0.0 && d.p0 < d.p1))
+      return fail(TJB_E_INVALID, "UniformLog needs 0 < a < b");
+    if (d.kind == kPriorBeta && !(d.p0 > 0.0 && d.p1 > 0.0))
+      return fail(TJB_E_INVALID, "Beta needs positive shape parameters");
+    if ((d.kind == kPriorNormal || d.kind == kPriorLogNormal) && !(d.p1 >= 0.0))
+      return fail(TJB_E_INVALID, "negative sigma");
+    ps.par[k].kind = d.kind;
+    ps.par[k].p0 = d.p0;
+    ps.par[k].p1 = d.p1;
+    ps.par[k].scale = d.scale;
+  }
+  ps.seed = gen->seed;
+  return TJB_OK;
+}
+
+}  // namespace
+
+int tjb_prior_sample(int device, void *cuda_stream, const TjbPriorGen *gen, int64_t index0,
+                     int64_t n, double *d_P, double *d_e, double *d_omega, double *d_M0,
+                     double *d_s) {
+  if (n < 0 || index0 < 0) return fail(TJB_E_INVALID, "negative n / index0");
+  PriorGenSpec ps;
+  int rc = make_gen(gen, ps);
+  if (rc || n == 0) return rc;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1)
+    return fail(TJB_E_CUDA, "no CUDA device available: libthejoker_b200 has no CPU path");
+  if (device < 0 || device >= n_dev) return fail(TJB_E_INVALID, "device index out of range");
+  CU(cudaSetDevice(device));
+  int n_sm = 0;
+  CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)n_sm * 8);
+  prior_sample_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(ps, index0, n, d_P, d_e, d_omega,
+                                                                  d_M0, d_s);
+  CU(cudaGetLastError());
+  return TJB_OK;
+}
+
+int tjb_prior_rows(TjbHandle *h, const TjbPriorGen *gen, const int64_t *h_idx, int64_t k,
+                   double *h_rows) {
+  if (!h) return fail(TJB_E_INVALID, "null handle");
+  if (k < 0 || k > (1 << 30)) return fail(TJB_E_INVALID, "bad row count");
+  PriorGenSpec ps;
+  int rc = make_gen(gen, ps);
+  if (rc || k == 0) return rc;
+  if (!h_idx || !h_rows) return fail(TJB_E_INVALID, "null host pointer");
+  CU(cudaSetDevice(h->device));
+  if (h->misc.ensure((size_t)k * 6 * sizeof(double))) return fail(TJB_E_NOMEM, "cudaMalloc");
+  long long *d_idx = (long long *)h->misc.p;
+  double *d_rows = (double *)h->misc.p + k;
+  CU(cudaMemcpyAsync(d_idx, h_idx, (size_t)k * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+  prior_rows_kernel<<<(int)((k + 127) / 128), 128, 0, h->stream>>>(ps, d_idx, (int)k, d_rows);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(h_rows, d_rows, (size_t)k * 5 * sizeof(double), cudaMemcpyDeviceToHost,
+                     h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return TJB_OK;
+}
+
+int tjb_marginal_ll_generated(TjbHandle *h, const TjbPriorGen *gen, int64_t index0, int64_t n,
+                              double *d_ll, int64_t *d_llmax_key) {
+  if (!h) return fail(TJB_E_INVALID, "null handle");
+  if (n < 0 || index0 < 0) return fail(TJB_E_INVALID, "negative n / index0");
+  PriorGenView pv;
+  int rc = make_gen(gen, pv.gen);
+  if (rc || n == 0) return rc;
+  if (!d_ll) return fail(TJB_E_INVALID, "null device pointer");
+  pv.index0 = index0;
+  // a constant jitter prior (the default, prior.py:476-479) is folded into the epoch table
+  const PriorDist &ds = pv.gen.par[4];
+  const bool uniform_s = ds.kind == kPriorConstant;
+  return run_ll(h, pv, uniform_s, uniform_s ? ds.p0 * ds.scale : 0.0, n, d_ll,
+                (long long *)d_llmax_key, h->stream);
 }
 
 // ---- accept -----------------------------------------------------------------

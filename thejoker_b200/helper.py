@@ -419,6 +419,35 @@ class CJokerHelper:
                                                  self._ptr(llmax_key)))
         return out
 
+    def marginal_ll_generated(self, gen, index0, n, out=None, llmax_key=None):
+        """ll of the prior samples with global indices [index0, index0 + n) of the
+        counter-based generator ``gen`` (JokerPrior.device_generator): the likelihood
+        kernel draws each sample in registers, no prior array exists.  Asynchronous on
+        torch's current stream."""
+        import torch
+
+        if out is None:
+            out = torch.empty(int(n), dtype=torch.float64, device=f"cuda:{self.device}")
+        self._check_dev(out, torch.float64, "out")
+        if out.numel() != int(n):
+            raise ValueError("out has the wrong length")
+        self._sync_stream()
+        _lib.check(self._lib.tjb_marginal_ll_generated(self._h, ctypes.byref(gen), int(index0),
+                                                       int(n), self._ptr(out),
+                                                       self._ptr(llmax_key)))
+        return out
+
+    def prior_rows(self, gen, idx):
+        """Packed (k, 5) host rows [P, e, omega, M0, s] (internal units) of the generated
+        prior samples with the given global indices."""
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        rows = np.empty((len(idx), 5))
+        if len(idx):
+            self._sync_stream()
+            _lib.check(self._lib.tjb_prior_rows(self._h, ctypes.byref(gen), _vp(idx), len(idx),
+                                                _vp(rows)))
+        return rows
+
     def marginal_ll_host_columns(self, P, e, omega, M0, s=None, s_const=0.0, out=None,
                                  llmax_key=None):
         """ll for HOST columns (numpy / memory-mapped, internal units), left on the device
@@ -520,3 +549,20 @@ class CJokerHelper:
         v = [ctypes.c_int() for _ in range(4)]
         _lib.check(self._lib.tjb_device_info(self._h, *[ctypes.byref(x) for x in v]))
         return dict(n_sm=v[0].value, ctas_per_sm=v[1].value, cc=(v[2].value, v[3].value))
+
+
+def prior_sample_device(gen, index0, n, device, with_s=True):
+    """Columns [P, e, omega, M0(, s)] of the generated prior samples with global indices
+    [index0, index0 + n) as float64 CUDA tensors on ``device`` (tjb_prior_sample; no star
+    handle needed).  Asynchronous on torch's current stream."""
+    import torch
+
+    lib = _lib.load()
+    with torch.cuda.device(device):
+        cols = [torch.empty(int(n), dtype=torch.float64, device=f"cuda:{device}")
+                for _ in range(5 if with_s else 4)]
+        st = torch.cuda.current_stream(device).cuda_stream
+        ptrs = [ctypes.c_void_p(c.data_ptr()) for c in cols] + ([] if with_s else [None])
+        _lib.check(lib.tjb_prior_sample(int(device), ctypes.c_void_p(st), ctypes.byref(gen),
+                                        int(index0), int(n), *ptrs))
+    return cols

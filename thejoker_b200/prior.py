@@ -20,6 +20,9 @@ __all__ = ["JokerPrior", "Normal", "FixedCompanionMass", "UniformLog", "Uniform"
            "Kipping13Global", "Kipping13Long", "Kipping13Short", "Constant", "LogNormal"]
 
 
+# distribution kinds of the library's prior sampler (include/thejoker_b200.h TJB_PRIOR_*)
+PRIOR_CONSTANT, PRIOR_UNIFORM, PRIOR_UNIFORMLOG, PRIOR_BETA, PRIOR_LOGNORMAL, PRIOR_NORMAL = range(6)
+
 # ----------------------------------------------------------------------------
 # distributions
 
@@ -37,11 +40,9 @@ class Distribution:
     def logp(self, value, **ctx):
         raise NotImplementedError
 
-    # device-side counterparts (torch CUDA generator); None -> not supported on device
-    def draw_device(self, gen, size, device):
-        return None
-
-    def logp_device(self, value):
+    def device_spec(self):
+        """(kind, p0, p1) for the library's counter-based sampler (include/thejoker_b200.h
+        TJB_PRIOR_*, csrc/prior_gen.cuh), or None: no device sampler for this family."""
         return None
 
 
@@ -61,6 +62,9 @@ class Normal(Distribution):
 
     def draw(self, rng, size, **ctx):
         return rng.normal(self.mu, self.sigma, size=size)
+
+    def device_spec(self):
+        return (PRIOR_NORMAL, self.mu, self.sigma) if type(self) is Normal else None
 
     def logp(self, value, **ctx):
         return -0.5 * (np.log(2 * np.pi * self.sigma**2) + ((value - self.mu) / self.sigma) ** 2)
@@ -112,17 +116,8 @@ class UniformLog(Distribution):
         fac = np.log(self.b) - np.log(self.a)
         return np.exp(rng.uniform(size=size) * fac + np.log(self.a))  # distributions.py:25-28
 
-    def draw_device(self, gen, size, device):
-        import torch
-
-        fac = np.log(self.b) - np.log(self.a)
-        uu = torch.rand(size, dtype=torch.float64, device=device, generator=gen)
-        return torch.exp(uu * fac + np.log(self.a))
-
-    def logp_device(self, value):
-        import torch
-
-        return -torch.log(value) - np.log(np.log(self.b) - np.log(self.a))
+    def device_spec(self):
+        return (PRIOR_UNIFORMLOG, self.a, self.b)
 
     def logp(self, value, **ctx):
         # normalised density of 1/x on (a,b).  (distributions.py:44-46 writes
@@ -138,16 +133,8 @@ class Uniform(Distribution):
     def draw(self, rng, size, **ctx):
         return rng.uniform(self.lower, self.upper, size=size)
 
-    def draw_device(self, gen, size, device):
-        import torch
-
-        uu = torch.rand(size, dtype=torch.float64, device=device, generator=gen)
-        return uu * (self.upper - self.lower) + self.lower
-
-    def logp_device(self, value):
-        import torch
-
-        return torch.full_like(value, -np.log(self.upper - self.lower))
+    def device_spec(self):
+        return (PRIOR_UNIFORM, self.lower, self.upper)
 
     def logp(self, value, **ctx):
         return np.full(np.shape(value), -np.log(self.upper - self.lower))
@@ -169,24 +156,8 @@ class Beta(Distribution):
     def draw(self, rng, size, **ctx):
         return rng.beta(self.alpha, self.beta, size=size)
 
-    def draw_device(self, gen, size, device):
-        import torch
-
-        # Beta(a, b) = Ga / (Ga + Gb); torch's CUDA gamma sampler has no generator
-        # argument, so it is driven by a seed drawn from `gen`
-        seed = int(torch.randint(0, 2**62, (1,), device=device, generator=gen).item())
-        with torch.random.fork_rng(devices=[torch.device(device)]):
-            torch.manual_seed(seed)
-            ga = torch._standard_gamma(torch.full((size,), self.alpha, dtype=torch.float64, device=device))
-            gb = torch._standard_gamma(torch.full((size,), self.beta, dtype=torch.float64, device=device))
-        return (ga / (ga + gb)).clamp_(1e-300, 1.0 - 1e-16)
-
-    def logp_device(self, value):
-        import torch
-        from math import lgamma
-
-        lB = lgamma(self.alpha) + lgamma(self.beta) - lgamma(self.alpha + self.beta)
-        return (self.alpha - 1) * torch.log(value) + (self.beta - 1) * torch.log1p(-value) - lB
+    def device_spec(self):
+        return (PRIOR_BETA, self.alpha, self.beta)
 
     def logp(self, value, **ctx):
         from math import lgamma
@@ -219,11 +190,8 @@ class Constant(Distribution):
     def draw(self, rng, size, **ctx):
         return np.full(size, self.value)
 
-    def draw_device(self, gen, size, device):
-        return self.value  # a scalar: the engine folds a constant jitter into the epoch table
-
-    def logp_device(self, value):
-        return 0.0
+    def device_spec(self):
+        return (PRIOR_CONSTANT, self.value, 0.0)
 
     def logp(self, value, **ctx):
         return np.zeros(np.shape(value))
@@ -239,17 +207,8 @@ class LogNormal(Distribution):
     def draw(self, rng, size, **ctx):
         return np.exp(rng.normal(self.mu, self.sigma, size=size))
 
-    def draw_device(self, gen, size, device):
-        import torch
-
-        z = torch.randn(size, dtype=torch.float64, device=device, generator=gen)
-        return torch.exp(z * self.sigma + self.mu)
-
-    def logp_device(self, value):
-        import torch
-
-        lv = torch.log(value)
-        return -lv - 0.5 * (np.log(2 * np.pi * self.sigma**2) + ((lv - self.mu) / self.sigma) ** 2)
+    def device_spec(self):
+        return (PRIOR_LOGNORMAL, self.mu, self.sigma)
 
     def logp(self, value, **ctx):
         lv = np.log(value)
@@ -451,34 +410,64 @@ class JokerPrior:
     def __str__(self):
         return ", ".join(self.par_names)
 
-    def sample_device(self, size, device, seed, rv_unit, return_logprobs=False):
-        """Draw the nonlinear parameters on a GPU: returns
+    _NONLINEAR_INTERNAL = ("P", "e", "omega", "M0", "s")
+
+    def device_generator(self, seed, rv_unit):
+        """The nonlinear prior as the library's counter-based sampler sees it
+        (SURVEY.md section 8 f2): a ``_lib.TjbPriorGen`` -- per parameter the distribution
+        kind, its two numbers and the factor into the helper's internal units
+        [day, -, rad, rad, rv_unit] -- or None if a parameter's family has no device
+        sampler (the caller then samples on the host).  Sample i of the prior is a pure
+        function of (seed, i), see csrc/prior_gen.cuh; like the reference's pm.draw path
+        the stream is not numpy's, the distributions are the same."""
+        from . import _lib
+
+        gen = _lib.TjbPriorGen()
+        to = {"P": u.day, "e": u.one, "omega": u.rad, "M0": u.rad, "s": rv_unit}
+        for k, name in enumerate(self._NONLINEAR_INTERNAL):
+            spec = self.pars[name].device_spec()
+            if spec is None:
+                return None
+            gen.par[k].kind, gen.par[k].p0, gen.par[k].p1 = int(spec[0]), float(spec[1]), float(spec[2])
+            gen.par[k].scale = float(self.pars[name].unit.to(to[name]))
+        gen.seed = int(seed) & (2**64 - 1)
+        return gen
+
+    def ln_prior_rows(self, rows, rv_unit):
+        """ln prior density of packed rows [P, e, omega, M0, s] given in internal units
+        (what ``sample(..., return_logprobs=True)`` stores per sample, prior.py:388-400)."""
+        rows = np.asarray(rows, dtype=np.float64).reshape(-1, 5)
+        to = {"P": u.day, "e": u.one, "omega": u.rad, "M0": u.rad, "s": rv_unit}
+        logp = np.zeros(len(rows))
+        for k, name in enumerate(self._NONLINEAR_INTERNAL):
+            p = self.pars[name]
+            logp = logp + p.logp(rows[:, k] / float(p.unit.to(to[name])))
+        return logp
+
+    def sample_device(self, size, device, seed, rv_unit, return_logprobs=False, index0=0):
+        """Materialise ``size`` prior samples (global indices index0 ...) on a GPU:
         ``([P, e, omega, M0] float64 CUDA tensors in [day, -, rad, rad], s, ln_prior)``
-        where ``s`` is a tensor in ``rv_unit`` or a python float for a constant jitter and
-        ``ln_prior`` is a tensor or None.  Returns None if a distribution has no device
-        sampler (the caller then samples on the host).  Streams come from torch's Philox
-        generator seeded with ``seed``; like the reference's pm.draw path this is not
-        stream-compatible with numpy, the distributions are the same."""
+        with ``s`` a tensor in ``rv_unit`` or a python float for a constant jitter and
+        ``ln_prior`` a host array or None.  None if a distribution has no device sampler.
+        One hand-written kernel (``tjb_prior_sample``); the rejection sampler itself does
+        not call this -- its likelihood kernel generates the same samples in registers."""
         import torch
 
-        gen = torch.Generator(device=device).manual_seed(int(seed))
-        out, logp = {}, None
-        for name in ("P", "e", "omega", "M0", "s"):
-            p = self.pars[name]
-            v = p.draw_device(gen, int(size), device)
-            if v is None:
-                return None
-            if return_logprobs:
-                lp = p.logp_device(v)
-                if lp is None:
-                    return None
-                logp = lp if logp is None else logp + lp
-            to = {"P": u.day, "e": u.one, "omega": u.rad, "M0": u.rad, "s": rv_unit}[name]
-            f = float(p.unit.to(to))
-            out[name] = v * f if f != 1.0 else v
-        if return_logprobs and not hasattr(logp, "shape"):
-            logp = torch.full((int(size),), float(logp), dtype=torch.float64, device=device)
-        return [out["P"], out["e"], out["omega"], out["M0"]], out["s"], logp
+        from .helper import prior_sample_device
+
+        gen = self.device_generator(seed, rv_unit)
+        if gen is None:
+            return None
+        dev = torch.device(device)
+        const_s = self.pars["s"].device_spec()[0] == PRIOR_CONSTANT
+        cols = prior_sample_device(gen, int(index0), int(size), dev.index or 0, with_s=not const_s)
+        s = float(gen.par[4].p0 * gen.par[4].scale) if const_s else cols[4]
+        logp = None
+        if return_logprobs:
+            rows = np.stack([c.cpu().numpy() for c in cols[:4]]
+                            + [np.full(int(size), s) if const_s else cols[4].cpu().numpy()], axis=1)
+            logp = self.ln_prior_rows(rows, rv_unit)
+        return cols[:4], s, logp
 
     def sample(self, size=1, generate_linear=False, return_logprobs=False, rng=None, dtype=None,
                **kwargs):

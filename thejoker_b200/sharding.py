@@ -229,10 +229,33 @@ class DeviceEngine:
         self._link_peers()
         return self
 
+    @classmethod
+    def from_generator(cls, make_helper, gen, n_local, devices=(0,), group=None, global_offset=0,
+                       global_size=None):
+        """Engine over a prior that is *drawn*, not stored: sample g (global index) is a
+        pure function of (gen.seed, g) (csrc/prior_gen.cuh), generated in registers by the
+        likelihood kernel and re-generated for the accepted indices.  No prior column
+        exists on any device; a shard only owns its ll array."""
+        import torch
+
+        self = cls.__new__(cls)
+        self.torch, self.group, self.gen = torch, group, gen
+        self.s_const = 0.0
+        self.shards = []
+        for d, (lo, hi) in zip(devices, shard_ranges(int(n_local), len(devices))):
+            self._add_shard(make_helper, d, lo, hi, None, None)
+        self.n_local = int(n_local)
+        self.global_offset = int(global_offset)
+        self.n_global = int(n_local if global_size is None else global_size)
+        self._link_peers()
+        return self
+
     def rows(self, local_idx):
         """Packed (k, 5) host rows [P, e, omega, M0, s] for local sample indices."""
         torch = self.torch
         local_idx = np.asarray(local_idx, dtype=np.int64)
+        if getattr(self, "gen", None) is not None:
+            return self.shards[0].helper.prior_rows(self.gen, local_idx + self.global_offset)
         out = np.empty((len(local_idx), 5))
         if getattr(self, "host_cols", None) is not None:
             for j, c in enumerate(self.host_cols[:4]):
@@ -264,6 +287,10 @@ class DeviceEngine:
                 continue
             with torch.cuda.device(sh.device):
                 sl = slice(a - sh.lo, b - sh.lo)
+                if getattr(self, "gen", None) is not None:
+                    sh.helper.marginal_ll_generated(self.gen, self.global_offset + a, b - a,
+                                                    out=sh.ll[sl], llmax_key=sh.key)
+                    continue
                 sh.helper.marginal_ll_soa(*[c[sl] for c in sh.cols],
                                           s=None if sh.s is None else sh.s[sl],
                                           s_const=self.s_const, out=sh.ll[sl], llmax_key=sh.key)

@@ -155,11 +155,11 @@ class TheJoker:
                                global_offset=lo, global_size=n)
         return eng, make(self.devices[0])
 
-    def _engine_device_prior(self, data, n, return_logprobs):
-        """Prior samples drawn directly on the GPUs (no host copy); None if the prior
-        has a distribution without a device sampler."""
-        import torch
-
+    def _engine_device_prior(self, data, n):
+        """Engine over n prior samples *drawn on the GPUs* by the library's counter-based
+        sampler (csrc/prior_gen.cuh): the likelihood kernel generates them in registers,
+        nothing of the prior is stored on the host or in HBM.  None if the prior has a
+        distribution family without a device sampler."""
         helpers = {}
 
         def make(d):
@@ -168,34 +168,24 @@ class TheJoker:
             return helpers[d]
 
         helper0 = make(self.devices[0])
-        rv_unit = helper0.internal_units["s"]
-        base_seed = int(self.rng.integers(0, 2**62))
+        # the seed is taken from self.rng on every rank alike (SPMD contract): sample g is
+        # a function of (seed, g), so every sharding of [0, n) sees the same prior
+        gen = self.prior.device_generator(int(self.rng.integers(0, 2**62)),
+                                          helper0.internal_units["s"])
+        if gen is None:
+            return None
         from .sharding import shard_ranges
 
-        rank, world, glo = 0, 1, 0
-        devices = self.devices
+        rank, world, devices = 0, 1, self.devices
         if self.group is not None:
             import torch.distributed as dist
 
             rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
             devices = self.devices[:1]
         r_lo, r_hi = shard_ranges(n, world)[rank]
-        shards, ln_priors, s_const = [], [], 0.0
-        for di, (a, b) in enumerate(shard_ranges(r_hi - r_lo, len(devices))):
-            d = devices[di]
-            with torch.cuda.device(d):
-                got = self.prior.sample_device(b - a, f"cuda:{d}", base_seed + 7919 * (rank * 64 + di),
-                                               rv_unit, return_logprobs)
-            if got is None:
-                return None
-            cols, s, lp = got
-            if not hasattr(s, "shape"):
-                s_const, s = float(s), None
-            shards.append((d, cols, s))
-            ln_priors.append(lp)
-        eng = DeviceEngine.from_device_columns(make, shards, s_const=s_const, group=self.group,
-                                               global_offset=r_lo, global_size=n)
-        return eng, helper0, ln_priors
+        eng = DeviceEngine.from_generator(make, gen, r_hi - r_lo, devices=devices, group=self.group,
+                                          global_offset=r_lo, global_size=n)
+        return eng, helper0
 
     @staticmethod
     def _rows(cols, idx):
@@ -312,33 +302,23 @@ class TheJoker:
 
     def _rejection_sample_device_prior(self, data, n, max_posterior_samples, n_linear_samples,
                                        return_logprobs, return_all_logprobs, in_memory, n_batches):
-        if self.group is not None and (return_logprobs or return_all_logprobs):
-            return None  # keep the SPMD path simple: logprobs go through host samples
-        got = self._engine_device_prior(data, n, return_logprobs)
+        got = self._engine_device_prior(data, n)
         if got is None:
             return None
-        eng, helper, ln_priors = got
+        eng, helper = got
         if max_posterior_samples is None:
             max_posterior_samples = n
         eng.compute_ll()
         good, _ = self._uniform_accept(eng, n, max_posterior_samples)
-        if self.group is None:
-            rows = eng.rows(good)
-        else:
-            import torch.distributed as dist
-
-            mine = (good >= eng.global_offset) & (good < eng.global_offset + eng.n_local)
-            parts = [None] * dist.get_world_size(self.group)
-            dist.all_gather_object(parts, (good[mine], eng.rows(good[mine] - eng.global_offset)),
-                                   group=self.group)
-            rows = np.concatenate([p[1] for p in parts]) if len(good) else np.zeros((0, 5))
+        # the accepted rows are re-generated from their global indices (any rank can)
+        rows = helper.prior_rows(eng.gen, good)
         samples = self._full_samples(helper, rows, self.rng, n_linear_samples, in_memory, n_batches)
         lls = None
         if return_logprobs or return_all_logprobs:
             lls = eng.gather_ll()
         if return_logprobs:
-            lp = np.concatenate([t.cpu().numpy() for t in ln_priors])
-            samples["ln_prior"] = np.repeat(lp[good], n_linear_samples)
+            lp = self.prior.ln_prior_rows(rows, helper.internal_units["s"])
+            samples["ln_prior"] = np.repeat(lp, n_linear_samples)
             samples["ln_likelihood"] = np.repeat(lls[good], n_linear_samples)
         if return_all_logprobs:
             return samples, lls

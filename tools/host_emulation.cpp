@@ -79,6 +79,29 @@ int emu_marginal_ll(int N, int L, double t_ref, const double *t, const double *r
   return 0;
 }
 
+// ---- prior_gen.cuh: the counter-based prior sampler --------------------------------------
+void emu_philox4x32_10(const unsigned *ctr, const unsigned *key, unsigned *out) {
+  uint32_t x0 = ctr[0], x1 = ctr[1], x2 = ctr[2], x3 = ctr[3];
+  philox4x32_10(x0, x1, x2, x3, key[0], key[1]);
+  out[0] = x0; out[1] = x1; out[2] = x2; out[3] = x3;
+}
+// rows[n, 5] for global indices index0 .. index0 + n; kind / p0 / p1 / scale: 5 entries each
+void emu_prior_rows(const int *kind, const double *p0, const double *p1, const double *scale,
+                    unsigned long long seed, long long index0, long n, double *rows) {
+  PriorGenSpec ps;
+  for (int k = 0; k < 5; k++) {
+    ps.par[k].kind = kind[k]; ps.par[k].p0 = p0[k]; ps.par[k].p1 = p1[k]; ps.par[k].scale = scale[k];
+  }
+  ps.seed = seed;
+  for (long i = 0; i < n; i++) prior_row(ps, (unsigned long long)(index0 + i), rows + 5 * i);
+}
+// the first n uniforms of one sample's stream
+void emu_prior_uniforms(unsigned long long seed, unsigned long long index, int n, double *out) {
+  Philox g;
+  g.init(seed, index);
+  for (int i = 0; i < n; i++) out[i] = g.next_open();
+}
+
 long long emu_ll_to_key(double x) { return ll_to_key(x); }
 double emu_key_to_ll(long long k) { return key_to_ll(k); }
 
