@@ -186,6 +186,34 @@ int tjb_accept(TjbHandle *h, const double *d_ll, int64_t n, const int64_t *d_llm
                const double *d_uniforms, const TjbPcg64 *pcg, int64_t pcg_offset,
                int64_t index_base, int64_t max_keep, double near_tol, int64_t *d_idx,
                int64_t *h_counts);
+/* ---- the same accept step over shards that live in different processes (one rank per
+ * GPU): NCCL inside the library, no torch / MPI types in the interface.  Replaces the
+ * master-side gather + max + compare + where of multiproc_helpers.py:256-263, 373-381.
+ * NCCL is bound at run time (dlopen of libnccl.so.2; inside a PyTorch process that is
+ * torch's own copy); without it these entry points fail with TJB_E_CUDA and everything
+ * else works.  Bootstrap: rank 0 calls tjb_comm_unique_id and distributes the
+ * TJB_COMM_ID_BYTES it gets by any host-side means (a file, MPI_Bcast, a TCP store);
+ * every rank then calls tjb_comm_create (collective: ncclCommInitRank). */
+#define TJB_COMM_ID_BYTES 128
+typedef struct TjbComm TjbComm;
+int tjb_comm_unique_id(void *out_id);
+int tjb_comm_create(const void *id_bytes, int n_ranks, int rank, int device, TjbComm **out);
+void tjb_comm_destroy(TjbComm *comm);
+/* integer MAX all-reduce of *d_llmax_key over the ranks, on the handle's stream */
+int tjb_comm_allreduce_max_key(TjbHandle *h, TjbComm *comm, int64_t *d_llmax_key);
+/* Collective accept.  This rank owns the global samples [global_offset, global_offset +
+ * n_local) with lls d_ll and the running max of its shard in *d_llmax_key, which is
+ * replaced by the max over all ranks (ncclAllReduce MAX on the int64 key).  Uniforms: as
+ * tjb_accept, addressed globally (u of global sample g is the g-th double of the PCG64
+ * stream; d_uniforms, if given, is this rank's slice).  Every rank receives in
+ * d_idx[max_keep] the same ascending global indices -- the rank-ordered concatenation
+ * truncated to max_keep -- and in h_counts the global [accepted, written, near].  Two
+ * small all-gathers (counts, then indices); synchronises the stream. */
+int tjb_accept_dist(TjbHandle *h, TjbComm *comm, const double *d_ll, int64_t n_local,
+                    int64_t *d_llmax_key, const double *d_uniforms, const TjbPcg64 *pcg,
+                    int64_t global_offset, int64_t max_keep, double near_tol, int64_t *d_idx,
+                    int64_t *h_counts);
+
 /* the uniforms themselves (tests; parity with numpy) */
 int tjb_pcg64_uniform(TjbHandle *h, const TjbPcg64 *pcg, int64_t offset, int64_t n,
                       double *d_out);

@@ -14,13 +14,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TJB_LIB_PATH", os.path.join(_HERE, "libthejoker_b200.so"))  # override: tuning builds
 _SRC = [os.path.join(_HERE, "csrc", f) for f in
         ("tjb_api.cu", "kepler.cuh", "linalg.cuh", "marginal_ll.cuh", "accept.cuh", "posterior.cuh",
-         "prior_gen.cuh", "star_tables.hpp")]
+         "prior_gen.cuh", "comm.hpp", "star_tables.hpp")]
 _HDR = os.path.join(os.path.dirname(_HERE), "include", "thejoker_b200.h")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
 TJB_MAX_LINEAR = 8
+TJB_COMM_ID_BYTES = 128
 _dp = ctypes.POINTER(ctypes.c_double)
 _i64p = ctypes.POINTER(ctypes.c_int64)
 
@@ -117,6 +118,14 @@ SYMBOLS = {
     "tjb_accept": (ctypes.c_int, [_H, _vp, ctypes.c_int64, _vp, _vp, ctypes.POINTER(TjbPcg64),
                                   ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_double,
                                   _vp, _i64p]),
+    "tjb_comm_unique_id": (ctypes.c_int, [_vp]),
+    "tjb_comm_create": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.POINTER(ctypes.c_void_p)]),
+    "tjb_comm_destroy": (None, [_vp]),
+    "tjb_comm_allreduce_max_key": (ctypes.c_int, [_H, _vp, _vp]),
+    "tjb_accept_dist": (ctypes.c_int, [_H, _vp, _vp, ctypes.c_int64, _vp, _vp,
+                                       ctypes.POINTER(TjbPcg64), ctypes.c_int64, ctypes.c_int64,
+                                       ctypes.c_double, _vp, _i64p]),
     "tjb_pcg64_uniform": (ctypes.c_int, [_H, ctypes.POINTER(TjbPcg64), ctypes.c_int64,
                                          ctypes.c_int64, _vp]),
     "tjb_posterior_aA": (ctypes.c_int, [_H, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp]),
@@ -130,6 +139,22 @@ SYMBOLS = {
 }
 
 _lib = None
+
+
+def source_hash() -> str:
+    """sha256 over the CUDA sources, the header and the nvcc flags: identifies the code a
+    built library (and an ncu profile of it) belongs to.  profiles/kernel_counts.json
+    carries the hash of the sources its counters were measured on; bench.py flags counters
+    whose hash differs from the sources in the tree."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for path in sorted(_SRC + [_HDR]):
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
 
 
 def needs_build() -> bool:

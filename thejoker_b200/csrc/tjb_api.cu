@@ -16,6 +16,7 @@
 
 #include "../../include/thejoker_b200.h"
 #include "accept.cuh"
+#include "comm.hpp"
 #include "marginal_ll.cuh"
 #include "posterior.cuh"
 #include "star_tables.hpp"
@@ -158,6 +159,7 @@ struct TjbHandle {
   double const_s = 0;
   // scratch
   DevBuf acc_mask, acc_counts, acc_offsets, acc_totals, misc, stats;
+  DevBuf dist_counts, dist_send, dist_gather;  // tjb_accept_dist
   void *trig = nullptr;  // shared per-device sin/cos table (DeviceShared)
   StagePool *stg = nullptr;  // this device's host-streaming resources (shared by handles)
   int ll_ctas_per_sm = 0;
@@ -416,6 +418,7 @@ void tjb_destroy(TjbHandle *h) {
   h->tab_const.release(); h->tab_jit.release();
   h->acc_mask.release(); h->acc_counts.release(); h->acc_offsets.release();
   h->acc_totals.release(); h->misc.release(); h->stats.release();
+  h->dist_counts.release(); h->dist_send.release(); h->dist_gather.release();
   delete h;
 }
 
@@ -435,6 +438,13 @@ int tjb_set_peer_keys(TjbHandle *h, int64_t *const *d_peer_keys, const int *peer
     int can = 0;
     CU(cudaDeviceCanAccessPeer(&can, h->device, peer_devices[p]));
     if (!can) return fail(TJB_E_CUDA, "no peer access between the devices");
+    // the fused max exchange does atomicMax_system on the peers' keys: peer *access* alone
+    // (PCIe-only P2P, some virtualised topologies) does not guarantee native peer atomics
+    int native = 0;
+    CU(cudaDeviceGetP2PAttribute(&native, cudaDevP2PAttrNativeAtomicSupported, h->device,
+                                 peer_devices[p]));
+    if (!native)
+      return fail(TJB_E_CUDA, "peer access without native atomics: use the host / NCCL max combine");
     cudaError_t e = cudaDeviceEnablePeerAccess(peer_devices[p], 0);
     if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
     else if (e != cudaSuccess) return fail(TJB_E_CUDA, cudaGetErrorString(e));
@@ -860,28 +870,24 @@ int tjb_pcg64_uniform(TjbHandle *h, const TjbPcg64 *pcg, int64_t offset, int64_t
   return TJB_OK;
 }
 
-int tjb_accept(TjbHandle *h, const double *d_ll, int64_t n, const int64_t *d_llmax_key,
-               const double *d_uniforms, const TjbPcg64 *pcg, int64_t pcg_offset,
-               int64_t index_base, int64_t max_keep, double near_tol, int64_t *d_idx,
-               int64_t *h_counts) {
-  if (!h || !h_counts) return fail(TJB_E_INVALID, "null argument");
-  h_counts[0] = h_counts[1] = h_counts[2] = 0;
+namespace {
+
+// flag / scan / scatter of one contiguous ll range on the handle's stream; the totals
+// [accepted, near] are left in h->acc_totals (device).  No host synchronisation.
+int accept_local_async(TjbHandle *h, const double *d_ll, int64_t n, const int64_t *d_llmax_key,
+                       const double *d_uniforms, const TjbPcg64 *pcg, int64_t pcg_offset,
+                       int64_t index_base, int64_t max_keep, double near_tol, int64_t *d_idx) {
+  if (h->acc_totals.ensure(2 * sizeof(unsigned long long)))
+    return fail(TJB_E_NOMEM, "cudaMalloc accept scratch");
+  CU(cudaMemsetAsync(h->acc_totals.p, 0, 2 * sizeof(unsigned long long), h->stream));
   if (n <= 0) return TJB_OK;
-  if (!d_ll || !d_llmax_key) return fail(TJB_E_INVALID, "null device pointer");
-  if ((d_uniforms == nullptr) == (pcg == nullptr))
-    return fail(TJB_E_INVALID, "exactly one of d_uniforms / pcg must be given");
-  if (max_keep < 0) return fail(TJB_E_INVALID, "negative max_keep");
-  if (max_keep > 0 && !d_idx) return fail(TJB_E_INVALID, "null index buffer");
-  CU(cudaSetDevice(h->device));
   const long long n_words = (n + 31) / 32;
   const int wpc = acc_words_per_cta(n_words, h->n_sm);
   const int n_cta = (int)((n_words + wpc - 1) / wpc);
   if (h->acc_mask.ensure((size_t)n_words * sizeof(unsigned)) ||
       h->acc_counts.ensure((size_t)n_cta * sizeof(unsigned)) ||
-      h->acc_offsets.ensure((size_t)n_cta * sizeof(unsigned long long)) ||
-      h->acc_totals.ensure(2 * sizeof(unsigned long long)))
+      h->acc_offsets.ensure((size_t)n_cta * sizeof(unsigned long long)))
     return fail(TJB_E_NOMEM, "cudaMalloc accept scratch");
-  CU(cudaMemsetAsync(h->acc_totals.p, 0, 2 * sizeof(unsigned long long), h->stream));
   const PcgParams pp = make_pcg(pcg, pcg_offset, kAccThreads);
   accept_flag_kernel<<<n_cta, kAccThreads, 0, h->stream>>>(
       d_ll, n, (const long long *)d_llmax_key, d_uniforms, pp, near_tol, wpc,
@@ -896,12 +902,162 @@ int tjb_accept(TjbHandle *h, const double *d_ll, int64_t n, const int64_t *d_llm
         index_base, max_keep, wpc, (long long *)d_idx);
     CU(cudaGetLastError());
   }
+  return TJB_OK;
+}
+
+}  // namespace
+
+int tjb_accept(TjbHandle *h, const double *d_ll, int64_t n, const int64_t *d_llmax_key,
+               const double *d_uniforms, const TjbPcg64 *pcg, int64_t pcg_offset,
+               int64_t index_base, int64_t max_keep, double near_tol, int64_t *d_idx,
+               int64_t *h_counts) {
+  if (!h || !h_counts) return fail(TJB_E_INVALID, "null argument");
+  h_counts[0] = h_counts[1] = h_counts[2] = 0;
+  if (n <= 0) return TJB_OK;
+  if (!d_ll || !d_llmax_key) return fail(TJB_E_INVALID, "null device pointer");
+  if ((d_uniforms == nullptr) == (pcg == nullptr))
+    return fail(TJB_E_INVALID, "exactly one of d_uniforms / pcg must be given");
+  if (max_keep < 0) return fail(TJB_E_INVALID, "negative max_keep");
+  if (max_keep > 0 && !d_idx) return fail(TJB_E_INVALID, "null index buffer");
+  CU(cudaSetDevice(h->device));
+  int rc = accept_local_async(h, d_ll, n, d_llmax_key, d_uniforms, pcg, pcg_offset, index_base,
+                              max_keep, near_tol, d_idx);
+  if (rc) return rc;
   unsigned long long tot[2] = {0, 0};
   CU(cudaMemcpyAsync(tot, h->acc_totals.p, sizeof(tot), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   h_counts[0] = (int64_t)tot[0];
   h_counts[1] = std::min<int64_t>((int64_t)tot[0], max_keep);
   h_counts[2] = (int64_t)tot[1];
+  return TJB_OK;
+}
+
+// ---- multi-rank accept: NCCL inside the library (comm.hpp) -----------------------------
+
+#define NC(call)                                                                          \
+  do {                                                                                    \
+    ncclResult_t r_ = (call);                                                             \
+    if (r_ != ncclSuccess)                                                                \
+      return fail(TJB_E_CUDA, std::string(#call) + ": " + nccl_api().GetErrorString(r_));  \
+  } while (0)
+
+int tjb_comm_unique_id(void *out_id) {
+  if (!out_id) return fail(TJB_E_INVALID, "null argument");
+  NcclApi &nc = nccl_api();
+  if (!nc.ok) return fail(TJB_E_CUDA, nc.error);
+  static_assert(sizeof(ncclUniqueId) == TJB_COMM_ID_BYTES, "NCCL unique id size");
+  ncclUniqueId id;
+  NC(nc.GetUniqueId(&id));
+  memcpy(out_id, &id, sizeof(id));
+  return TJB_OK;
+}
+
+int tjb_comm_create(const void *id_bytes, int n_ranks, int rank, int device, TjbComm **out) {
+  if (!id_bytes || !out) return fail(TJB_E_INVALID, "null argument");
+  *out = nullptr;
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(TJB_E_INVALID, "bad rank / n_ranks");
+  NcclApi &nc = nccl_api();
+  if (!nc.ok) return fail(TJB_E_CUDA, nc.error);
+  CU(cudaSetDevice(device));
+  ncclUniqueId id;
+  memcpy(&id, id_bytes, sizeof(id));
+  ncclComm_t comm = nullptr;
+  NC(nc.CommInitRank(&comm, n_ranks, id, rank));
+  TjbComm *c = new TjbComm();
+  c->comm = comm;
+  c->n_ranks = n_ranks;
+  c->rank = rank;
+  c->device = device;
+  *out = c;
+  return TJB_OK;
+}
+
+void tjb_comm_destroy(TjbComm *comm) {
+  if (!comm) return;
+  if (comm->comm && nccl_api().ok) {
+    cudaSetDevice(comm->device);
+    nccl_api().CommDestroy(comm->comm);
+  }
+  delete comm;
+}
+
+int tjb_comm_allreduce_max_key(TjbHandle *h, TjbComm *comm, int64_t *d_llmax_key) {
+  if (!h || !comm || !d_llmax_key) return fail(TJB_E_INVALID, "null argument");
+  if (comm->device != h->device) return fail(TJB_E_INVALID, "communicator is on another device");
+  CU(cudaSetDevice(h->device));
+  NC(nccl_api().AllReduce(d_llmax_key, d_llmax_key, 1, ncclInt64, ncclMax, comm->comm, h->stream));
+  return TJB_OK;
+}
+
+int tjb_accept_dist(TjbHandle *h, TjbComm *comm, const double *d_ll, int64_t n_local,
+                    int64_t *d_llmax_key, const double *d_uniforms, const TjbPcg64 *pcg,
+                    int64_t global_offset, int64_t max_keep, double near_tol, int64_t *d_idx,
+                    int64_t *h_counts) {
+  if (!h || !comm || !h_counts) return fail(TJB_E_INVALID, "null argument");
+  h_counts[0] = h_counts[1] = h_counts[2] = 0;
+  if (comm->device != h->device) return fail(TJB_E_INVALID, "communicator is on another device");
+  if (n_local < 0 || global_offset < 0) return fail(TJB_E_INVALID, "negative n / offset");
+  if (!d_llmax_key || (n_local > 0 && !d_ll)) return fail(TJB_E_INVALID, "null device pointer");
+  if (n_local > 0 && (d_uniforms == nullptr) == (pcg == nullptr))
+    return fail(TJB_E_INVALID, "exactly one of d_uniforms / pcg must be given");
+  if (max_keep < 0) return fail(TJB_E_INVALID, "negative max_keep");
+  if (max_keep > 0 && !d_idx) return fail(TJB_E_INVALID, "null index buffer");
+  NcclApi &nc = nccl_api();
+  CU(cudaSetDevice(h->device));
+  const int W = comm->n_ranks;
+  cudaStream_t st = h->stream;
+  // (1) lls.max() over all shards: integer MAX all-reduce of the order-preserving key
+  NC(nc.AllReduce(d_llmax_key, d_llmax_key, 1, ncclInt64, ncclMax, comm->comm, st));
+  // (2) local flag / scan / scatter; uniforms and indices are addressed globally
+  const int64_t keep_local = std::min(max_keep, n_local);
+  if (h->dist_send.ensure((size_t)std::max<int64_t>(keep_local, 1) * sizeof(int64_t)) ||
+      h->dist_counts.ensure((size_t)W * 2 * sizeof(unsigned long long)))
+    return fail(TJB_E_NOMEM, "cudaMalloc accept scratch");
+  int rc = accept_local_async(h, d_ll, n_local, d_llmax_key, d_uniforms, pcg, global_offset,
+                              global_offset, keep_local, near_tol, (int64_t *)h->dist_send.p);
+  if (rc) return rc;
+  // (3) every rank learns every rank's [accepted, near]
+  NC(nc.AllGather(h->acc_totals.p, h->dist_counts.p, 2, ncclUint64, comm->comm, st));
+  std::vector<unsigned long long> cnt((size_t)W * 2);
+  CU(cudaMemcpyAsync(cnt.data(), h->dist_counts.p, cnt.size() * sizeof(unsigned long long),
+                     cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  // good_samples_idx[:max_keep] over the rank-ordered concatenation
+  // (likelihood_helpers.py:109): rank r keeps what is left of max_keep after ranks < r
+  std::vector<int64_t> kept(W), pos(W);
+  int64_t total = 0, near = 0, written = 0, m = 0;
+  for (int r = 0; r < W; r++) {
+    const int64_t a = (int64_t)cnt[2 * r];
+    total += a;
+    near += (int64_t)cnt[2 * r + 1];
+    pos[r] = written;
+    kept[r] = std::max<int64_t>(0, std::min(a, max_keep - written));
+    written += kept[r];
+    m = std::max(m, kept[r]);
+  }
+  h_counts[0] = total;
+  h_counts[1] = written;
+  h_counts[2] = near;
+  if (m == 0) return TJB_OK;
+  // (4) fixed-size all-gather of the first m local indices of every rank, then the kept
+  //     prefixes are laid end to end
+  if (h->dist_send.bytes < (size_t)m * sizeof(int64_t)) {  // this rank keeps fewer than m
+    DevBuf bigger;
+    if (bigger.ensure((size_t)m * sizeof(int64_t))) return fail(TJB_E_NOMEM, "cudaMalloc");
+    if (kept[comm->rank] > 0)
+      CU(cudaMemcpyAsync(bigger.p, h->dist_send.p, (size_t)kept[comm->rank] * sizeof(int64_t),
+                         cudaMemcpyDeviceToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    h->dist_send.release();
+    h->dist_send = bigger;
+  }
+  if (h->dist_gather.ensure((size_t)W * m * sizeof(int64_t))) return fail(TJB_E_NOMEM, "cudaMalloc");
+  NC(nc.AllGather(h->dist_send.p, h->dist_gather.p, (size_t)m, ncclInt64, comm->comm, st));
+  for (int r = 0; r < W; r++)
+    if (kept[r] > 0)
+      CU(cudaMemcpyAsync(d_idx + pos[r], (const int64_t *)h->dist_gather.p + (size_t)r * m,
+                         (size_t)kept[r] * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  CU(cudaStreamSynchronize(st));
   return TJB_OK;
 }
 

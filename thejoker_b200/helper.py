@@ -521,6 +521,41 @@ class CJokerHelper:
                                         float(near_tol), self._ptr(idx), counts))
         return idx[: counts[1]], int(counts[0]), int(counts[2])
 
+    def accept_dist(self, comm, ll, llmax_key, global_offset, uniforms=None, rng=None,
+                    max_keep=None, n_global=None, near_tol=1e-12):
+        """The accept step over shards owned by different ranks (tjb_accept_dist): NCCL MAX
+        all-reduce of the key, local flag / scan / scatter with globally addressed
+        uniforms, all-gather of counts and indices -- all inside the library.  Collective:
+        every rank of ``comm`` (a ``sharding.LibComm``) calls it.  ``ll`` is this rank's
+        shard (global samples global_offset ...).  Returns (global idx int64 device tensor,
+        n_accepted_total, n_near), identical on every rank."""
+        import torch
+
+        n = ll.numel()
+        n_global = n if n_global is None else int(n_global)
+        max_keep = n_global if max_keep is None else min(int(max_keep), n_global)
+        idx = torch.empty(max(max_keep, 1), dtype=torch.int64, device=ll.device)
+        counts = (ctypes.c_int64 * 3)()
+        pcg = None
+        if uniforms is None:
+            pcg = _pcg_struct(rng)
+            if pcg is None:
+                raise ValueError("device-side uniforms need a numpy Generator on PCG64")
+        self._sync_stream()
+        _lib.check(self._lib.tjb_accept_dist(self._h, comm.handle, self._ptr(ll), n,
+                                             self._ptr(llmax_key), self._ptr(uniforms),
+                                             ctypes.byref(pcg) if pcg is not None else None,
+                                             int(global_offset), max_keep, float(near_tol),
+                                             self._ptr(idx), counts))
+        return idx[: counts[1]], int(counts[0]), int(counts[2])
+
+    def allreduce_max_key(self, comm, llmax_key):
+        """Integer MAX all-reduce of the key over the ranks of ``comm`` (library NCCL)."""
+        self._sync_stream()
+        _lib.check(self._lib.tjb_comm_allreduce_max_key(self._h, comm.handle,
+                                                        self._ptr(llmax_key)))
+        return llmax_key
+
     def pcg64_uniform(self, rng, n, offset=0):
         """The doubles ``rng.random(n)`` would return (without advancing rng), on device."""
         import torch

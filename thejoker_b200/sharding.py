@@ -25,7 +25,7 @@ from __future__ import annotations
 import numpy as np
 
 __all__ = ["batch_tasks", "shard_ranges", "DeviceEngine", "merge_accepted", "allreduce_max_key",
-           "gather_accepted"]
+           "gather_accepted", "allgather_ragged", "LibComm"]
 
 
 def batch_tasks(n_tasks, n_batches, arr=None, args=None, start_idx=0):
@@ -109,16 +109,108 @@ def allreduce_max_key(key, group=None):
     return key
 
 
-def gather_accepted(idx, total, near, max_keep, group=None):
+def gather_accepted(idx, total, near, max_keep, group=None, device=None):
     """All ranks get the rank-ordered concatenation of the per-rank ascending index
-    lists, truncated to max_keep, plus the global counts."""
+    lists, truncated to max_keep, plus the global counts.  Two fixed-size tensor
+    all-gathers (counts, then indices padded to the longest kept list) -- nothing is
+    pickled.  This is the torch.distributed path (gloo in the CPU tests, or several index
+    segments per rank); one contiguous shard per rank under NCCL goes through the
+    library's own tjb_accept_dist instead."""
+    import torch
     import torch.distributed as dist
 
-    gathered = [None] * dist.get_world_size(group)
-    dist.all_gather_object(gathered, (np.asarray(idx, dtype=np.int64), int(total), int(near)),
-                           group=group)
-    idx, total = merge_accepted([g[0] for g in gathered], [g[1] for g in gathered], max_keep)
-    return idx, total, sum(g[2] for g in gathered)
+    world = dist.get_world_size(group)
+    dev = torch.device("cpu") if dist.get_backend(group) == "gloo" or device is None else device
+    idx = np.asarray(idx, dtype=np.int64)
+    if max_keep is not None:
+        idx = idx[:max_keep]
+    mine = torch.tensor([len(idx), int(total), int(near)], dtype=torch.int64, device=dev)
+    counts = torch.empty(world * 3, dtype=torch.int64, device=dev)  # flat: gloo wants 1-D
+    dist.all_gather_into_tensor(counts, mine, group=group)
+    counts = counts.cpu().numpy().reshape(world, 3)
+    m = int(counts[:, 0].max())
+    parts = []
+    if m > 0:
+        send = torch.zeros(m, dtype=torch.int64, device=dev)
+        send[: len(idx)] = torch.from_numpy(idx).to(dev)
+        recv = torch.empty(world * m, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        recv = recv.cpu().numpy().reshape(world, m)
+        parts = [recv[r, : counts[r, 0]] for r in range(world)]
+    idx, total = merge_accepted(parts, counts[:, 1], max_keep)
+    return idx, total, int(counts[:, 2].sum())
+
+
+class LibComm:
+    """The library's own NCCL communicator over the ranks of a torch.distributed group
+    (tjb_comm_create).  torch.distributed is used once, to hand rank 0's NCCL unique id to
+    the other ranks; the collectives of the accept step then run inside
+    libthejoker_b200.so (tjb_accept_dist).  One communicator per (group, device), cached."""
+
+    _cache = {}
+
+    def __init__(self, group, device):
+        import ctypes
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+
+        lib = _lib.load()
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        ident = torch.zeros(_lib.TJB_COMM_ID_BYTES, dtype=torch.uint8)
+        if rank == 0:
+            buf = (ctypes.c_ubyte * _lib.TJB_COMM_ID_BYTES)()
+            _lib.check(lib.tjb_comm_unique_id(buf))
+            ident = torch.frombuffer(bytearray(buf), dtype=torch.uint8).clone()
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        if dist.get_backend(group) == "nccl":
+            ident = ident.to(f"cuda:{device}")
+            dist.broadcast(ident, src=src, group=group)
+            ident = ident.cpu()
+        else:
+            dist.broadcast(ident, src=src, group=group)
+        raw = bytes(ident.numpy().tobytes())
+        h = ctypes.c_void_p()
+        _lib.check(lib.tjb_comm_create(raw, world, rank, int(device), ctypes.byref(h)))
+        self.handle, self.rank, self.world, self.device, self._lib = h, rank, world, int(device), lib
+
+    @classmethod
+    def get(cls, group, device):
+        key = (id(group), int(device))
+        if key not in cls._cache:
+            cls._cache[key] = cls(group, device)
+        return cls._cache[key]
+
+    def close(self):
+        if self.handle:
+            self._lib.tjb_comm_destroy(self.handle)
+            self.handle = None
+
+
+def allgather_ragged(arr, group, device=None):
+    """Rank-ordered concatenation of per-rank float64 arrays of different lengths: a
+    length all-gather, then one padded tensor all-gather (no pickling)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    dev = torch.device("cpu") if dist.get_backend(group) == "gloo" or device is None else device
+    arr = np.ascontiguousarray(arr, dtype=np.float64)
+    lens = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(lens, torch.tensor([len(arr)], dtype=torch.int64, device=dev),
+                                group=group)
+    lens = lens.cpu().numpy()
+    m = int(lens.max())
+    if m == 0:
+        return np.zeros(0)
+    send = torch.zeros(m, dtype=torch.float64, device=dev)
+    send[: len(arr)] = torch.from_numpy(arr).to(dev)
+    recv = torch.empty(world * m, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    recv = recv.cpu().numpy().reshape(world, m)
+    return np.concatenate([recv[r, : lens[r]] for r in range(world)])
 
 
 class _Shard:
@@ -141,13 +233,21 @@ class DeviceEngine:
     """
 
     def __init__(self, make_helper, columns, devices=(0,), group=None, global_offset=0,
-                 global_size=None, resident=False):
+                 global_size=None, resident=False, cyclic=False):
         import torch
 
         self.torch = torch
         self.group = group
         P, e, om, M0, s = columns
         n_local = len(P)
+        # cyclic (SPMD ranks, host-resident prior that every rank holds in full): a range
+        # [glo, ghi) handed to compute_ll_global is split evenly over ALL ranks, range by
+        # range -- the block-cyclic layout the iterative sampler needs, whose early rounds
+        # cover a small prefix of the cache that a contiguous layout would leave on rank 0
+        # alone (multiproc_helpers.py:355-410 maps every round over the whole pool too).
+        # A rank then owns a list of segments (glo, ghi, ll) instead of one contiguous shard.
+        self.cyclic = bool(cyclic) and group is not None
+        self.segments, self.rounds = [], []
         self.n_local = n_local
         self.global_offset = int(global_offset)
         self.n_global = int(n_local if global_size is None else global_size)
@@ -163,6 +263,12 @@ class DeviceEngine:
         # stops after a small prefix), and H2D overlaps the kernel.
         # resident=True: upload each shard once, for caches that are evaluated repeatedly.
         self.host_cols = None if resident else [P, e, om, M0, None if s_is_scalar else s]
+        if self.cyclic:
+            if resident or len(devices) != 1:
+                raise ValueError("cyclic sharding streams a host-resident prior, one GPU per rank")
+            self._add_shard(make_helper, devices[0], 0, 0, None, None)
+            self.peer_max = False
+            return
         for d, (lo, hi) in zip(devices, shard_ranges(n_local, len(devices))):
             cols, s_dev = None, None
             if resident:
@@ -195,14 +301,25 @@ class DeviceEngine:
             for sh in self.shards:
                 sh.helper.set_peer_keys([])
 
+    def _ctx(self, d):
+        """CUDA device context of a shard (a no-op for the CPU stand-in helpers of the
+        gloo tests, whose device is the string "cpu")."""
+        import contextlib
+
+        return contextlib.nullcontext() if d == "cpu" else self.torch.cuda.device(d)
+
+    @staticmethod
+    def _devstr(d):
+        return "cpu" if d == "cpu" else f"cuda:{d}"
+
     def _add_shard(self, make_helper, d, lo, hi, cols, s_dev):
         torch = self.torch
         sh = _Shard()
         sh.device, sh.lo, sh.hi = d, lo, hi
         sh.helper = make_helper(d)
         sh.cols, sh.s = cols, s_dev
-        with torch.cuda.device(d):
-            sh.ll = torch.full((hi - lo,), float("nan"), dtype=torch.float64, device=f"cuda:{d}")
+        with self._ctx(d):
+            sh.ll = torch.full((hi - lo,), float("nan"), dtype=torch.float64, device=self._devstr(d))
             sh.key = sh.helper.new_llmax_key()
         self.shards.append(sh)
 
@@ -285,7 +402,7 @@ class DeviceEngine:
             a, b = max(lo, sh.lo), min(hi, sh.hi)
             if a >= b:
                 continue
-            with torch.cuda.device(sh.device):
+            with self._ctx(sh.device):
                 sl = slice(a - sh.lo, b - sh.lo)
                 if getattr(self, "gen", None) is not None:
                     sh.helper.marginal_ll_generated(self.gen, self.global_offset + a, b - a,
@@ -308,7 +425,7 @@ class DeviceEngine:
         def run(item):
             sh, a, b = item
             P, e, om, M0, s = self.host_cols
-            with torch.cuda.device(sh.device):
+            with self._ctx(sh.device):
                 sh.helper.marginal_ll_host_columns(
                     P[a:b], e[a:b], om[a:b], M0[a:b], s=None if s is None else s[a:b],
                     s_const=self.s_const, out=sh.ll[a - sh.lo:b - sh.lo], llmax_key=sh.key)
@@ -323,20 +440,92 @@ class DeviceEngine:
 
     def compute_ll_global(self, glo, ghi):
         """ll for the part of the GLOBAL index range [glo, ghi) this process owns."""
+        if getattr(self, "cyclic", False):
+            return self._compute_ll_cyclic(int(glo), int(ghi))
         lo = max(glo, self.global_offset) - self.global_offset
         hi = min(ghi, self.global_offset + self.n_local) - self.global_offset
         if lo < hi:
             self.compute_ll(lo, hi)
 
+    def _compute_ll_cyclic(self, glo, ghi):
+        """This rank's 1/world slice of the global range, streamed from the host columns
+        into a new ll segment."""
+        import torch.distributed as dist
+
+        torch = self.torch
+        rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.rounds.append((glo, ghi))
+        a, b = shard_ranges(ghi - glo, world)[rank]
+        a, b = a + glo, b + glo
+        if a >= b:
+            return
+        sh = self.shards[0]
+        P, e, om, M0, s = self.host_cols
+        with self._ctx(sh.device):
+            ll = torch.empty(b - a, dtype=torch.float64, device=self._devstr(sh.device))
+            sh.helper.marginal_ll_host_columns(P[a:b], e[a:b], om[a:b], M0[a:b],
+                                               s=None if s is None else s[a:b],
+                                               s_const=self.s_const, out=ll, llmax_key=sh.key)
+        self.segments.append((a, b, ll))
+
+    def _accept_cyclic(self, rng, n_accum, max_keep, uniforms, near_tol):
+        """Accept over this rank's segments (each with its own PCG offset = its first
+        global index), then the union over the ranks in ascending global order."""
+        torch = self.torch
+        sh = self.shards[0]
+        self.global_max_key()
+        per_idx, total, near = [], 0, 0
+        with self._ctx(sh.device):
+            for a, b, ll in self.segments:
+                b = min(b, n_accum)
+                if a >= b:
+                    continue
+                if uniforms is not None:
+                    u_dev = torch.from_numpy(np.ascontiguousarray(uniforms[a:b])).to(ll.device)
+                    idx, tot, nn = sh.helper.accept(ll[: b - a], sh.key, uniforms=u_dev, index_base=a,
+                                                    max_keep=max_keep, near_tol=near_tol)
+                else:
+                    idx, tot, nn = sh.helper.accept(ll[: b - a], sh.key, rng=rng, rng_offset=a,
+                                                    index_base=a, max_keep=max_keep,
+                                                    near_tol=near_tol)
+                per_idx.append(idx.cpu().numpy())
+                total += tot
+                near += nn
+        mine = np.concatenate(per_idx) if per_idx else np.zeros(0, dtype=np.int64)
+        # the global first max_keep are among every rank's own first max_keep
+        idx, total, near = gather_accepted(mine, total, near, None if max_keep is None else max_keep,
+                                           self.group, device=sh.key.device)
+        idx = np.sort(idx)
+        return (idx if max_keep is None else idx[:max_keep]), total, near
+
+    def _gather_ll_cyclic(self, glo, ghi):
+        import torch.distributed as dist
+
+        world = dist.get_world_size(self.group)
+        mine = [ll.cpu().numpy() for _, _, ll in self.segments]
+        flat = allgather_ragged(np.concatenate(mine) if mine else np.zeros(0), self.group,
+                                self.shards[0].key.device)
+        # every rank knows every rank's segment layout: rank-major, rounds in order
+        n_hi = max((b for _, b in self.rounds), default=0)
+        out = np.full(n_hi, np.nan)
+        pos = 0
+        for r in range(world):
+            for (lo, hi) in self.rounds:
+                a, b = shard_ranges(hi - lo, world)[r]
+                out[lo + a:lo + b] = flat[pos:pos + (b - a)]
+                pos += b - a
+        return out[glo:ghi]
+
     def reset_max(self):
         self.synchronize()
         for sh in self.shards:
-            with self.torch.cuda.device(sh.device):
+            with self._ctx(sh.device):
                 sh.key.copy_(sh.helper.new_llmax_key())
 
     def synchronize(self):
         for sh in self.shards:
-            self.torch.cuda.synchronize(sh.device)
+            if sh.device != "cpu":
+                self.torch.cuda.synchronize(sh.device)
 
     def global_max_key(self):
         """Combine the shard keys: host max within the process, then an integer MAX
@@ -349,7 +538,7 @@ class DeviceEngine:
             # ordering: each GPU's stream waits for the other GPUs' likelihood kernels
             events = []
             for sh in self.shards:
-                with torch.cuda.device(sh.device):
+                with self._ctx(sh.device):
                     ev = torch.cuda.Event()
                     ev.record(torch.cuda.current_stream(sh.device))
                     events.append(ev)
@@ -362,7 +551,12 @@ class DeviceEngine:
             for k in keys:
                 k.fill_(m)
         if self.group is not None:
-            allreduce_max_key(keys[0], self.group)
+            if self._lib_collectives():
+                sh = self.shards[0]
+                with self._ctx(sh.device):
+                    sh.helper.allreduce_max_key(LibComm.get(self.group, sh.device), keys[0])
+            else:
+                allreduce_max_key(keys[0], self.group)
             for k in keys[1:]:
                 k.copy_(keys[0].to(k.device))
         return keys[0]
@@ -383,14 +577,32 @@ class DeviceEngine:
         """
         torch = self.torch
         # hi is a GLOBAL count of accumulated samples; this process owns part of it
+        n_accum = self.n_global if hi is None else int(hi)
+        if getattr(self, "cyclic", False):
+            return self._accept_cyclic(rng, n_accum, max_keep, uniforms, near_tol)
         hi = self.n_local if hi is None else max(0, min(hi - self.global_offset, self.n_local))
+        if self._lib_collectives():
+            # one rank per GPU over NCCL: max all-reduce, accept and the gathers of counts
+            # and indices all run inside the library (tjb_accept_dist)
+            sh = self.shards[0]
+            with self._ctx(sh.device):
+                comm = LibComm.get(self.group, sh.device)
+                u_dev = None
+                if uniforms is not None:
+                    g0 = self.global_offset
+                    u_dev = torch.from_numpy(np.ascontiguousarray(uniforms[g0:g0 + hi])).to(sh.ll.device)
+                idx, tot, nn = sh.helper.accept_dist(
+                    comm, sh.ll[:hi], sh.key, self.global_offset, uniforms=u_dev,
+                    rng=None if uniforms is not None else rng, max_keep=max_keep,
+                    n_global=n_accum, near_tol=near_tol)
+                return idx.cpu().numpy(), tot, nn
         self.global_max_key()
         per_idx, per_tot, near = [], [], 0
         for sh in self.shards:
             a, b = sh.lo, min(hi, sh.hi)
             if a >= b:
                 continue
-            with torch.cuda.device(sh.device):
+            with self._ctx(sh.device):
                 ll = sh.ll[: b - a]
                 if uniforms is not None:
                     g0 = self.global_offset
@@ -408,13 +620,25 @@ class DeviceEngine:
                 near += nn
         idx, total = merge_accepted(per_idx, per_tot, max_keep)
         if self.group is not None:
-            idx, total, near = gather_accepted(idx, total, near, max_keep, self.group)
+            idx, total, near = gather_accepted(idx, total, near, max_keep, self.group,
+                                               device=self.shards[0].ll.device)
         return idx, total, near
+
+    def _lib_collectives(self):
+        """True when the cross-rank accept can run inside the library: a torch group on the
+        NCCL backend and one shard (GPU) per rank."""
+        if self.group is None or len(self.shards) != 1:
+            return False
+        import torch.distributed as dist
+
+        return dist.get_backend(self.group) == "nccl"
 
     def gather_ll(self, glo=0, ghi=None):
         """ll over the GLOBAL range [glo, ghi) on every rank (rank-ordered concatenation,
         multiproc_helpers.py:120 ``np.concatenate(results)``)."""
         ghi = self.n_global if ghi is None else ghi
+        if getattr(self, "cyclic", False):
+            return self._gather_ll_cyclic(glo, ghi)
         lo = max(glo, self.global_offset) - self.global_offset
         hi = min(ghi, self.global_offset + self.n_local) - self.global_offset
         mine = self.download_ll(lo, hi) if lo < hi else np.zeros(0)
@@ -422,9 +646,7 @@ class DeviceEngine:
             return mine
         import torch.distributed as dist
 
-        parts = [None] * dist.get_world_size(self.group)
-        dist.all_gather_object(parts, mine, group=self.group)
-        return np.concatenate(parts)
+        return allgather_ragged(mine, self.group, self.shards[0].ll.device)
 
     # -- host access ------------------------------------------------------------
     def download_ll(self, lo=0, hi=None):

@@ -130,7 +130,7 @@ class TheJoker:
             raise ValueError("packed prior samples must have shape (n, 5)")
         return [np.ascontiguousarray(arr[:, i]) for i in range(5)], None
 
-    def _engine(self, data, cols, helper0=None):
+    def _engine(self, data, cols, helper0=None, cyclic=False):
         # helper0: the helper the caller already built to read units / columns; reused
         # for its device instead of creating a second handle for the same star
         helpers = {} if helper0 is None else {helper0.device: helper0}
@@ -148,6 +148,11 @@ class TheJoker:
             from .sharding import shard_ranges
 
             n = len(cols[0])
+            if cyclic:
+                # every range the iterative sampler evaluates is split over all the ranks
+                eng = DeviceEngine(make, cols, devices=self.devices[:1], group=self.group,
+                                   global_offset=0, global_size=n, cyclic=True)
+                return eng, make(self.devices[0])
             rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
             lo, hi = shard_ranges(n, world)[rank]
             local = [c if np.ndim(c) == 0 else c[lo:hi] for c in cols]
@@ -358,7 +363,7 @@ class TheJoker:
             if n_max < n_total:
                 cols = [c if np.ndim(c) == 0 else c[:n_max] for c in cols]
 
-        eng, helper = self._engine(data, cols, helper0)
+        eng, helper = self._engine(data, cols, helper0, cyclic=True)
         start_idx = 0
         n_accum = 0
         good = np.zeros(0, dtype=np.int64)
