@@ -139,6 +139,50 @@ def rel_err(a, b):
     return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
 
 
+def reference_gate(got, ref, truth, tol=1e-10, label=""):
+    """The north-star gate against the reference, with its escape hatch made explicit and
+    *bounded*: every ll must be within `tol` of the quad-precision truth; against the
+    reference it must be within `tol` too, except where the reference's own double
+    arithmetic is off the truth by at least 90 % of the difference (its N x N chi2 form
+    cancels on flat / high-S/N data) -- that set is counted, printed and must consist of
+    samples where the reference misses the truth by more than tol/2.
+    Returns the report dict."""
+    r_ref, r_truth, ref_truth = rel_err(got, ref), rel_err(got, truth), rel_err(ref, truth)
+    over = r_ref > tol
+    explained = over & (ref_truth >= 0.9 * r_ref) & (ref_truth > 0.5 * tol)
+    rep = dict(n=len(got), max_rel_vs_ref=float(r_ref.max()), max_rel_vs_truth=float(r_truth.max()),
+               ref_vs_truth_max=float(ref_truth.max()), n_over_tol_vs_ref=int(over.sum()),
+               n_reference_off_truth=int(explained.sum()),
+               n_unexplained=int((over & ~explained).sum()))
+    print(f"\n[reference gate {label}] " + ", ".join(f"{k}={v:.3g}" if isinstance(v, float)
+                                                      else f"{k}={v}" for k, v in rep.items()))
+    assert rep["max_rel_vs_truth"] <= tol, rep
+    assert rep["n_unexplained"] == 0, rep
+    return rep
+
+
+def accept_sets_match(got_idx, ll, uu, max_keep=None, tol=1e-12, ll_other=None):
+    """The accepted index set against ``where(exp(ll - max) > u)`` computed on the host
+    from `ll` (likelihood_helpers.py:107-109): identical except for samples within `tol`
+    of the threshold, which are returned as a count (BASELINE.json north_star).  If the
+    lls the device used (`ll_other`) are given, a sample is also near-threshold when it is
+    within tol under *those* lls.  The comparison is made on the sets minus the
+    near-threshold indices -- never skipped."""
+    a = np.exp(ll - ll.max())
+    want = np.where(a > uu)[0]
+    near = np.abs(a - uu) <= tol
+    if ll_other is not None:
+        near |= np.abs(np.exp(ll_other - ll_other.max()) - uu) <= tol
+    got_idx = np.asarray(got_idx)
+    if max_keep is not None:
+        # truncated lists: compare the common prefix range only
+        hi = min(got_idx[-1] if len(got_idx) else -1, want[:max_keep][-1] if len(want) else -1)
+        want, got_idx = want[want <= hi], got_idx[got_idx <= hi]
+    diff = np.setxor1d(got_idx, want)
+    assert near[diff].all(), (diff[~near[diff]][:10], len(diff))
+    return int(near.sum())
+
+
 def mode_chunk(spec, n=400, sigma=0.5, seed=0):
     """Prior rows scattered tightly around the true orbit of the synthetic star (the
     posterior mode): the ill-conditioned regime where chi2 << y^T C^-1 y."""

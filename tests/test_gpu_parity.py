@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 import pytest
-from helpers import prior_chunk, rel_err, star_spec
+from helpers import accept_sets_match, prior_chunk, reference_gate, rel_err, star_spec
 
 pytestmark = pytest.mark.gpu
 
@@ -42,10 +42,13 @@ def make_helper(spec_args, device=0, **kw):
     return tj.CJokerHelper(all_data, prior, trend_M, device=device, jitter_mode=jm), spec, data, prior
 
 
-def parity_ok(got, ref, truth):
-    r_ref, r_truth, ref_truth = rel_err(got, ref), rel_err(got, truth), rel_err(ref, truth)
-    ok = (r_ref <= 1e-10) | (r_truth <= ref_truth)
-    return ok, r_ref, r_truth, ref_truth
+def rows_to_idx(column, values):
+    """Indices of `values` in a prior column of distinct numbers (accepted rows -> indices)."""
+    order = np.argsort(column)
+    pos = np.searchsorted(column[order], values)
+    idx = order[pos]
+    assert np.array_equal(column[idx], values)
+    return idx
 
 
 SPEC_KEYS = ("t", "rv", "ivar", "t0", "trend_M", "mu", "Lambda", "K_prior_kind", "sigma_K0", "P0",
@@ -61,9 +64,7 @@ def test_golden_vectors(torch_cuda, path):
     spec = {k: (z[k] if z[k].ndim else z[k].item()) for k in SPEC_KEYS}
     helper = tj.CJokerHelper.from_spec(spec, device=0)
     ll = helper.batch_marginal_ln_likelihood(np.ascontiguousarray(z["chunk"]))
-    ok, r_ref, r_truth, ref_truth = parity_ok(ll, z["ll"], z["ll_truth"])
-    assert ok.all(), (r_ref.max(), r_truth.max(), ref_truth.max())
-    assert r_truth.max() < 1e-10
+    reference_gate(ll, z["ll"], z["ll_truth"], label=os.path.basename(path)[:-4])
     lls, a, A = helper.posterior_aA(z["chunk"][:16])
     assert np.allclose(a, z["post_a"], rtol=1e-8, atol=1e-10)
     assert np.allclose(A, z["post_A"], rtol=1e-7, atol=1e-14)
@@ -74,8 +75,15 @@ def test_golden_vectors(torch_cuda, path):
     key = helper.new_llmax_key()
     helper.llmax_update(ll_dev, key)
     idx, tot, near = helper.accept(ll_dev, key, uniforms=torch.from_numpy(z["uniforms"]).cuda())
-    if near == 0 and np.max(r_ref) < 1e-12:
-        assert np.array_equal(idx.cpu().numpy(), z["good"])
+    # the device set against the host rule on the device's own lls: bit-exact minus the
+    # near-threshold samples; against the oracle's set: the same minus samples the
+    # ll difference (<= 1e-10 relative) moves across the threshold, which are counted
+    n_near = accept_sets_match(idx.cpu().numpy(), ll, z["uniforms"])
+    assert n_near == near
+    a_ref = np.exp(z["ll"] - z["ll"].max())
+    moved = np.abs(a_ref - z["uniforms"]) <= np.abs(a_ref - np.exp(ll - ll.max())) + 1e-12
+    diff = np.setxor1d(idx.cpu().numpy(), z["good"])
+    assert moved[diff].all() and len(diff) <= 1, (len(diff), diff[:5])
 
 
 @pytest.mark.parametrize("path", REF_GOLDEN, ids=[os.path.basename(p)[:-4] for p in REF_GOLDEN])
@@ -92,12 +100,17 @@ def test_reference_cython_golden_vectors(torch_cuda, path):
     helper = tj.CJokerHelper.from_spec(spec, device=0)
     chunk = np.ascontiguousarray(z["chunk"])
     ll = helper.batch_marginal_ln_likelihood(chunk)
-    r = rel_err(ll, z["ref_ll"])
-    flat = "flat" in path  # K = 1e-4: chi2 cancels to ~1e-12 of its terms in the reference
-    assert r.max() < (1e-8 if flat else 1e-10), r.max()
+    # quad-precision value of the same inputs (tests/golden/make_ref_truth.py): the gate is
+    # 1e-10 against the reference AND against the truth; on the flat star (K = 1e-4) the
+    # reference's own N x N chi2 form is up to 2e-10 off the truth on a few rows, which the
+    # gate counts instead of loosening the tolerance
+    name = os.path.basename(path)[:-4]
+    truth = np.load(os.path.join(os.path.dirname(path), "ref_truth.npz"))[name]
+    rep = reference_gate(ll, z["ref_ll"], truth, label=name)
+    assert rep["n_reference_off_truth"] <= (4 if "flat" in path else 0)
     n_post = len(z["ref_worker_ll"])
     lls, a, A = helper.posterior_aA(chunk[:n_post], clamp_K=False)
-    assert np.max(rel_err(lls, z["ref_worker_ll"])) < (1e-8 if flat else 1e-10)
+    reference_gate(lls, z["ref_worker_ll"], truth[:n_post], label=name + " worker")
     assert np.allclose(a, z["ref_worker_a"], rtol=1e-8, atol=1e-10)
     assert np.allclose(A, z["ref_worker_A"], rtol=1e-7, atol=1e-14)
     # the reference's own draw: numpy multivariate_normal(a, inv(Ainv)) with the same rng
@@ -169,19 +182,24 @@ def test_live_reference_cython(torch_cuda, N, pt, kw):
     chunk = prior_chunk(4096, seed=77, s_lognormal=(-1.0, 1.0))
     want = ref.batch_marginal_ln_likelihood(chunk)
     got = helper.batch_marginal_ln_likelihood(chunk)
-    r = rel_err(got, want)
+    from oracle.oracle import OracleHelper
+
+    truth, _ = OracleHelper.from_spec(spec_ref_mode).truth_ll(chunk)
     flat = "K" in kw  # chi2 cancels to ~1e-12 of its terms in the reference itself
-    assert r.max() < (1e-8 if flat else 1e-10), r.max()
+    rep = reference_gate(got, want, truth, label=f"live N={N} pt={pt} {kw}")
+    assert rep["n_reference_off_truth"] <= (0.02 * len(chunk) if flat else 0)
     lls, a, A = helper.posterior_aA(chunk[:8], clamp_K=False)
     for i in range(8):
         ll_ref, mats = ref.test_likelihood_worker(chunk[i])
-        assert abs(lls[i] - ll_ref) <= (1e-8 if flat else 1e-10) * abs(ll_ref)
+        assert abs(lls[i] - ll_ref) <= 1e-10 * abs(ll_ref) or \
+            abs(ll_ref - truth[i]) >= 0.9 * abs(lls[i] - ll_ref)
+        assert abs(lls[i] - truth[i]) <= 1e-10 * abs(truth[i])
         assert np.allclose(a[i], mats["a"], rtol=1e-8, atol=1e-10)
         assert np.allclose(A[i], mats["A"], rtol=1e-7, atol=1e-14)
     # the single-row entry point leaves the reference's public attributes behind
     ll1 = helper.test_likelihood_worker(chunk[0])
     ll_ref, mats = ref.test_likelihood_worker(chunk[0])
-    assert abs(ll1 - ll_ref) <= (1e-8 if flat else 1e-10) * abs(ll_ref)
+    assert abs(ll1 - truth[0]) <= 1e-10 * abs(truth[0])
     assert np.allclose(helper.a, mats["a"], rtol=1e-8, atol=1e-10)
     assert np.allclose(helper.A, mats["A"], rtol=1e-7, atol=1e-14)
     assert np.allclose(helper.Ainv, mats["Ainv"], rtol=1e-6)
@@ -221,10 +239,12 @@ def test_reference_rejection_driver_vectors(torch_cuda, path):
 
     mk = lambda seed: tj.TheJoker(prior, rng=np.random.default_rng(seed), devices=[0],
                                   jitter_mode="reference", draw="numpy")
-    flat = "flat" in path
     smp, lls = mk(int(z["seed_rej"])).rejection_sample(data, chunk, n_linear_samples=2,
                                                        return_all_logprobs=True, in_memory=True)
-    assert np.max(rel_err(lls, z["rej_lls"])) < (1e-8 if flat else 1e-10)
+    name = os.path.basename(path)[:-4]
+    truth = np.load(os.path.join(os.path.dirname(path), "ref_truth.npz"))[name]
+    rep = reference_gate(lls, z["rej_lls"], truth, label=name)
+    assert rep["n_reference_off_truth"] <= (16 if "flat" in path else 0)
     close(packed(smp), z["rej_raw"])
     smp = mk(int(z["seed_rej"])).rejection_sample(data, chunk, max_posterior_samples=3,
                                                   in_memory=True)
@@ -259,12 +279,10 @@ def test_ll_parity_host_path(torch_cuda, oracle_lib, args, sl, kw):
     ref = orc.batch_marginal_ln_likelihood(chunk, n_threads=0)
     truth, kappa = orc.truth_ll(chunk)
     ll = helper.batch_marginal_ln_likelihood(chunk)
-    ok, r_ref, r_truth, ref_truth = parity_ok(ll, ref, truth)
-    print(f"\n{args} {kw}: max rel vs oracle {r_ref.max():.2e} (frac>1e-10: "
-          f"{np.mean(r_ref > 1e-10):.1e}), vs truth {r_truth.max():.2e}, oracle vs truth "
-          f"{ref_truth.max():.2e}")
-    assert ok.all()
-    assert r_truth.max() < 1e-10
+    rep = reference_gate(ll, ref, truth, label=f"{args} {kw}")
+    # how many samples lean on the truth is bounded: a handful on the flat star (the
+    # reference's uncentred chi2 cancels) and with high-order trend columns, none otherwise
+    assert rep["n_reference_off_truth"] <= (0.005 * n if (kw.get("K") == 1e-4 or args[1] >= 2) else 0), rep
     # ragged / tiny / empty inputs
     for m in (0, 1, 31, 33, 257):
         part = helper.batch_marginal_ln_likelihood(np.ascontiguousarray(chunk[:m]))
@@ -543,10 +561,13 @@ def test_accept_bit_exact(torch_cuda, oracle_lib, flat):
                                          max_keep=max_keep)
         idx2, tot2, _ = helper.accept(ll_dev, key, rng=rng, max_keep=max_keep)
         assert n_near == near
+        # same ll, same uniforms: the sets are identical minus the near-threshold samples
+        # (the comparison is always made; near-threshold indices are removed, not the test)
+        assert accept_sets_match(idx.cpu().numpy(), ll, uu, max_keep) == near
+        assert accept_sets_match(idx2.cpu().numpy(), ll, uu, max_keep) == near
+        assert tot == tot2 and abs(tot - len(oracle_lib.rejection_accept(ll, uu))) <= near
         if near == 0:
             assert np.array_equal(idx.cpu().numpy(), want)
-            assert np.array_equal(idx2.cpu().numpy(), want)
-            assert tot == tot2 == len(oracle_lib.rejection_accept(ll, uu))
     if flat:
         assert tot > 10  # test_sampler.py:156: uninformative data keeps many samples
     # offsets: shard [lo, hi) of a larger stream reports global indices
@@ -606,7 +627,9 @@ def test_rejection_sample_api(torch_cuda, oracle_lib):
         ref_ll = orc.batch_marginal_ln_likelihood(chunk, 0)
         uu = np.random.default_rng(42).uniform(size=len(chunk))
         good = oracle_lib.rejection_accept(ref_ll, uu, 64)
-        if oracle_lib.near_threshold_count(ref_ll, uu) == 0:
+        # the accepted rows against the oracle's, minus the near-threshold samples
+        n_near = accept_sets_match(rows_to_idx(chunk[:, 0], got["P"].value), ref_ll, uu, 64)
+        if n_near == 0:
             assert np.array_equal(got["P"].value, chunk[good, 0])
         assert joker.last_stats["n_near_threshold"] == oracle_lib.near_threshold_count(ref_ll, uu)
         with pytest.raises(ValueError):
@@ -1001,14 +1024,15 @@ def test_baseline_config3_jitter_trend(torch_cuda, oracle_lib):
     ref = orc.batch_marginal_ln_likelihood(chunk, 0)
     uu = np.random.default_rng(42).uniform(size=len(chunk))
     good = oracle_lib.rejection_accept(ref, uu, 256)
-    if oracle_lib.near_threshold_count(ref, uu) == 0:
+    got_idx = rows_to_idx(chunk[:, 0], got["P"].value)
+    n_near = accept_sets_match(got_idx, ref, uu, 256)
+    assert np.array_equal(got["s"].value, chunk[got_idx, 4])
+    if n_near == 0:
         assert np.array_equal(got["P"].value, chunk[good, 0])
-        assert np.array_equal(got["s"].value, chunk[good, 4])
     assert list(got.keys())[:8] == ["P", "e", "omega", "M0", "s", "K", "v0", "v1"]
     ll = joker.marginal_ln_likelihood(data, ps)
     truth, _ = orc.truth_ll(chunk[:4096])
-    ok, r_ref, r_truth, ref_truth = parity_ok(ll[:4096], ref[:4096], truth)
-    assert ok.all() and r_truth.max() < 1e-10
+    reference_gate(ll[:4096], ref[:4096], truth, label="config3 jitter + trend")
 
 
 def test_baseline_config4_iterative_n256(torch_cuda, oracle_lib):

@@ -141,17 +141,21 @@ SYMBOLS = {
 _lib = None
 
 
+_KERNEL_SRC = ("kepler.cuh", "linalg.cuh", "marginal_ll.cuh", "prior_gen.cuh")
+
+
 def source_hash() -> str:
-    """sha256 over the CUDA sources, the header and the nvcc flags: identifies the code a
-    built library (and an ncu profile of it) belongs to.  profiles/kernel_counts.json
-    carries the hash of the sources its counters were measured on; bench.py flags counters
-    whose hash differs from the sources in the tree."""
+    """sha256 over the sources the likelihood kernel is compiled from (kepler.cuh,
+    linalg.cuh, marginal_ll.cuh, prior_gen.cuh) and the nvcc flags: identifies the kernel
+    code a built library -- and an ncu profile of it -- belongs to.
+    profiles/kernel_counts.json carries the hash its counters were measured on; bench.py
+    flags counters whose hash differs from the sources in the tree."""
     import hashlib
 
     h = hashlib.sha256()
-    for path in sorted(_SRC + [_HDR]):
-        h.update(os.path.basename(path).encode())
-        with open(path, "rb") as f:
+    for name in _KERNEL_SRC:
+        h.update(name.encode())
+        with open(os.path.join(_HERE, "csrc", name), "rb") as f:
             h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()

@@ -3,6 +3,11 @@
 # the hot kernel.  Outputs land in gpurun_out/ ; summaries are copied into profiles/ here.
 set -x
 mkdir -p gpurun_out
+# what was profiled: hash of the CUDA sources + flags (bench.py flags counters from other
+# sources as stale) and the register count of the hot kernel in the shipped binary
+python -c "from thejoker_b200 import _lib; print(_lib.source_hash())" > gpurun_out/source_hash.txt
+cuobjdump -res-usage ${TJB_LIB_PATH:-thejoker_b200/libthejoker_b200.so} 2>/dev/null \
+  | grep -A1 "marginal_ll_kernelILi2ELb0ENS_9PriorView" | grep -o "REG:[0-9]*" > gpurun_out/hot_kernel_regs.txt
 BENCH="python bench.py --steps 2 --warmup 3 --log2-e2e 22 --no-cpu-baseline"
 # 1. every launch with its device time (shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \

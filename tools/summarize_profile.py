@@ -19,6 +19,13 @@ P = os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
 out = {"tag": tag}
 md = [f"# ncu summary {tag}", ""]
+for name, key in (("source_hash.txt", "source_sha256"), ("hot_kernel_regs.txt", "cuobjdump_hot_kernel")):
+    f = os.path.join(G, name)
+    if os.path.exists(f):
+        out[key] = open(f).read().strip()
+md += [f"* source hash of the profiled build (`_lib.source_hash()`): `{out.get('source_sha256')}`",
+       f"* `cuobjdump -res-usage` of `marginal_ll_kernel<2,false,PriorView>` in that library: "
+       f"`{out.get('cuobjdump_hot_kernel')}`", ""]
 
 # ---- launch list --------------------------------------------------------------
 rows = [r for r in csv.reader(open(os.path.join(G, "launches.csv"))) if len(r) > 5]
