@@ -161,26 +161,35 @@ def reference_gate(got, ref, truth, tol=1e-10, label=""):
     return rep
 
 
-def accept_sets_match(got_idx, ll, uu, max_keep=None, tol=1e-12, ll_other=None):
+def accept_sets_match(got_idx, ll, uu, max_keep=None, tol=1e-12, ll_other=None, llmax=None,
+                      index_base=0):
     """The accepted index set against ``where(exp(ll - max) > u)`` computed on the host
     from `ll` (likelihood_helpers.py:107-109): identical except for samples within `tol`
     of the threshold, which are returned as a count (BASELINE.json north_star).  If the
-    lls the device used (`ll_other`) are given, a sample is also near-threshold when it is
-    within tol under *those* lls.  The comparison is made on the sets minus the
-    near-threshold indices -- never skipped."""
-    a = np.exp(ll - ll.max())
+    lls the device used (`ll_other`) are given, a sample is also excused when its
+    threshold u lies between exp(ll - max) and exp(ll_other - max), i.e. when the (<= 1e-10
+    relative) difference of the two implementations' ll moves it across; those are counted
+    separately.  The comparison is made on the sets minus those indices -- never skipped.
+    `llmax` overrides ll.max() (a slice of a larger run); `index_base` is subtracted from
+    got_idx.  Returns (n_near, n_moved)."""
+    m = ll.max() if llmax is None else llmax
+    a = np.exp(ll - m)
     want = np.where(a > uu)[0]
     near = np.abs(a - uu) <= tol
+    moved = np.zeros(len(ll), dtype=bool)
     if ll_other is not None:
-        near |= np.abs(np.exp(ll_other - ll_other.max()) - uu) <= tol
-    got_idx = np.asarray(got_idx)
+        b = np.exp(ll_other - m)
+        near |= np.abs(b - uu) <= tol
+        moved = ((a > uu) != (b > uu)) & ~near
+    got_idx = np.asarray(got_idx) - index_base
     if max_keep is not None:
         # truncated lists: compare the common prefix range only
         hi = min(got_idx[-1] if len(got_idx) else -1, want[:max_keep][-1] if len(want) else -1)
         want, got_idx = want[want <= hi], got_idx[got_idx <= hi]
     diff = np.setxor1d(got_idx, want)
-    assert near[diff].all(), (diff[~near[diff]][:10], len(diff))
-    return int(near.sum())
+    ok = near[diff] | moved[diff]
+    assert ok.all(), (diff[~ok][:10], len(diff))
+    return int(near.sum()), int(moved[diff].sum())
 
 
 def mode_chunk(spec, n=400, sigma=0.5, seed=0):

@@ -39,6 +39,11 @@ def _run(joker, flat, ps):
     s = joker.iterative_rejection_sample(flat, ps, n_requested_samples=64, in_memory=True)
     out["it_P"], out["it_K"] = s["P"].value, s["K"].value
     out["n_eval"] = joker.last_stats["n_ll_evaluated"]
+    # a prior that is drawn (counter-based generator): sample g depends on (seed, g) only,
+    # so every sharding evaluates the same prior and accepts the same rows
+    s = joker.rejection_sample(flat, 1 << 17, max_posterior_samples=100, return_logprobs=True)
+    out["gen_P"], out["gen_K"] = s["P"].value, s["K"].value
+    out["gen_lp"], out["gen_ll"] = s["ln_prior"].value, s["ln_likelihood"].value
     return out
 
 

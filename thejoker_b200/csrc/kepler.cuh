@@ -53,8 +53,10 @@ namespace tjb {
 #define TJB_TRIG_TABLE 1
 #endif
 
-// Instruction-trimmed variant of the epoch loop (default off until it has been timed on the
-// GPU; tools/build_variants.sh builds it, tests/test_host_logic.py checks its numerics):
+// Instruction-trimmed variant of the epoch loop (the default since round 2: timed on B200,
+// profiles/r02a_tune_variants.jsonl -- together with TJB_PHASE_FIXED, TJB_HALLEY, a
+// 2048-node table and 3 epochs per iteration 3.07e9 -> 3.73e9 samples/s at N = 64;
+// tests/test_host_logic.py checks the numerics of every combination):
 //   * e cosE / (6 f1) = (1/f1 - 1)/6: one FMA instead of two multiplies, FP64 and FP32 stage
 //   * FP32 stage: t/2 computed once
 //   * convergence vote on one max of the sign-stripped high words (per-epoch flags are
@@ -62,10 +64,10 @@ namespace tjb {
 //   * 0.5 pinned in a register pair (ptxas otherwise materialises it per iteration)
 // Saves ~1 FP64 and ~4.5 other instructions per (sample, epoch).
 #ifndef TJB_TRIM
-#define TJB_TRIM 0
+#define TJB_TRIM 1
 #endif
 
-// Phase reduction of the FP32 stage in fixed point (default off until timed on the GPU).
+// Phase reduction of the FP32 stage in fixed point (default on since round 2).
 // The shipped loop rounds the unreduced phase x4 to float first, so its starter carries an
 // error of ulp_float(x4)/2 -- 3.8e-4 rad at 2000 revolutions (P = 2 d over a 4000 d
 // baseline), above the 2^-13 threshold of the one-pass FP64 step: such lanes send their
@@ -77,11 +79,11 @@ namespace tjb {
 // |x4| < 2^(19+U) units (2^19 revolutions).  Replaces F2F.F32.F64 + three FP32
 // instructions by DADD + I2F.
 #ifndef TJB_PHASE_FIXED
-#define TJB_PHASE_FIXED 0
+#define TJB_PHASE_FIXED 1
 #endif
 
 // Second-order (Halley) FP64 step on the main path instead of the third-order one (default
-// off until timed on the GPU).  The FP32 stage leaves an error of a few 1e-7 / (1 - e cosE);
+// on since round 2).  The FP32 stage leaves an error of a few 1e-7 / (1 - e cosE);
 // a cubically convergent step takes that below 1e-16 as long as the step itself is below
 // 2^-17 (7.6e-6: error <= 4.4e-16 (t^2/2 - e cosE/(6 f1)), i.e. 1e-15 at e = 0.9 and 1e-13
 // at e = 0.999 in the worst case), and for such a step sin(delta) = delta to 7e-17.  Saves
@@ -90,7 +92,14 @@ namespace tjb {
 // the third-order step.  Meant to be combined with TJB_PHASE_FIXED (a float-rounded phase
 // alone exceeds the tighter threshold beyond ~100 revolutions).
 #ifndef TJB_HALLEY
-#define TJB_HALLEY 0
+#define TJB_HALLEY 1
+#endif
+
+// Convergence vote on the high word of delta^2 (which the rotation needs anyway and which
+// has no sign to strip) instead of the sign-stripped high word of delta: one integer
+// instruction less per epoch.  Needs TJB_TRIM.
+#ifndef TJB_VOTE_D2
+#define TJB_VOTE_D2 0
 #endif
 
 // 1.5 * 2^52 (1.5 * 2^23): adding it rounds to the nearest integer and leaves
@@ -99,7 +108,7 @@ constexpr double kMagic = 6755399441055744.0;
 constexpr float kMagicF = 12582912.0f;
 constexpr double kTwoPi = 6.28318530717958647692528676655900577;
 #ifndef TJB_TRIG_TABLE_LOG2
-#define TJB_TRIG_TABLE_LOG2 10
+#define TJB_TRIG_TABLE_LOG2 11
 #endif
 #if TJB_TRIG_TABLE
 constexpr int kTrigTableSize = 1 << TJB_TRIG_TABLE_LOG2;
@@ -357,6 +366,7 @@ constexpr int kF64MaxIter = 64;
 #define TJB_NEED_LOG2 (TJB_HALLEY ? 17 : 13)
 #endif
 constexpr unsigned kNeedHi = (unsigned)(1023 - TJB_NEED_LOG2) << 20;
+constexpr unsigned kNeedHiSq = (unsigned)(1023 - 2 * TJB_NEED_LOG2) << 20;  // of the threshold squared
 
 // run-wide solver statistics (device counters, touched only on the rare path):
 // [0] extra FP64 passes (lane-epochs), [1] epochs that hit kF64MaxIter
@@ -557,7 +567,10 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
     // error map of the step: eps -> ~C eps^4 (tools/kepler_solver_study.py); a lane
     // that moved by 2^-13 (1.2e-4) or more, or produced a NaN, takes further passes.
     // The test reads the exponent field on the integer pipe instead of a DSETP.
-#if TJB_TRIM
+#if TJB_TRIM && TJB_VOTE_D2
+    const unsigned hk = (unsigned)hi32(del[k] * del[k]);  // NaN: 0x7ff8.. / 0xfff8.. -> above
+    top = hk > top ? hk : top;
+#elif TJB_TRIM
     const unsigned hk = (unsigned)hi32(del[k]) << 1;
     top = hk > top ? hk : top;
 #else
@@ -565,7 +578,9 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
     any_need = any_need || need[k];
 #endif
   }
-#if TJB_TRIM
+#if TJB_TRIM && TJB_VOTE_D2
+  any_need = top >= kNeedHiSq;
+#elif TJB_TRIM
   any_need = top >= (kNeedHi << 1);
 #endif
   if (!any_lane(any_need)) {
@@ -578,7 +593,9 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
     for (int k = 0; k < K; k++) {
       SinCos fr = {sE[k], cE[k]};
       TJB_MAIN_ROTATE(tc, del[k], fr.s, fr.c);
-#if TJB_TRIM
+#if TJB_TRIM && TJB_VOTE_D2
+      need[k] = (unsigned)hi32(del[k] * del[k]) >= kNeedHiSq;
+#elif TJB_TRIM
       need[k] = ((unsigned)hi32(del[k]) << 1) >= (kNeedHi << 1);
 #endif
       const SinCos r = solve_extra_passes<kCountStats>(oc.e, tc.table, x4[k], D[k] + del[k], fr,

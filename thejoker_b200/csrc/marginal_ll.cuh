@@ -47,7 +47,7 @@ TJB_HD constexpr int row_stride(int L) { return (L + 2 + 1) & ~1; }
 
 // epochs processed per loop iteration of the constant-jitter kernel
 #ifndef TJB_EPOCHS_PER_ITER
-#define TJB_EPOCHS_PER_ITER 2
+#define TJB_EPOCHS_PER_ITER 3
 #endif
 constexpr int kEpochsPerIter = TJB_EPOCHS_PER_ITER;
 
