@@ -983,6 +983,7 @@ def test_prior_cache_path(torch_cuda, tmp_path):
     (thejoker.py:243-255) on the native SoA cache."""
     import thejoker_b200 as tj
     from helpers import default_prior
+    from thejoker_b200 import units as u
     from thejoker_b200.cache import write_prior_cache
     from thejoker_b200.synthetic import make_data
 
@@ -997,6 +998,32 @@ def test_prior_cache_path(torch_cuda, tmp_path):
     assert len(a) == len(b) > 10
     for k in ("P", "K", "ln_prior", "ln_likelihood"):
         assert np.array_equal(a[k].value, b[k].value)
+    # the file path under the reference's own file name: JokerSamples.write (this package's
+    # container, whatever the extension) and a file in the reference's HDF5 layout
+    # (tests/hdf5_writer.py), both told apart by their first bytes
+    import json
+    import warnings
+
+    from hdf5_writer import write_reference_style_hdf5
+
+    npz_path = str(tmp_path / "prior_samples.hdf5")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)
+        ps.write(npz_path)
+    hdr = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_table_headers.json")))
+    rows = np.zeros(len(ps), dtype=[(c, "<f8") for c in ("P", "e", "omega", "M0", "s", "ln_prior")])
+    for c in ("P", "e", "omega", "M0"):
+        rows[c] = ps[c].value
+    rows["s"] = ps["s"].to_value(u.m / u.s)  # the stored header declares s in m/s
+    rows["ln_prior"] = ps["ln_prior"].value
+    h5_path = write_reference_style_hdf5(str(tmp_path / "ref_layout.hdf5"), rows,
+                                         [ln.encode() for ln in hdr["prior_samples"]],
+                                         chunk_rows=4096, two_level=True)
+    for pth in (npz_path, h5_path):
+        c = tj.TheJoker(prior, rng=np.random.default_rng(4)).rejection_sample(
+            flat, pth, return_logprobs=True, n_prior_samples=20_000)
+        for k in ("P", "K", "ln_prior", "ln_likelihood"):
+            assert np.array_equal(a[k].value, c[k].value), (pth, k)
 
 
 def test_baseline_config3_jitter_trend(torch_cuda, oracle_lib):

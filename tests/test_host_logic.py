@@ -365,7 +365,7 @@ def test_host_emulated_ll_matches_oracle(N, pt, sl, kw):
         assert np.max(r_truth) < 1e-10
 
 
-VARIANTS = [LEGACY, "TJB_VOTE_D2=1", "TJB_VOTE_D2=1 TJB_EPOCHS_PER_ITER=4",
+VARIANTS = [LEGACY, "TJB_NEED_LOG2=16", "TJB_NEED_LOG2=17", "TJB_VOTE_D2=1", "TJB_VOTE_D2=1 TJB_EPOCHS_PER_ITER=4",
             "TJB_TRIM=1", "TJB_PHASE_FIXED=1", "TJB_TRIM=1 TJB_PHASE_FIXED=1",
             "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_TRIG_TABLE=0",
             "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_HALLEY=1",
@@ -765,12 +765,109 @@ def test_reference_hdf5_cache_reader_and_converter(tmp_path, monkeypatch):
     assert np.array_equal(b[:, 0], rows["P"][10:20]) and np.allclose(b[:, 2], rows["s"][10:20])
 
 
-def test_reference_hdf5_reader_needs_h5py(monkeypatch):
-    from thejoker_b200.cache import read_reference_hdf5
+def test_hdf5_min_reads_a_real_libhdf5_file():
+    """hdf5_min on bytes written by libhdf5 itself (not by anything in this repository):
+    scipy ships MATLAB's ``testhdf5_7.4_GLNX86.mat`` -- an HDF5 file behind a 512-byte user
+    block, version-0 superblock, old-style root group (B-tree + local heap + symbol-table
+    node), one contiguous float64 dataset holding 0 : pi/4 : 2 pi."""
+    import scipy.io
 
-    monkeypatch.setitem(sys.modules, "h5py", None)  # import h5py -> ImportError
-    with pytest.raises(ImportError, match="h5py"):
-        read_reference_hdf5("nope.hdf5")
+    from thejoker_b200 import hdf5_min
+    from thejoker_b200.samples import file_format
+
+    path = os.path.join(os.path.dirname(scipy.io.__file__), "matlab", "tests", "data",
+                        "testhdf5_7.4_GLNX86.mat")
+    if not os.path.exists(path):
+        pytest.skip("scipy's test data is not installed")
+    assert file_format(path) == "hdf5"
+    with hdf5_min.File(path) as f:
+        assert f.keys() == ["testdouble"] and "testdouble" in f
+        d = f["testdouble"]
+        assert d.shape == (9, 1) and d.dtype == np.dtype("<f8")
+        assert np.allclose(d[()].ravel(), np.arange(9) * np.pi / 4, rtol=0, atol=1e-15)
+        with pytest.raises(KeyError):
+            f["nope"]
+
+
+@pytest.mark.parametrize("two_level,user_block", [(False, 0), (True, 0), (True, 1024)])
+def test_reference_hdf5_layout_through_hdf5_min(tmp_path, two_level, user_block):
+    """The reference's prior-cache file layout -- compound rows in a *chunked*, resizable
+    dataset (``maxshape=(None,)``, samples.py:535-545) indexed by a version-1 B-tree, YAML
+    header in a fixed-string dataset -- written byte by byte from the HDF5 format
+    specification (tests/hdf5_writer.py; no HDF5 library is in the image) and read back with
+    the dependency-free reader through the public entry points: read_reference_hdf5,
+    JokerSamples.read (format detected from the bytes), convert_reference_hdf5, read_batch."""
+    import json
+
+    from hdf5_writer import write_reference_style_hdf5
+
+    from thejoker_b200.cache import (PriorCache, convert_reference_hdf5, read_batch,
+                                     read_reference_hdf5)
+
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_table_headers.json")))
+    n = 1000  # not a multiple of the chunk size: the last chunk is partly unused
+    rng = np.random.default_rng(4)
+    rows = np.zeros(n, dtype=[(c, "<f8") for c in ("P", "e", "omega", "M0", "s", "ln_prior")])
+    rows["P"], rows["e"] = rng.uniform(2, 100, n), rng.uniform(0, 0.9, n)
+    rows["omega"], rows["M0"] = rng.uniform(0, 6, n), rng.uniform(0, 6, n)
+    rows["s"], rows["ln_prior"] = rng.uniform(0, 300, n), rng.normal(size=n)  # s in m/s
+    path = write_reference_style_hdf5(str(tmp_path / "prior_samples.hdf5"), rows,
+                                      [ln.encode() for ln in g["prior_samples"]], chunk_rows=64,
+                                      two_level=two_level, user_block=user_block)
+    assert "h5py" not in sys.modules
+    smp = read_reference_hdf5(path)
+    assert len(smp) == n and smp.poly_trend == 1 and smp.n_offsets == 0
+    for c in ("P", "e", "omega", "M0"):
+        assert np.array_equal(smp[c].value, rows[c])
+    assert np.allclose(smp["s"].to_value(u.km / u.s), rows["s"] / 1e3, rtol=1e-15)
+    assert np.array_equal(smp["ln_prior"].value, rows["ln_prior"])
+    # row ranges that start / end inside chunks and cross B-tree nodes
+    for lo, hi in ((0, 1), (63, 65), (100, 164), (500, 1000), (999, 1000), (10, 10)):
+        part = read_reference_hdf5(path, lo=lo, hi=hi)
+        assert np.array_equal(part["e"].value, rows["e"][lo:hi])
+    # the name does not matter: JokerSamples.read tells the formats apart by their bytes
+    other = str(tmp_path / "cache.dat")
+    os.replace(path, other)
+    again = tj.JokerSamples.read(other)
+    assert np.array_equal(again["M0"].value, rows["M0"])
+    out = convert_reference_hdf5(other, str(tmp_path / "native"), rows_per_block=128)
+    cols = PriorCache(out).columns()
+    for i, c in enumerate(("P", "e", "omega", "M0")):
+        assert np.array_equal(cols[i], rows[c])
+    b = read_batch(out, ["P", "e", "s"], (10, 20), units={"s": u.m / u.s})
+    assert np.array_equal(b[:, 0], rows["P"][10:20]) and np.allclose(b[:, 2], rows["s"][10:20])
+
+
+def test_hdf5_min_refuses_what_it_does_not_implement(tmp_path):
+    """Never a wrong answer: files in the new-style format or not HDF5 at all raise."""
+    from thejoker_b200 import hdf5_min
+
+    p = tmp_path / "v2.h5"
+    p.write_bytes(b"\x89HDF\r\n\x1a\n" + bytes([2]) + b"\x00" * 100)
+    with pytest.raises(NotImplementedError, match="superblock version 2"):
+        hdf5_min.File(str(p))
+    q = tmp_path / "junk.h5"
+    q.write_bytes(b"not an hdf5 file" * 10)
+    with pytest.raises(OSError):
+        hdf5_min.File(str(q))
+    with pytest.raises(OSError):
+        tj.JokerSamples.read(str(q))
+
+
+def test_samples_file_round_trip_under_the_reference_file_name(tmp_path):
+    """``prior.sample(...).write('prior_samples.hdf5')`` followed by reading the
+    same path back.  The container is this package's .npz whatever the name (a warning says
+    so); reading detects the format from the file's bytes, so the round trip works."""
+    prior = default_prior(1, sigma_K0=25.0)
+    ps = prior.sample(size=257, rng=np.random.default_rng(2), return_logprobs=True)
+    path = str(tmp_path / "prior_samples.hdf5")
+    with pytest.warns(UserWarning, match="npz"):
+        ps.write(path)
+    back = tj.JokerSamples.read(path)
+    for k in ("P", "e", "omega", "M0", "s", "ln_prior"):
+        assert np.array_equal(np.asarray(back[k].value), np.asarray(ps[k].value))
+    with pytest.raises(OSError):
+        ps.write(path)  # exists
 
 
 def test_poly_trend_zero_is_rejected_like_the_reference():

@@ -13,9 +13,8 @@ Native format here: a directory with one little-endian float64 ``.npy`` file per
 touching the rest of the file, and a constant jitter column is stored as a scalar.
 
 ``read_reference_hdf5`` / ``convert_reference_hdf5`` read the reference's own HDF5 layout
-through ``h5py`` (the reference's own dependency; it is not in the build image, so the
-tests drive these functions through a stand-in module with h5py's dataset interface and
-headers in astropy's serialisation format); the conversion is blockwise.
+through ``h5py`` when it is installed and through the package's dependency-free reader
+``hdf5_min`` otherwise (h5py is not in the build image); the conversion is blockwise.
 """
 from __future__ import annotations
 
@@ -247,21 +246,24 @@ def _meta_kwargs(meta):
 
 
 def _open_reference_hdf5(filename):
+    """h5py when it is installed (every user of the reference has it), else the package's
+    own minimal reader (hdf5_min: the structures the reference's writer produces -- version-0
+    superblock, old-style groups, chunked compound dataset, fixed-string header)."""
     try:
         import h5py
-    except ImportError as e:
-        raise ImportError("reading the reference's HDF5 prior cache needs h5py; convert it "
-                          "once with thejoker_b200.cache.convert_reference_hdf5 on a machine "
-                          "that has it") from e
+    except ImportError:
+        from . import hdf5_min
+
+        return hdf5_min.File(filename, "r")
     return h5py.File(filename, "r")
 
 
 def read_reference_hdf5(filename, lo=0, hi=None):
     """JokerSamples from rows [lo, hi) of a file written by the reference's
     ``JokerSamples.write`` (HDF5 dataset ``samples`` of compound rows; column units in the
-    YAML header stored next to it, thejoker/samples.py:480-563, utils.py:75-103).  Needs
-    h5py (not PyTables: the reference's workers read the same dataset with ``tables``,
-    utils.py:168-198)."""
+    YAML header stored next to it, thejoker/samples.py:480-563, utils.py:75-103), through
+    h5py or, without it, hdf5_min (the reference's workers read the same dataset with
+    PyTables, utils.py:168-198)."""
     with _open_reference_hdf5(filename) as f:
         dset = f[JokerSamples._hdf5_path]
         units, columns, meta = parse_table_column_meta(

@@ -250,7 +250,9 @@ class CJokerHelper:
         if chunk.dtype != np.float64 or not chunk.flags.c_contiguous:
             raise ValueError("Buffer dtype mismatch / not C-contiguous: expected float64[:, ::1]")
         n = chunk.shape[0]
-        ll = np.full(n, np.nan)  # pyx:443
+        # pyx:443 pre-fills with NaN; every element is written on success and a failure
+        # raises, so the fill pass over a multi-GB array is skipped
+        ll = np.empty(n)
         _lib.check(self._lib.tjb_marginal_ll_host(self._h, _vp(chunk), n, _vp(ll)))
         return ll
 
@@ -266,7 +268,7 @@ class CJokerHelper:
             s = np.ascontiguousarray(s, dtype=np.float64)
             if len(s) != n:
                 raise ValueError("prior columns differ in length")
-        ll = np.full(n, np.nan) if out is None else out
+        ll = np.empty(n) if out is None else out
         _lib.check(self._lib.tjb_marginal_ll_host_soa(
             self._h, *[_vp(c) for c in cols], _vp(s) if s is not None else None, float(s_const),
             n, _vp(ll)))

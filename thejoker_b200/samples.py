@@ -26,6 +26,26 @@ _nonlinear_packed_order = ["P", "e", "omega", "M0", "s"]
 _nonlinear_internal_units = {"P": u.day, "e": u.one, "omega": u.radian, "M0": u.radian}
 
 
+def file_format(filename):
+    """'npz' | 'hdf5' | None from the first bytes of a file, whatever its name: this
+    package's ``JokerSamples.write`` produces a zip (.npz) container, the reference's an
+    HDF5 file (signature at offset 0 or, after a user block, at 512, 1024, ...)."""
+    with open(filename, "rb") as f:
+        head = f.read(8)
+        if head[:2] == b"PK":
+            return "npz"
+        off = 0
+        while len(head) == 8:
+            if head == b"\x89HDF\r\n\x1a\n":
+                return "hdf5"
+            off = 512 if off == 0 else off * 2
+            if off > (1 << 26):
+                break
+            f.seek(off)
+            head = f.read(8)
+    return None
+
+
 class JokerSamples:
     _hdf5_path = "samples"
 
@@ -202,6 +222,15 @@ class JokerSamples:
             return merged.write(output, overwrite=True)
         if os.path.exists(output) and not overwrite:
             raise OSError(f"File {output} exists: use overwrite=True")
+        if str(output).lower().endswith((".hdf5", ".h5", ".fits")):
+            import warnings
+
+            # the reference writes HDF5 / FITS under these names (samples.py:480-545); no
+            # HDF5 / FITS writer exists here (h5py / astropy are not dependencies)
+            warnings.warn(f"{output}: written in thejoker_b200's own .npz container, not "
+                          "HDF5 / FITS -- thejoker_b200 reads it back under any name (the format "
+                          "is detected from the file's first bytes); the reference cannot",
+                          UserWarning, stacklevel=2)
         payload = {f"col:{k}": v.value for k, v in self.tbl.items()}
         payload["__units__"] = np.array([f"{k}={v.unit.scale!r}|{v.unit.dims!r}"
                                          for k, v in self.tbl.items()])
@@ -215,6 +244,14 @@ class JokerSamples:
         .npz container written by ``write`` has a single table, so it is ignored."""
         import ast
 
+        kind = file_format(filename)
+        if kind == "hdf5":  # a file written by the reference's JokerSamples.write
+            from .cache import read_reference_hdf5
+
+            return read_reference_hdf5(filename)
+        if kind != "npz":
+            raise OSError(f"{filename}: neither an .npz container written by JokerSamples.write "
+                          "nor an HDF5 file written by the reference")
         with np.load(filename, allow_pickle=False) as z:
             meta = ast.literal_eval(str(z["__meta__"][0]))
             new = cls(**meta)

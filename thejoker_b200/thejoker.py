@@ -103,13 +103,11 @@ class TheJoker:
     def _columns(self, helper, prior_samples):
         """[P, e, omega, M0, s] host columns in internal units + optional ln_prior."""
         if isinstance(prior_samples, str):
-            from .cache import PriorCache, read_reference_hdf5
+            from .cache import PriorCache
 
             if os.path.isdir(prior_samples):
                 prior_samples = PriorCache(prior_samples)
-            elif prior_samples.endswith((".hdf5", ".h5")):
-                prior_samples = read_reference_hdf5(prior_samples)
-            else:
+            else:  # .npz container or the reference's HDF5: told apart by the file's bytes
                 prior_samples = JokerSamples.read(prior_samples)
         if type(prior_samples).__name__ == "PriorCache":
             cols = prior_samples.columns(rv_unit=helper.internal_units["s"])
