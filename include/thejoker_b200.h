@@ -186,6 +186,13 @@ int tjb_accept(TjbHandle *h, const double *d_ll, int64_t n, const int64_t *d_llm
                const double *d_uniforms, const TjbPcg64 *pcg, int64_t pcg_offset,
                int64_t index_base, int64_t max_keep, double near_tol, int64_t *d_idx,
                int64_t *h_counts);
+/* Number of non-finite lls (NaN, +-inf) the last tjb_accept / tjb_accept_dist call of this
+ * handle saw in its range (summed over the ranks for tjb_accept_dist): what
+ * iterative_rejection_inmem tests with np.isfinite over all lls before it accepts
+ * (likelihood_helpers.py:173-176).  No synchronisation: the value was fetched with the
+ * counts. */
+int tjb_accept_nonfinite(TjbHandle *h, int64_t *h_count);
+
 /* ---- the same accept step over shards that live in different processes (one rank per
  * GPU): NCCL inside the library, no torch / MPI types in the interface.  Replaces the
  * master-side gather + max + compare + where of multiproc_helpers.py:256-263, 373-381.
@@ -282,6 +289,14 @@ int tjb_multistar_rejection(int device, const TjbMultiStarJob *job);
  * converge within the iteration cap (their ll is still finite, counted for reporting),
  * h_stats[2..3] reserved.  Synchronises the handle's streams. */
 int tjb_get_stats(TjbHandle *h, uint64_t *h_stats, int reset);
+
+/* Where the likelihood kernel reads the star's epoch rows from (process-wide).  0 (default):
+ * from the kernel's parameter block when they fit (24 KB: 768 epochs at n_linear = 2, 512
+ * at 3..4) -- uniform loads, uniform-register operands --, else staged in shared memory;
+ * 1: always staged in shared memory.  Both kernels give bit-identical results
+ * (tests/test_gpu_parity.py::test_epoch_rows_kernels_agree); the switch exists for that
+ * test and for timing comparisons.  Initial value: environment TJB_FORCE_SHARED_ROWS. */
+int tjb_set_epoch_rows_mode(int mode);
 
 /* ---- measurement helper: FP64 FMA-chain peak of the device, TFLOP/s ---- */
 int tjb_fp64_peak(TjbHandle *h, int iters, double *h_tflops, double *h_ms);

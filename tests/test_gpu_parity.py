@@ -298,6 +298,35 @@ def test_ll_parity_host_path(torch_cuda, oracle_lib, args, sl, kw):
         helper.batch_marginal_ln_likelihood(chunk[:, :4])
 
 
+def test_epoch_rows_kernels_agree(torch_cuda, oracle_lib):
+    """The likelihood kernel that reads the epoch rows from its parameter block (uniform
+    loads, the default when the table fits) and the one that stages them in shared memory
+    (long tables, n_linear > 4) give identical bits; tables beyond the parameter block's
+    capacity take the shared-memory kernel by themselves and match the oracle."""
+    from thejoker_b200 import _lib
+
+    lib = _lib.load()
+    try:
+        for shape, sl in (((64, 1), None), ((64, 2), (-2.0, 1.0)), ((21, 1), None),
+                          ((256, 1), None), ((3, 3), (-2.0, 1.0))):
+            helper, spec, _, _ = make_helper(shape)
+            chunk = prior_chunk(20_000, s_lognormal=sl)
+            _lib.check(lib.tjb_set_epoch_rows_mode(0))
+            a = helper.batch_marginal_ln_likelihood(chunk)
+            _lib.check(lib.tjb_set_epoch_rows_mode(1))
+            b = helper.batch_marginal_ln_likelihood(chunk)
+            assert np.array_equal(a, b), shape
+    finally:
+        _lib.check(lib.tjb_set_epoch_rows_mode(0))
+    # 1000 epochs at L = 2: 4000 doubles > kParamRowDoubles (3072) -> shared-memory rows
+    helper, spec, _, _ = make_helper((1000, 1))
+    chunk = prior_chunk(2048)
+    got = helper.batch_marginal_ln_likelihood(chunk)
+    orc = oracle_lib.OracleHelper.from_spec(spec)
+    truth, _ = orc.truth_ll(chunk)
+    assert np.max(rel_err(got, truth)) < 1e-10
+
+
 def test_ll_device_paths_agree(torch_cuda, oracle_lib):
     """SoA / AoS device entry points and the host entry point give identical bits, for
     both kernels (constant jitter folded into the table vs per-sample jitter)."""
@@ -535,6 +564,38 @@ def test_pcg64_uniforms_bit_exact(torch_cuda):
         dev = helper.pcg64_uniform(rng, n, offset=off).cpu().numpy()
         want = np.random.default_rng(seed).random(n + off)[off:]
         assert np.array_equal(dev, want)
+
+
+def test_accept_counts_nonfinite_lls(torch_cuda):
+    """likelihood_helpers.py:173-176 tests np.isfinite over every ll before it accepts: the
+    accept kernel counts NaN / +-inf lls (a -inf does not show in the max), and the
+    in-memory iterative sampler returns the reference's RuntimeError object when there is one."""
+    import thejoker_b200 as tj
+    from thejoker_b200 import units as u
+    from thejoker_b200.synthetic import make_noisy_data
+
+    torch = torch_cuda
+    helper, spec, data, prior = make_helper((16, 1))
+    n = 100_000
+    ll = np.random.default_rng(0).normal(-50.0, 3.0, n)
+    ll[[5, 70_000]] = -np.inf
+    ll_dev = torch.from_numpy(ll).cuda()
+    key = helper.new_llmax_key()
+    helper.llmax_update(ll_dev, key)
+    idx, tot, _ = helper.accept(ll_dev, key, rng=np.random.default_rng(1))
+    assert helper.last_nonfinite == 2 and tot > 0
+    ll[123] = np.inf
+    ll[99_999] = np.nan
+    helper.accept(torch.from_numpy(ll).cuda(), key, rng=np.random.default_rng(1))
+    assert helper.last_nonfinite == 4
+    helper.accept(torch.from_numpy(ll[1000:60_000].copy()).cuda(), key, rng=np.random.default_rng(1))
+    assert helper.last_nonfinite == 0
+    # a zero-weight data set whose ll is -inf for some samples is hard to build from the
+    # public API; the sampler's rule is exercised through its stats instead
+    joker = tj.TheJoker(prior, rng=np.random.default_rng(3), devices=[0])
+    chunk = prior_chunk(4096)
+    out = joker.iterative_rejection_sample(data, chunk, n_requested_samples=8, in_memory=True)
+    assert not isinstance(out, Exception) and joker.last_stats["n_nonfinite"] == 0
 
 
 @pytest.mark.parametrize("flat", [False, True])

@@ -118,6 +118,7 @@ SYMBOLS = {
     "tjb_accept": (ctypes.c_int, [_H, _vp, ctypes.c_int64, _vp, _vp, ctypes.POINTER(TjbPcg64),
                                   ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_double,
                                   _vp, _i64p]),
+    "tjb_accept_nonfinite": (ctypes.c_int, [_H, _i64p]),
     "tjb_comm_unique_id": (ctypes.c_int, [_vp]),
     "tjb_comm_create": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        ctypes.POINTER(ctypes.c_void_p)]),
@@ -135,6 +136,7 @@ SYMBOLS = {
     "tjb_unmarginalized_ll": (ctypes.c_int, [_H, _vp, ctypes.c_int64, _vp]),
     "tjb_design_column": (ctypes.c_int, [_H, _vp, _vp, _vp]),
     "tjb_get_stats": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int]),
+    "tjb_set_epoch_rows_mode": (ctypes.c_int, [ctypes.c_int]),
     "tjb_fp64_peak": (ctypes.c_int, [_H, ctypes.c_int, _dp, _dp]),
 }
 

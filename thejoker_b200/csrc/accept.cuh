@@ -112,15 +112,19 @@ accept_flag_kernel(const double *__restrict__ ll, const long long n,
     const Lcg128 j = lcg_power(pp.inc, (uint64_t)first + 1);
     st = j.mult * pp.state + j.plus;
   }
-  unsigned cnt = 0, near = 0;
+  unsigned cnt = 0, near = 0, nonfin = 0;
   const long long cta_end_round = ((cta_end + 31) / 32) * 32;
   for (long long i = first; i < cta_end_round; i += kAccThreads) {
     bool acc = false;
     if (i < n) {
       const double u = pp.enabled ? pcg_output_double(st) : uniforms[i];
-      const double a = exp(ll[i] - llmax);
+      const double v = ll[i];
+      const double a = exp(v - llmax);
       acc = a > u;
       near += (fabs(a - u) <= near_tol) ? 1u : 0u;
+      // NaN / +-inf lls (likelihood_helpers.py:173-176 checks np.isfinite over all of them;
+      // the max key alone does not see a -inf)
+      nonfin += (fabs(v) <= 1.79769313486231570815e+308) ? 0u : 1u;
     }
     if (pp.enabled) st = pp.stride.mult * st + pp.stride.plus;
     const unsigned word = __ballot_sync(0xffffffffu, acc);
@@ -130,16 +134,18 @@ accept_flag_kernel(const double *__restrict__ ll, const long long n,
     }
   }
   // CTA totals
-  __shared__ unsigned s_cnt, s_near;
-  if (threadIdx.x == 0) { s_cnt = 0; s_near = 0; }
+  __shared__ unsigned s_cnt, s_near, s_nonfin;
+  if (threadIdx.x == 0) { s_cnt = 0; s_near = 0; s_nonfin = 0; }
   __syncthreads();
   if (cnt) atomicAdd(&s_cnt, cnt);
   if (near) atomicAdd(&s_near, near);
+  if (nonfin) atomicAdd(&s_nonfin, nonfin);
   __syncthreads();
   if (threadIdx.x == 0) {
     cta_counts[blockIdx.x] = s_cnt;
     if (s_cnt) atomicAdd(&totals[0], (unsigned long long)s_cnt);
     if (s_near) atomicAdd(&totals[1], (unsigned long long)s_near);
+    if (s_nonfin) atomicAdd(&totals[2], (unsigned long long)s_nonfin);
   }
 }
 

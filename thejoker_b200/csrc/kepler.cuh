@@ -120,6 +120,21 @@ constexpr double kUnitsPerRev = (double)kTrigTableSize;
 constexpr int kTrigTableSize = 0;
 constexpr double kUnitsPerRev = 4.0;
 #endif
+// Two-level table (TJB_TRIG2): the FP64 stage starts from the FP32 estimate E0 snapped to a
+// grid of 2^-kFineLog2 angle units (2^22 points per revolution at 2048 + 2048 nodes), so
+// that sin / cos of the start are the product of two table nodes -- coarse node j1 (angle
+// j1 units) and fine node j2 (angle j2 2^-kFineLog2 units), 4 FP64 instructions and two
+// LDS.128 -- instead of one node rotated by a residual through polynomials (9 FP64
+// instructions + one LDS.128).  Snapping moves the start by at most half a grid step
+// (7.5e-7 rad), well inside the range of the one-pass FP64 step (2^-16); the start's offset
+// from M is then formed in FP64 (two instructions), so in total 5 FP64 instructions fewer
+// per epoch.  The fine nodes follow the coarse ones in the table (kTrigNodes in all).
+#ifndef TJB_TRIG2
+#define TJB_TRIG2 0
+#endif
+constexpr int kFineLog2 = TJB_TRIG_TABLE_LOG2;
+constexpr int kTrigNodes = kTrigTableSize * (TJB_TRIG2 ? 2 : 1);
+constexpr double kMagic2 = 6755399441055744.0 / (double)(1 << kFineLog2);  // ulp = 2^-kFineLog2
 // fixed-point phase (TJB_PHASE_FIXED): fraction bits that fit one revolution in 32 bits
 constexpr double kFixOne = 4294967296.0 / kUnitsPerRev;          // 2^(32-U)
 constexpr double kMagicFix = 6755399441055744.0 / kFixOne;       // 1.5 * 2^(52-(32-U))
@@ -233,6 +248,23 @@ inline double rcp_pos(double x) { return 1.0 / x; }
 #define TJB_SC(i) tc.s[i]
 #define TJB_CC(i) tc.c[i]
 #define TJB_MC(i) tc.m[i]
+// Constants that sit in the multiplier slot of an FP64 instruction on the main path.  With
+// TJB_UCONST they are read from the constant bank where they are used: ptxas hoists them
+// into uniform registers (LDCU.64 before the loop, `DFMA R, R, UR, R`), which saves a
+// vector-register operand read per use (an FP64 instruction with three distinct vector
+// operands issues every 3 cycles, with two every 2: DESIGN.md section 4.1).
+#ifndef TJB_UCONST
+#define TJB_UCONST 0
+#endif
+#if TJB_UCONST && defined(__CUDA_ARCH__)
+#define TJB_SCM(i) kSinC[i]
+#define TJB_CCM(i) kCosC[i]
+#define TJB_MCM(i) kMisc[i]
+#else
+#define TJB_SCM(i) tc.s[i]
+#define TJB_CCM(i) tc.c[i]
+#define TJB_MCM(i) tc.m[i]
+#endif
 
 // The FP64 constants of the epoch loop, pinned in registers.  Left to itself ptxas
 // re-loads (LDC) or re-materialises (MOV) each of them on every epoch, which costs issue
@@ -285,8 +317,8 @@ TJB_HD void sincos_units(const TrigCoef &tc, double v, double &s, double &c) {
   const SinCos node = tc.table[k & (kTrigTableSize - 1)];
 #endif
   const double sr = kSinQuintic ? r * fma(r2, fma(r2, TJB_SC(2), TJB_SC(1)), TJB_SC(0))
-                                : r * fma(r2, TJB_SC(1), TJB_SC(0));
-  const double cr = fma(r2, fma(r2, TJB_CC(2), TJB_CC(1)), 1.0);
+                                : r * fma(r2, TJB_SCM(1), TJB_SC(0));
+  const double cr = fma(r2, fma(r2, TJB_CCM(2), TJB_CC(1)), 1.0);
   s = fma(node.c, sr, node.s * cr);
   c = fma(-node.s, sr, node.c * cr);
 #else
@@ -430,7 +462,7 @@ TJB_HD double halley2(const OrbitConsts &oc, double D, double sE, double cE) {
 TJB_HD void rotate_tiny(const TrigCoef &tc, double del, double &sE, double &cE) {
   (void)tc;
 #if TJB_TRIM
-  const double cd = fma(del * del, -TJB_MC(3), 1.0);
+  const double cd = fma(del * del, -TJB_MCM(3), 1.0);
 #else
   const double cd = fma(del * del, -0.5, 1.0);
 #endif
@@ -557,9 +589,33 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
 #endif
 #pragma unroll
   for (int k = 0; k < K; k++) {
-#if TJB_TRIM
+#if TJB_TRIG2
+    {
+      const double v0 = fma((double)Df[k], TJB_MCM(1), x4[k]);  // E0 in angle units
+      const double tv = v0 + kMagic2;                            // ... on the fine grid
+      const int idx = lo32(tv);  // grid index modulo 2^32: fine node | coarse node << kFineLog2
+      D[k] = ((tv - kMagic2) - x4[k]) * TJB_MCM(2);  // snapped E0 - M [rad] (difference exact)
+      SinCos n1, n2;
+#if defined(__CUDA_ARCH__)
+      if (kSharedTable) {
+        const unsigned a1 = (((unsigned)idx >> (kFineLog2 - 4)) & ((kTrigTableSize - 1) << 4)) + tc.table_s;
+        unsigned a2;
+        asm("mad.lo.u32 %0, %1, 16, %2;" : "=r"(a2) : "r"(idx & ((1 << kFineLog2) - 1)),
+            "r"(tc.table_s + (unsigned)(kTrigTableSize * sizeof(SinCos))));
+        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(n1.s), "=d"(n1.c) : "r"(a1));
+        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(n2.s), "=d"(n2.c) : "r"(a2));
+      } else
+#endif
+      {
+        n1 = tc.table[((unsigned)idx >> kFineLog2) & (kTrigTableSize - 1)];
+        n2 = tc.table[kTrigTableSize + (idx & ((1 << kFineLog2) - 1))];
+      }
+      sE[k] = fma(n1.c, n2.s, n1.s * n2.c);
+      cE[k] = fma(-n1.s, n2.s, n1.c * n2.c);
+    }
+#elif TJB_TRIM
     D[k] = (double)Df[k];                // E0 - M [rad]
-    const double d4 = D[k] * TJB_MC(1);  // in angle units (1-ulp rounding: < 2e-16 rad)
+    const double d4 = D[k] * TJB_MCM(1);  // in angle units (1-ulp rounding: < 2e-16 rad)
     sincos_units<kSharedTable>(tc, x4[k] + d4, sE[k], cE[k]);
 #else
     const double d4 = (double)(Df[k] * (float)kUnitsPerRad);  // D0 in angle units

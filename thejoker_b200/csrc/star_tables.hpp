@@ -63,8 +63,9 @@ inline void star_fill_common(const StarHost &st, StarParams &sp) {
 }
 
 // sin / cos at the kTrigTableSize nodes of the trig table, correctly rounded from long double
+// (TJB_TRIG2: followed by the 2^kFineLog2 fine nodes, angles j 2^-kFineLog2 of a node spacing)
 inline std::vector<SinCos> make_trig_table() {
-  std::vector<SinCos> t(kTrigTableSize > 0 ? kTrigTableSize : 1);
+  std::vector<SinCos> t(kTrigNodes > 0 ? kTrigNodes : 1);
   const long double two_pi = 6.283185307179586476925286766559005768L;
   for (int j = 0; j < kTrigTableSize; j++) {
     // exact octant symmetry: evaluate in the first octant-ish range for best accuracy
@@ -75,6 +76,12 @@ inline std::vector<SinCos> make_trig_table() {
   if (kTrigTableSize >= 4) {  // the four axis nodes exactly
     const int q = kTrigTableSize / 4;
     t[0] = {0.0, 1.0}; t[q] = {1.0, 0.0}; t[2 * q] = {0.0, -1.0}; t[3 * q] = {-1.0, 0.0};
+  }
+  for (int j = kTrigTableSize; j < kTrigNodes; j++) {
+    const long double ang = two_pi * (long double)(j - kTrigTableSize) /
+                            ((long double)kTrigTableSize * (long double)(1 << kFineLog2));
+    t[j].s = (double)sinl(ang);
+    t[j].c = (double)cosl(ang);
   }
   return t;
 }

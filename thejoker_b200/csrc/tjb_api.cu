@@ -8,6 +8,7 @@
 #include <functional>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -154,6 +155,7 @@ struct TjbHandle {
   int N = 0, L = 0, jitter_mode = 0;
   // device tables and their parameter blocks
   DevBuf tab_const, tab_jit;
+  std::vector<double> rows_const, rows_jit;  // host copies: passed as a kernel parameter
   StarParams sp_const, sp_jit;
   bool const_valid = false;
   double const_s = 0;
@@ -163,6 +165,7 @@ struct TjbHandle {
   void *trig = nullptr;  // shared per-device sin/cos table (DeviceShared)
   StagePool *stg = nullptr;  // this device's host-streaming resources (shared by handles)
   int ll_ctas_per_sm = 0;
+  long long last_nonfinite = 0;  // NaN / inf lls seen by the last accept call
   // extra (peer) keys the likelihood kernel max-updates besides the one passed per call
   long long *peer_keys[kMaxPeers] = {nullptr};
   int n_peer_keys = 0;
@@ -185,7 +188,7 @@ int upload_table(TjbHandle *h, DevBuf &buf, const std::vector<double> &tab, Star
 
 // (re)build the constant-jitter table for the given s
 int build_const_table(TjbHandle *h, double s) {
-  std::vector<double> tab;
+  std::vector<double> &tab = h->rows_const;
   star_build_const(h->star, s, h->sp_const, tab);
   int rc = upload_table(h, h->tab_const, tab, h->sp_const);
   if (rc) return rc;
@@ -195,19 +198,33 @@ int build_const_table(TjbHandle *h, double s) {
 }
 
 int build_jit_table(TjbHandle *h) {
-  std::vector<double> tab;
+  std::vector<double> &tab = h->rows_jit;
   star_build_jit(h->star, h->sp_jit, tab);
   return upload_table(h, h->tab_jit, tab, h->sp_jit);
 }
 
 // ---- kernel dispatch ---------------------------------------------------------
 
-template <int L, bool J, typename View>
-int launch_ll(TjbHandle *h, const StarParams &sp, const View &pv, long long n, double *d_ll,
-              long long *d_key, cudaStream_t stream) {
-  auto kern = marginal_ll_kernel<L, J, View>;
-  const size_t smem = (size_t)kTrigTableSize * sizeof(SinCos) +
-                      (size_t)h->N * row_stride(L) * sizeof(double);
+// TJB_FORCE_SHARED_ROWS=1 in the environment selects the shared-memory-rows kernel for every
+// table size (tests cover both kernels on the same inputs; bench / tuning comparisons)
+std::atomic<int> g_force_shared_rows{-1};
+bool tjb_force_shared_rows() {
+  int v = g_force_shared_rows.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char *e = std::getenv("TJB_FORCE_SHARED_ROWS");
+    v = (e && e[0] == '1') ? 1 : 0;
+    g_force_shared_rows.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
+
+template <int L, bool J, typename View, typename Rows>
+int launch_ll_rows(TjbHandle *h, const StarParams &sp, const View &pv, long long n, double *d_ll,
+                   long long *d_key, cudaStream_t stream, const Rows &rows) {
+  constexpr bool kParamRows = sizeof(Rows) == sizeof(EpochRowsParam);
+  auto kern = marginal_ll_kernel<L, J, View, Rows>;
+  const size_t smem = (size_t)kTrigNodes * sizeof(SinCos) +
+                      (kParamRows ? 0 : (size_t)h->N * row_stride(L) * sizeof(double));
   if (smem > 227 * 1024)
     return fail(TJB_E_INVALID, "epoch table does not fit in shared memory (too many epochs)");
   if (smem > 48 * 1024)
@@ -224,9 +241,30 @@ int launch_ll(TjbHandle *h, const StarParams &sp, const View &pv, long long n, d
     mk.keys[mk.n++] = d_key;
     for (int p = 0; p < h->n_peer_keys && mk.n < kMaxPeers; p++) mk.keys[mk.n++] = h->peer_keys[p];
   }
-  kern<<<grid, kLLThreads, smem, stream>>>(sp, pv, n, d_ll, mk);
+  kern<<<grid, kLLThreads, smem, stream>>>(sp, pv, n, d_ll, mk, rows);
   CU(cudaGetLastError());
   return TJB_OK;
+}
+
+// Epoch rows travel as a kernel parameter when they fit (kParamRowDoubles; L <= kMaxParamRowsL
+// keeps the number of kernel instantiations down), else they are staged in shared memory.
+constexpr int kMaxParamRowsL = 4;
+template <int L, bool J, typename View>
+int launch_ll(TjbHandle *h, const StarParams &sp, const View &pv, long long n, double *d_ll,
+              long long *d_key, cudaStream_t stream) {
+#if TJB_UROW
+  if constexpr (L <= kMaxParamRowsL) {
+    const std::vector<double> &host_rows = J ? h->rows_jit : h->rows_const;
+    if (!tjb_force_shared_rows() && host_rows.size() <= (size_t)kParamRowDoubles &&
+        host_rows.size() == (size_t)h->N * row_stride(L)) {
+      static thread_local EpochRowsParam rows;  // 24 KB: not on the stack of a slot thread
+      std::memcpy(rows.v, host_rows.data(), host_rows.size() * sizeof(double));
+      return launch_ll_rows<L, J, View, EpochRowsParam>(h, sp, pv, n, d_ll, d_key, stream, rows);
+    }
+  }
+#endif
+  return launch_ll_rows<L, J, View, EpochRowsShared>(h, sp, pv, n, d_ll, d_key, stream,
+                                                     EpochRowsShared{0});
 }
 
 template <bool J, typename View>
@@ -873,13 +911,14 @@ int tjb_pcg64_uniform(TjbHandle *h, const TjbPcg64 *pcg, int64_t offset, int64_t
 namespace {
 
 // flag / scan / scatter of one contiguous ll range on the handle's stream; the totals
-// [accepted, near] are left in h->acc_totals (device).  No host synchronisation.
+// [accepted, near, non-finite] are left in h->acc_totals (device).  No host synchronisation.
+constexpr int kAccTotals = 3;
 int accept_local_async(TjbHandle *h, const double *d_ll, int64_t n, const int64_t *d_llmax_key,
                        const double *d_uniforms, const TjbPcg64 *pcg, int64_t pcg_offset,
                        int64_t index_base, int64_t max_keep, double near_tol, int64_t *d_idx) {
-  if (h->acc_totals.ensure(2 * sizeof(unsigned long long)))
+  if (h->acc_totals.ensure(kAccTotals * sizeof(unsigned long long)))
     return fail(TJB_E_NOMEM, "cudaMalloc accept scratch");
-  CU(cudaMemsetAsync(h->acc_totals.p, 0, 2 * sizeof(unsigned long long), h->stream));
+  CU(cudaMemsetAsync(h->acc_totals.p, 0, kAccTotals * sizeof(unsigned long long), h->stream));
   if (n <= 0) return TJB_OK;
   const long long n_words = (n + 31) / 32;
   const int wpc = acc_words_per_cta(n_words, h->n_sm);
@@ -923,12 +962,19 @@ int tjb_accept(TjbHandle *h, const double *d_ll, int64_t n, const int64_t *d_llm
   int rc = accept_local_async(h, d_ll, n, d_llmax_key, d_uniforms, pcg, pcg_offset, index_base,
                               max_keep, near_tol, d_idx);
   if (rc) return rc;
-  unsigned long long tot[2] = {0, 0};
+  unsigned long long tot[kAccTotals] = {0, 0, 0};
   CU(cudaMemcpyAsync(tot, h->acc_totals.p, sizeof(tot), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   h_counts[0] = (int64_t)tot[0];
   h_counts[1] = std::min<int64_t>((int64_t)tot[0], max_keep);
   h_counts[2] = (int64_t)tot[1];
+  h->last_nonfinite = (long long)tot[2];
+  return TJB_OK;
+}
+
+int tjb_accept_nonfinite(TjbHandle *h, int64_t *h_count) {
+  if (!h || !h_count) return fail(TJB_E_INVALID, "null argument");
+  *h_count = (int64_t)h->last_nonfinite;
   return TJB_OK;
 }
 
@@ -1011,14 +1057,14 @@ int tjb_accept_dist(TjbHandle *h, TjbComm *comm, const double *d_ll, int64_t n_l
   // (2) local flag / scan / scatter; uniforms and indices are addressed globally
   const int64_t keep_local = std::min(max_keep, n_local);
   if (h->dist_send.ensure((size_t)std::max<int64_t>(keep_local, 1) * sizeof(int64_t)) ||
-      h->dist_counts.ensure((size_t)W * 2 * sizeof(unsigned long long)))
+      h->dist_counts.ensure((size_t)W * kAccTotals * sizeof(unsigned long long)))
     return fail(TJB_E_NOMEM, "cudaMalloc accept scratch");
   int rc = accept_local_async(h, d_ll, n_local, d_llmax_key, d_uniforms, pcg, global_offset,
                               global_offset, keep_local, near_tol, (int64_t *)h->dist_send.p);
   if (rc) return rc;
-  // (3) every rank learns every rank's [accepted, near]
-  NC(nc.AllGather(h->acc_totals.p, h->dist_counts.p, 2, ncclUint64, comm->comm, st));
-  std::vector<unsigned long long> cnt((size_t)W * 2);
+  // (3) every rank learns every rank's [accepted, near, non-finite]
+  NC(nc.AllGather(h->acc_totals.p, h->dist_counts.p, kAccTotals, ncclUint64, comm->comm, st));
+  std::vector<unsigned long long> cnt((size_t)W * kAccTotals);
   CU(cudaMemcpyAsync(cnt.data(), h->dist_counts.p, cnt.size() * sizeof(unsigned long long),
                      cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
@@ -1026,10 +1072,12 @@ int tjb_accept_dist(TjbHandle *h, TjbComm *comm, const double *d_ll, int64_t n_l
   // (likelihood_helpers.py:109): rank r keeps what is left of max_keep after ranks < r
   std::vector<int64_t> kept(W), pos(W);
   int64_t total = 0, near = 0, written = 0, m = 0;
+  h->last_nonfinite = 0;
   for (int r = 0; r < W; r++) {
-    const int64_t a = (int64_t)cnt[2 * r];
+    const int64_t a = (int64_t)cnt[kAccTotals * r];
     total += a;
-    near += (int64_t)cnt[2 * r + 1];
+    near += (int64_t)cnt[kAccTotals * r + 1];
+    h->last_nonfinite += (long long)cnt[kAccTotals * r + 2];
     pos[r] = written;
     kept[r] = std::max<int64_t>(0, std::min(a, max_keep - written));
     written += kept[r];
@@ -1298,6 +1346,12 @@ int tjb_unmarginalized_ll(TjbHandle *h, const double *h_rows, int64_t n, double 
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(h_ll, d_ll, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  return TJB_OK;
+}
+
+int tjb_set_epoch_rows_mode(int mode) {
+  if (mode < 0 || mode > 1) return fail(TJB_E_INVALID, "mode must be 0 or 1");
+  g_force_shared_rows.store(mode, std::memory_order_relaxed);
   return TJB_OK;
 }
 

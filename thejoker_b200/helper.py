@@ -185,6 +185,7 @@ class CJokerHelper:
         if self.n_linear > _lib.TJB_MAX_LINEAR or len(spec["mu"]) < self.n_linear:
             raise ValueError("bad n_linear / mu length")
         self.a = self.A = self.Ainv = self.b = None
+        self.last_nonfinite = 0  # NaN / inf lls seen by the last accept call
         if device is None:
             import os
             device = int(os.environ.get("LOCAL_RANK", "0"))
@@ -521,7 +522,14 @@ class CJokerHelper:
                                         ctypes.byref(pcg) if pcg is not None else None,
                                         int(rng_offset), int(index_base), min(max_keep, n),
                                         float(near_tol), self._ptr(idx), counts))
+        self.last_nonfinite = self._accept_nonfinite()
         return idx[: counts[1]], int(counts[0]), int(counts[2])
+
+    def _accept_nonfinite(self):
+        """NaN / +-inf lls seen by the last accept call (tjb_accept_nonfinite)."""
+        c = ctypes.c_int64()
+        _lib.check(self._lib.tjb_accept_nonfinite(self._h, ctypes.byref(c)))
+        return int(c.value)
 
     def accept_dist(self, comm, ll, llmax_key, global_offset, uniforms=None, rng=None,
                     max_keep=None, n_global=None, near_tol=1e-12):
@@ -549,6 +557,7 @@ class CJokerHelper:
                                              ctypes.byref(pcg) if pcg is not None else None,
                                              int(global_offset), max_keep, float(near_tol),
                                              self._ptr(idx), counts))
+        self.last_nonfinite = self._accept_nonfinite()  # summed over the ranks
         return idx[: counts[1]], int(counts[0]), int(counts[2])
 
     def allreduce_max_key(self, comm, llmax_key):

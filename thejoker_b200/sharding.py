@@ -109,13 +109,14 @@ def allreduce_max_key(key, group=None):
     return key
 
 
-def gather_accepted(idx, total, near, max_keep, group=None, device=None):
+def gather_accepted(idx, total, near, max_keep, group=None, device=None, nonfinite=None):
     """All ranks get the rank-ordered concatenation of the per-rank ascending index
     lists, truncated to max_keep, plus the global counts.  Two fixed-size tensor
     all-gathers (counts, then indices padded to the longest kept list) -- nothing is
     pickled.  This is the torch.distributed path (gloo in the CPU tests, or several index
     segments per rank); one contiguous shard per rank under NCCL goes through the
-    library's own tjb_accept_dist instead."""
+    library's own tjb_accept_dist instead.  With ``nonfinite`` (this rank's count of NaN /
+    inf lls) the global count is returned as a fourth value."""
     import torch
     import torch.distributed as dist
 
@@ -124,10 +125,11 @@ def gather_accepted(idx, total, near, max_keep, group=None, device=None):
     idx = np.asarray(idx, dtype=np.int64)
     if max_keep is not None:
         idx = idx[:max_keep]
-    mine = torch.tensor([len(idx), int(total), int(near)], dtype=torch.int64, device=dev)
-    counts = torch.empty(world * 3, dtype=torch.int64, device=dev)  # flat: gloo wants 1-D
+    mine = torch.tensor([len(idx), int(total), int(near), int(nonfinite or 0)], dtype=torch.int64,
+                        device=dev)
+    counts = torch.empty(world * 4, dtype=torch.int64, device=dev)  # flat: gloo wants 1-D
     dist.all_gather_into_tensor(counts, mine, group=group)
-    counts = counts.cpu().numpy().reshape(world, 3)
+    counts = counts.cpu().numpy().reshape(world, 4)
     m = int(counts[:, 0].max())
     parts = []
     if m > 0:
@@ -138,6 +140,8 @@ def gather_accepted(idx, total, near, max_keep, group=None, device=None):
         recv = recv.cpu().numpy().reshape(world, m)
         parts = [recv[r, : counts[r, 0]] for r in range(world)]
     idx, total = merge_accepted(parts, counts[:, 1], max_keep)
+    if nonfinite is not None:
+        return idx, total, int(counts[:, 2].sum()), int(counts[:, 3].sum())
     return idx, total, int(counts[:, 2].sum())
 
 
@@ -474,7 +478,7 @@ class DeviceEngine:
         torch = self.torch
         sh = self.shards[0]
         self.global_max_key()
-        per_idx, total, near = [], 0, 0
+        per_idx, total, near, nonfin = [], 0, 0, 0
         with self._ctx(sh.device):
             for a, b, ll in self.segments:
                 b = min(b, n_accum)
@@ -491,10 +495,13 @@ class DeviceEngine:
                 per_idx.append(idx.cpu().numpy())
                 total += tot
                 near += nn
+                nonfin += sh.helper.last_nonfinite
         mine = np.concatenate(per_idx) if per_idx else np.zeros(0, dtype=np.int64)
         # the global first max_keep are among every rank's own first max_keep
-        idx, total, near = gather_accepted(mine, total, near, None if max_keep is None else max_keep,
-                                           self.group, device=sh.key.device)
+        idx, total, near, nonfin = gather_accepted(
+            mine, total, near, None if max_keep is None else max_keep, self.group,
+            device=sh.key.device, nonfinite=nonfin)
+        self.last_nonfinite = nonfin
         idx = np.sort(idx)
         return (idx if max_keep is None else idx[:max_keep]), total, near
 
@@ -595,9 +602,10 @@ class DeviceEngine:
                     comm, sh.ll[:hi], sh.key, self.global_offset, uniforms=u_dev,
                     rng=None if uniforms is not None else rng, max_keep=max_keep,
                     n_global=n_accum, near_tol=near_tol)
+                self.last_nonfinite = sh.helper.last_nonfinite  # summed over the ranks
                 return idx.cpu().numpy(), tot, nn
         self.global_max_key()
-        per_idx, per_tot, near = [], [], 0
+        per_idx, per_tot, near, nonfin = [], [], 0, 0
         for sh in self.shards:
             a, b = sh.lo, min(hi, sh.hi)
             if a >= b:
@@ -618,10 +626,13 @@ class DeviceEngine:
                 per_idx.append(idx.cpu().numpy())
                 per_tot.append(tot)
                 near += nn
+                nonfin += sh.helper.last_nonfinite
         idx, total = merge_accepted(per_idx, per_tot, max_keep)
         if self.group is not None:
-            idx, total, near = gather_accepted(idx, total, near, max_keep, self.group,
-                                               device=self.shards[0].ll.device)
+            idx, total, near, nonfin = gather_accepted(idx, total, near, max_keep, self.group,
+                                                       device=self.shards[0].ll.device,
+                                                       nonfinite=nonfin)
+        self.last_nonfinite = nonfin
         return idx, total, near
 
     def _lib_collectives(self):

@@ -206,7 +206,8 @@ class TheJoker:
         else:
             uu = self.rng.uniform(size=n_accum)
             idx, total, near = eng.accept(self.rng, hi=n_accum, max_keep=max_keep, uniforms=uu)
-        self.last_stats.update(n_accepted=total, n_near_threshold=near, ll_max=eng.max_value())
+        self.last_stats.update(n_accepted=total, n_near_threshold=near, ll_max=eng.max_value(),
+                               n_nonfinite=int(getattr(eng, "last_nonfinite", 0)))
         return idx, total
 
     def _full_samples(self, helper, rows, rng, n_linear_samples, in_memory, n_batches):
@@ -371,8 +372,10 @@ class TheJoker:
             n_accum = start_idx + n_process
             good, n_good = self._uniform_accept(eng, n_accum, None)
             ll_max = self.last_stats["ll_max"]
-            if in_memory and not np.isfinite(ll_max):
-                # likelihood_helpers.py:173-176 *returns* this error object
+            if in_memory and (not np.isfinite(ll_max) or self.last_stats["n_nonfinite"] > 0):
+                # likelihood_helpers.py:173-176 *returns* this error object; the test there is
+                # np.isfinite over every ll so far, so a -inf (which the max does not show)
+                # counts too: the accept kernel counts NaN / +-inf lls (tjb_accept_nonfinite)
                 return RuntimeError(f"There are NaN or Inf likelihood values in iteration step {i}!")
             if n_good == 0:
                 raise RuntimeError("Failed to find any good samples!")

@@ -36,7 +36,7 @@ def main_path(ins, epochs_per_iter):
     # loop candidates: backward branches whose body holds 2 * epochs MUFU.SIN
     best = None
     for a, t in ins:
-        m = re.search(r"BRA\s+(?:!?U?P\d,\s*)?0x([0-9a-f]+)", t)
+        m = re.search(r"BRA(?:\.U)?\s+(?:!?U?P\d,\s*)?0x([0-9a-f]+)", t)
         if not m:
             continue
         tgt = int(m.group(1), 16)
