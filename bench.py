@@ -417,7 +417,7 @@ def run_ours(args):
         "work_model_flop_per_sample": w_sample(N_EPOCHS),
         "achieved_work_model": achieved_tf,
         "frac_work_model": achieved_tf / peak_tf,
-        "kernel": "marginal_ll_kernel<2,false,PriorView>", "kernel_ms": kernel_ms,
+        "kernel": "marginal_ll_kernel<2,false,PriorView,EpochRowsParam>", "kernel_ms": kernel_ms,
         "traffic": prof.get("dram_bytes_per_launch_at_2p28") if n == (1 << 28) else None,
         "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
                 "algorithmic_bytes_per_sample": 40,

@@ -130,11 +130,47 @@ constexpr double kUnitsPerRev = 4.0;
 // from M is then formed in FP64 (two instructions), so in total 5 FP64 instructions fewer
 // per epoch.  The fine nodes follow the coarse ones in the table (kTrigNodes in all).
 #ifndef TJB_TRIG2
+#define TJB_TRIG2 1
+#endif
+// z-stage reciprocal refined from the main step's (see rv_unit_columns); needs TJB_HALLEY
+#ifndef TJB_XZ
+#define TJB_XZ 1
+#endif
+#if !TJB_HALLEY  // the third-order main step does not hand out its reciprocal
+#undef TJB_XZ
+#define TJB_XZ 0
+#endif
+#if !TJB_TRIG_TABLE || !TJB_TRIM  // needs the table back-end and its shared-window addressing
+#undef TJB_TRIG2
 #define TJB_TRIG2 0
 #endif
-constexpr int kFineLog2 = TJB_TRIG_TABLE_LOG2;
-constexpr int kTrigNodes = kTrigTableSize * (TJB_TRIG2 ? 2 : 1);
+// Fine nodes per coarse node (2^kFineLog2; the grid has 2^(TJB_TRIG_TABLE_LOG2 + kFineLog2)
+// points per revolution: 2^22 at 2048 x 2048, spacing 1.5e-6 rad).
+#ifndef TJB_FINE_LOG2
+#define TJB_FINE_LOG2 11
+#endif
+constexpr int kFineLog2 = TJB_FINE_LOG2;
+constexpr int kFineNodes = TJB_TRIG2 ? (1 << kFineLog2) : 0;
+constexpr int kTrigNodes = kTrigTableSize + kFineNodes;  // nodes of the table in global memory
 constexpr double kMagic2 = 6755399441055744.0 / (double)(1 << kFineLog2);  // ulp = 2^-kFineLog2
+// Shared-memory copies of the tables in the likelihood kernel.  A warp's 32 lookups are
+// random, and an LDS.128 serves 8 lanes per wavefront only if they hit 8 different 16-byte
+// bank groups: measured 10.4 wavefronts per lookup instead of 4 (ncu, profiles/r02c: the
+// shared-memory pipe is 58 % busy with two lookups per epoch).  With C interleaved copies
+// (copy c of node j at slot j C + c) lane l reads copy l mod C, so the 8 lanes of a wavefront
+// spread over C disjoint sets of bank groups (8 copies: conflict free).  Timed on B200 with
+// 2 x 8, 4 x 4, 1 x 8 and 1 x 4 copies of 2048 + 1024 nodes (192 KB, one CTA per SM): no
+// gain over single copies (profiles/r02c_tune_cta_shapes.jsonl) -- the wavefronts are not
+// what holds the kernel back -- so the default is one copy each.
+#ifndef TJB_COARSE_COPIES
+#define TJB_COARSE_COPIES 1
+#endif
+#ifndef TJB_FINE_COPIES
+#define TJB_FINE_COPIES 1
+#endif
+constexpr int kCoarseCopies = TJB_COARSE_COPIES;
+constexpr int kFineCopies = TJB_FINE_COPIES;
+constexpr int kTrigSlots = kTrigTableSize * kCoarseCopies + kFineNodes * kFineCopies;  // 16 B each
 // fixed-point phase (TJB_PHASE_FIXED): fraction bits that fit one revolution in 32 bits
 constexpr double kFixOne = 4294967296.0 / kUnitsPerRev;          // 2^(32-U)
 constexpr double kMagicFix = 6755399441055744.0 / kFixOne;       // 1.5 * 2^(52-(32-U))
@@ -254,7 +290,7 @@ inline double rcp_pos(double x) { return 1.0 / x; }
 // vector-register operand read per use (an FP64 instruction with three distinct vector
 // operands issues every 3 cycles, with two every 2: DESIGN.md section 4.1).
 #ifndef TJB_UCONST
-#define TJB_UCONST 0
+#define TJB_UCONST 1
 #endif
 #if TJB_UCONST && defined(__CUDA_ARCH__)
 #define TJB_SCM(i) kSinC[i]
@@ -271,15 +307,23 @@ inline double rcp_pos(double x) { return 1.0 / x; }
 // slots; measured: pinned 2.75e9 samples/s, LDC per use 2.61e9, literals 2.57e9.
 struct TrigCoef {
   double s[kNSin], c[kNCos], m[kNMisc];
-  const SinCos *table;  // kTrigTableSize nodes, sin/cos(2 pi j / size); null without a table
+  // kTrigNodes nodes in global (host emulation: host) memory: coarse sin/cos(2 pi j / size),
+  // then the fine nodes of TJB_TRIG2; null without a table
+  const SinCos *table;
 #if TJB_TRIM && defined(__CUDA_ARCH__)
-  // 32-bit shared-window address of the table where it is staged in shared memory (the
+  // 32-bit shared-window addresses of the tables where they are staged in shared memory (the
   // likelihood kernel; sincos_units<true>): ptxas otherwise re-derives the window base of
-  // the generic pointer inside the epoch loop (S2UR / UIADD3 / ULEA / moves)
-  unsigned table_s;
-  TJB_D void use_shared_table() {
-    table_s = (unsigned)__cvta_generic_to_shared(table);
-    asm volatile("" : "+r"(table_s));  // opaque: keep it in a register
+  // a generic pointer inside the epoch loop (S2UR / UIADD3 / ULEA / moves).  They point at
+  // this lane's copy of the coarse / fine nodes in the kernel's shared memory (kCoarseCopies,
+  // kFineCopies above): node j of the lane's copy is at table_c + j * 16 * kCoarseCopies
+  unsigned table_c, table_f;
+  TJB_D void use_shared_table(const SinCos *staged) {
+    const unsigned base = (unsigned)__cvta_generic_to_shared(staged);
+    const unsigned lane = threadIdx.x & 31;
+    table_c = base + (lane & (kCoarseCopies - 1)) * (unsigned)sizeof(SinCos);
+    table_f = base + (unsigned)(kTrigTableSize * kCoarseCopies * sizeof(SinCos)) +
+              (lane & (kFineCopies - 1)) * (unsigned)sizeof(SinCos);
+    asm volatile("" : "+r"(table_c), "+r"(table_f));  // opaque: keep them in registers
   }
 #endif
   // `zero` must be a run-time 0.0 (a kernel parameter): coefficient + zero is an
@@ -308,7 +352,8 @@ TJB_HD void sincos_units(const TrigCoef &tc, double v, double &s, double &c) {
   SinCos node;
   if (kSharedTable) {
     unsigned addr;  // mask, then one multiply-add (the compiler's shift / mask / add is three)
-    asm("mad.lo.u32 %0, %1, 16, %2;" : "=r"(addr) : "r"(k & (kTrigTableSize - 1)), "r"(tc.table_s));
+    asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(addr) : "r"(k & (kTrigTableSize - 1)), "r"(tc.table_c),
+        "n"(16 * kCoarseCopies));
     asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(node.s), "=d"(node.c) : "r"(addr));
   } else {
     node = tc.table[k & (kTrigTableSize - 1)];
@@ -451,10 +496,10 @@ TJB_HD void rotate_small(const TrigCoef &tc, double del, double &sE, double &cE)
 
 // Main-path step and rotation of the TJB_HALLEY variant: delta = u (1 - u t / 2) with
 // u = -f/f1, t = f2/f1; rotation by |delta| < 2^-17 with sin d = d, cos d = 1 - d^2/2.
-TJB_HD double halley2(const OrbitConsts &oc, double D, double sE, double cE) {
+TJB_HD double halley2(const OrbitConsts &oc, double D, double sE, double cE, double &r) {
   const double es = oc.e * sE;
   // 1/f1 to 1e-12 is enough: its error enters delta times |u| <= 2^-17
-  const double r = rcp_pos_newton(fma(-oc.e, cE, 1.0));
+  r = rcp_pos_newton(fma(-oc.e, cE, 1.0));
   const double t = es * r;
   const double u = fma(-D, r, t);
   return u * fma(u * -0.5, t, 1.0);
@@ -471,10 +516,10 @@ TJB_HD void rotate_tiny(const TrigCoef &tc, double del, double &sE, double &cE) 
   sE = sN;
 }
 #if TJB_HALLEY
-#define TJB_MAIN_STEP(oc, tc, D, s, c) halley2(oc, D, s, c)
+#define TJB_MAIN_STEP(oc, tc, D, s, c, r) halley2(oc, D, s, c, r)
 #define TJB_MAIN_ROTATE rotate_tiny
 #else
-#define TJB_MAIN_STEP(oc, tc, D, s, c) householder3(oc, tc, D, s, c)
+#define TJB_MAIN_STEP(oc, tc, D, s, c, r) householder3(oc, tc, D, s, c)
 #define TJB_MAIN_ROTATE rotate_small
 #endif
 
@@ -532,6 +577,20 @@ TJB_HD_NOINLINE SinCos solve_extra_passes(double e, const SinCos *table, double 
   return out;
 }
 
+// z from (sinE, cosE) after the main step, with 1 / (1 - e cosE) refined from the step's own
+// reciprocal r0 = 1 / (1 - e cosE0) (good to 1e-12) instead of a fresh MUFU.RCP64H seed
+// (TJB_XZ): eps = 1 - f1 r0 = (e sinE0 / f1) delta + O(1e-12) with |delta| < 2^-16 on the
+// main path, and r = r0 (1 + eps + eps^2 + eps^3) is good to eps^4 (< 1e-14 for e <= 0.9987
+// in the worst case).  One FP64 instruction more, one MUFU (8 cycles of the XU pipe per
+// warp instruction, profiles/r02c_microbench4.txt) and one move less per epoch.
+TJB_HD double z_from_step_rcp(const OrbitConsts &oc, double sE, double cE, double r0) {
+  const double eps = fma(-fma(-oc.e, cE, 1.0), r0, 1.0);
+  const double p = fma(fma(eps, eps, eps), eps, eps);
+  const double r = fma(r0, p, r0);
+  const double num = fma(oc.b, sE, fma(oc.a, cE, -oc.ea));
+  return fma(num, r, oc.ea);
+}
+
 // K epochs of one sample at once (K independent dependency chains interleaved by
 // the compiler).  dt[k] = t_n - t_ref [day]; z[k] receives z_n.  All lanes of a warp
 // must call together.  The result of a lane depends only on that lane's inputs (not
@@ -582,6 +641,7 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
 
   // ---- FP64: exact reduction of E0 = M + D0, one full sincos, one Householder step
   double del[K];
+  double r0[K];  // 1 / (1 - e cosE0) to 1e-12 from the main step (TJB_XZ)
   bool need[K];
   bool any_need = false;
 #if TJB_TRIM
@@ -598,10 +658,12 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
       SinCos n1, n2;
 #if defined(__CUDA_ARCH__)
       if (kSharedTable) {
-        const unsigned a1 = (((unsigned)idx >> (kFineLog2 - 4)) & ((kTrigTableSize - 1) << 4)) + tc.table_s;
-        unsigned a2;
-        asm("mad.lo.u32 %0, %1, 16, %2;" : "=r"(a2) : "r"(idx & ((1 << kFineLog2) - 1)),
-            "r"(tc.table_s + (unsigned)(kTrigTableSize * sizeof(SinCos))));
+        unsigned a1, a2;
+        asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(a1)
+            : "r"(((unsigned)idx >> kFineLog2) & (kTrigTableSize - 1)), "r"(tc.table_c),
+              "n"(16 * kCoarseCopies));
+        asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(a2) : "r"(idx & ((1 << kFineLog2) - 1)),
+            "r"(tc.table_f), "n"(16 * kFineCopies));
         asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(n1.s), "=d"(n1.c) : "r"(a1));
         asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(n2.s), "=d"(n2.c) : "r"(a2));
       } else
@@ -622,7 +684,7 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
     sincos_units<kSharedTable>(tc, x4[k] + d4, sE[k], cE[k]);
     D[k] = d4 * TJB_MC(2);  // E0 - M [rad]
 #endif
-    del[k] = TJB_MAIN_STEP(oc, tc, D[k], sE[k], cE[k]);
+    del[k] = TJB_MAIN_STEP(oc, tc, D[k], sE[k], cE[k], r0[k]);
     // error map of the step: eps -> ~C eps^4 (tools/kepler_solver_study.py); a lane
     // that moved by 2^-13 (1.2e-4) or more, or produced a NaN, takes further passes.
     // The test reads the exponent field on the integer pipe instead of a DSETP.
@@ -646,8 +708,16 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
     // the normal case: every lane of the warp converged in one pass
 #pragma unroll
     for (int k = 0; k < K; k++) TJB_MAIN_ROTATE(tc, del[k], sE[k], cE[k]);
+#if TJB_XZ
+#pragma unroll
+    for (int k = 0; k < K; k++) z[k] = z_from_step_rcp(oc, sE[k], cE[k], r0[k]);
+    return;
+#endif
   } else {
     // rare: see solve_extra_passes
+#if TJB_XZ
+    bool redo[K];
+#endif
 #pragma unroll
     for (int k = 0; k < K; k++) {
       SinCos fr = {sE[k], cE[k]};
@@ -657,13 +727,29 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
 #elif TJB_TRIM
       need[k] = ((unsigned)hi32(del[k]) << 1) >= (kNeedHi << 1);
 #endif
+#if TJB_XZ
+      // a converged lane keeps exactly the z of the main path (its result must not depend
+      // on what its warp-mates needed)
+      redo[k] = need[k];
+      z[k] = z_from_step_rcp(oc, fr.s, fr.c, r0[k]);
+#endif
       const SinCos r = solve_extra_passes<kCountStats>(oc.e, tc.table, x4[k], D[k] + del[k], fr,
                                                        need[k], st, gstats);
       sE[k] = r.s;
       cE[k] = r.c;
     }
+#if TJB_XZ
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const double r = rcp_pos(fma(-oc.e, cE[k], 1.0));
+      const double num = fma(oc.b, sE[k], fma(oc.a, cE[k], -oc.ea));
+      if (redo[k]) z[k] = fma(num, r, oc.ea);
+    }
+    return;
+#endif
   }
 
+#if !TJB_XZ
   // ---- z = [a (cosE - e) + b sinE] / (1 - e cosE) + e a ---------------------
 #pragma unroll
   for (int k = 0; k < K; k++) {
@@ -671,6 +757,7 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
     const double num = fma(oc.b, sE[k], fma(oc.a, cE[k], -oc.ea));
     z[k] = fma(num, r, oc.ea);
   }
+#endif
 }
 
 // One epoch.

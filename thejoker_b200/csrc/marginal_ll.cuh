@@ -47,7 +47,7 @@ TJB_HD constexpr int row_stride(int L) { return (L + 2 + 1) & ~1; }
 
 // epochs processed per loop iteration of the constant-jitter kernel
 #ifndef TJB_EPOCHS_PER_ITER
-#define TJB_EPOCHS_PER_ITER 3
+#define TJB_EPOCHS_PER_ITER 4
 #endif
 constexpr int kEpochsPerIter = TJB_EPOCHS_PER_ITER;
 
@@ -139,11 +139,14 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab,
                         double M0, double s) {
   constexpr int RS = row_stride(L);
   TrigCoef tc;
-  tc.load(sp.zero, trig);
 #if TJB_TRIM && defined(__CUDA_ARCH__)
-  tc.use_shared_table();  // `trig` is the kernel's shared-memory copy of the table
+  // `trig` is the kernel's shared-memory staging of the tables (interleaved copies, see
+  // kepler.cuh); everything off the epoch loop's main path reads the table in global memory
+  tc.load(sp.zero, sp.trig_table);
+  tc.use_shared_table(trig);
   constexpr bool kSh = true;
 #else
+  tc.load(sp.zero, trig);
   constexpr bool kSh = false;
 #endif
   const OrbitConsts oc = make_orbit_consts(tc, P, e, omega, M0);
@@ -297,10 +300,10 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab,
 #if defined(__CUDACC__)
 
 #ifndef TJB_LL_THREADS
-#define TJB_LL_THREADS 256
+#define TJB_LL_THREADS 640
 #endif
 #ifndef TJB_LL_MIN_CTAS
-#define TJB_LL_MIN_CTAS 2
+#define TJB_LL_MIN_CTAS 1
 #endif
 constexpr int kLLThreads = TJB_LL_THREADS;
 
@@ -343,6 +346,9 @@ struct EpochRowsParam {
 struct EpochRowsShared {  // rows staged in shared memory from sp.table
   int unused;
 };
+struct EpochRowsGlobal {  // rows read where they lie in global memory (sp.table): tables too
+  int unused[2];          // long for shared memory (> ~4900 epochs at L = 2); L1 / L2 hits
+};
 
 template <int L, bool kJit, typename View, typename Rows>
 __global__ void __launch_bounds__(kLLThreads, TJB_LL_MIN_CTAS)
@@ -350,14 +356,21 @@ marginal_ll_kernel(const __grid_constant__ StarParams sp, const View pv,
                    const long long n, double *__restrict__ ll_out, const MaxKeys mk,
                    const __grid_constant__ Rows rows) {
   constexpr bool kParamRows = sizeof(Rows) == sizeof(EpochRowsParam);
-  // dynamic shared memory: [trig table (16-byte aligned) | epoch table unless kParamRows]
+  constexpr bool kGlobalRows = sizeof(Rows) == sizeof(EpochRowsGlobal);
+  // dynamic shared memory: [trig table (16-byte aligned) | epoch table if EpochRowsShared]
   extern __shared__ SinCos smem_trig[];
-  for (int i = threadIdx.x; i < kTrigNodes; i += blockDim.x) smem_trig[i] = sp.trig_table[i];
+  // coarse nodes in kCoarseCopies interleaved copies, then the fine nodes in kFineCopies
+  for (int i = threadIdx.x; i < kTrigTableSize * kCoarseCopies; i += blockDim.x)
+    smem_trig[i] = sp.trig_table[i / kCoarseCopies];
+  for (int i = threadIdx.x; i < kFineNodes * kFineCopies; i += blockDim.x)
+    smem_trig[kTrigTableSize * kCoarseCopies + i] = sp.trig_table[kTrigTableSize + i / kFineCopies];
   const double *tab;
   if constexpr (kParamRows) {
     tab = rows.v;
+  } else if constexpr (kGlobalRows) {
+    tab = sp.table;
   } else {
-    double *stab = reinterpret_cast<double *>(smem_trig + kTrigNodes);
+    double *stab = reinterpret_cast<double *>(smem_trig + kTrigSlots);
     const int tab_len = sp.n_times * row_stride(L);
     for (int i = threadIdx.x; i < tab_len; i += blockDim.x) stab[i] = sp.table[i];
     tab = stab;

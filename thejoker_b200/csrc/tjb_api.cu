@@ -218,16 +218,18 @@ bool tjb_force_shared_rows() {
   return v != 0;
 }
 
+constexpr size_t kMaxSmemPerCta = 227 * 1024;
+
 template <int L, bool J, typename View, typename Rows>
 int launch_ll_rows(TjbHandle *h, const StarParams &sp, const View &pv, long long n, double *d_ll,
                    long long *d_key, cudaStream_t stream, const Rows &rows) {
-  constexpr bool kParamRows = sizeof(Rows) == sizeof(EpochRowsParam);
+  constexpr bool kSharedRows = sizeof(Rows) == sizeof(EpochRowsShared);
   auto kern = marginal_ll_kernel<L, J, View, Rows>;
-  const size_t smem = (size_t)kTrigNodes * sizeof(SinCos) +
-                      (kParamRows ? 0 : (size_t)h->N * row_stride(L) * sizeof(double));
-  if (smem > 227 * 1024)
+  const size_t smem = (size_t)kTrigSlots * sizeof(SinCos) +
+                      (kSharedRows ? (size_t)h->N * row_stride(L) * sizeof(double) : 0);
+  if (smem > kMaxSmemPerCta)
     return fail(TJB_E_INVALID, "epoch table does not fit in shared memory (too many epochs)");
-  if (smem > 48 * 1024)
+  if (smem > 40 * 1024)  // (the static part counts towards the 48 KB default limit)
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kLLThreads, smem));
@@ -263,6 +265,11 @@ int launch_ll(TjbHandle *h, const StarParams &sp, const View &pv, long long n, d
     }
   }
 #endif
+  // a table beyond one CTA's shared memory is read from global memory (L1 / L2 hits)
+  if ((size_t)kTrigSlots * sizeof(SinCos) + (size_t)h->N * row_stride(L) * sizeof(double) >
+      kMaxSmemPerCta)
+    return launch_ll_rows<L, J, View, EpochRowsGlobal>(h, sp, pv, n, d_ll, d_key, stream,
+                                                       EpochRowsGlobal{{0, 0}});
   return launch_ll_rows<L, J, View, EpochRowsShared>(h, sp, pv, n, d_ll, d_key, stream,
                                                      EpochRowsShared{0});
 }

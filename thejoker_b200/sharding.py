@@ -495,7 +495,7 @@ class DeviceEngine:
                 per_idx.append(idx.cpu().numpy())
                 total += tot
                 near += nn
-                nonfin += sh.helper.last_nonfinite
+                nonfin += getattr(sh.helper, "last_nonfinite", 0)
         mine = np.concatenate(per_idx) if per_idx else np.zeros(0, dtype=np.int64)
         # the global first max_keep are among every rank's own first max_keep
         idx, total, near, nonfin = gather_accepted(
@@ -626,7 +626,7 @@ class DeviceEngine:
                 per_idx.append(idx.cpu().numpy())
                 per_tot.append(tot)
                 near += nn
-                nonfin += sh.helper.last_nonfinite
+                nonfin += getattr(sh.helper, "last_nonfinite", 0)
         idx, total = merge_accepted(per_idx, per_tot, max_keep)
         if self.group is not None:
             idx, total, near, nonfin = gather_accepted(idx, total, near, max_keep, self.group,

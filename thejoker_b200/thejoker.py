@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import logging
 import os
+import warnings
 
 import numpy as np
 
@@ -128,7 +129,27 @@ class TheJoker:
             raise ValueError("packed prior samples must have shape (n, 5)")
         return [np.ascontiguousarray(arr[:, i]) for i in range(5)], None
 
+    _warned_jitter = False
+
+    def _warn_jitter(self, cols):
+        """One warning per process when a non-zero jitter meets jitter_mode="apply": the
+        reference's compiled likelihood ignores s (fast_likelihood.pyx:458 stores the inflated
+        ivar and never reads it), so results differ from it by design."""
+        if TheJoker._warned_jitter or self.jitter_mode != "apply" or len(cols) < 5:
+            return
+        s = cols[4]
+        nonzero = bool(s != 0) if np.ndim(s) == 0 else bool(len(s) and np.any(np.asarray(s[:64]) != 0))
+        if nonzero:
+            TheJoker._warned_jitter = True
+            warnings.warn(
+                "prior samples carry a non-zero jitter s and jitter_mode='apply': s is added "
+                "to the variance of every epoch (the documented model).  adrn/thejoker's "
+                "compiled likelihood ignores s (fast_likelihood.pyx:458), so log-likelihoods "
+                "and accepted samples differ from it; pass jitter_mode='reference' to "
+                "reproduce the reference bit for bit.", stacklevel=3)
+
     def _engine(self, data, cols, helper0=None, cyclic=False):
+        self._warn_jitter(cols)
         # helper0: the helper the caller already built to read units / columns; reused
         # for its device instead of creating a second handle for the same star
         helpers = {} if helper0 is None else {helper0.device: helper0}

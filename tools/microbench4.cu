@@ -67,6 +67,42 @@ __global__ void __launch_bounds__(256) k(int iters, double *out, double seed, fl
           d[i] = fma(d[i], d[(i + 3) % 12], d[(i + 7) % 12]);
           f[i] = __sinf(f[i]);
         }
+      } else if (MODE >= 10 && MODE <= 13) {  // (MODE - 10) x 8 DFMA distinct + 8 MUFU.RSQ
+#pragma unroll
+        for (int rep = 0; rep < MODE - 10; rep++)
+#pragma unroll
+          for (int i = 0; i < 8; i++) d[i] = fma(d[i], d[(i + 3) % 12], d[(i + 7) % 12]);
+#pragma unroll
+        for (int i = 0; i < 8; i++) asm("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(f[i]));
+      } else if (MODE == 14) {  // 8 DFMA distinct + 8 RCP64H
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          d[i] = fma(d[i], d[(i + 3) % 12], d[(i + 7) % 12]);
+          if (i < 4) asm("rcp.approx.ftz.f64 %0, %0;" : "+d"(d[8 + i]));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) asm("rcp.approx.ftz.f64 %0, %0;" : "+d"(d[8 + i]));
+      } else if (MODE == 15) {  // 8 DFMA distinct + 8 F2F.F64.F32 (results folded into FP32 adds)
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          d[i] = fma(d[i], d[(i + 3) % 12], d[(i + 7) % 12]);
+          double t = (double)f[i];
+          f[i] = __int_as_float(__double2loint(t) ^ __float_as_int(f[i]));
+        }
+      } else if (MODE == 16) {  // 8 DFMA distinct + 8 I2FP.F32.S32
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          d[i] = fma(d[i], d[(i + 3) % 12], d[(i + 7) % 12]);
+          f[i] = (float)__float_as_int(f[i]);
+        }
+      } else if (MODE == 17) {  // 8 DFMA distinct + 8 LDS.128 with a lane-dependent (random) address
+        extern __shared__ double2 sm[];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          d[i] = fma(d[i], d[(i + 3) % 12], d[(i + 7) % 12]);
+          const double2 v = sm[(__double2loint(d[i]) * 2654435761u >> 21) & 2047];
+          d[8 + (i & 3)] += v.x * v.y;
+        }
       } else if (MODE == 9) {  // 8 FFMA2 only
 #pragma unroll
         for (int i = 0; i < 8; i++)
@@ -89,9 +125,9 @@ void run(const char *name, int nsm) {
   const int iters = 4000, grid = nsm * 8;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  k<MODE><<<grid, 256>>>(100, out, 1e-3, 1e-3f, 0.999, 1.001, 1e-9, -1e-9);
+  k<MODE><<<grid, 256, 32768>>>(100, out, 1e-3, 1e-3f, 0.999, 1.001, 1e-9, -1e-9);
   cudaEventRecord(e0);
-  k<MODE><<<grid, 256>>>(iters, out, 1e-3, 1e-3f, 0.999, 1.001, 1e-9, -1e-9);
+  k<MODE><<<grid, 256, 32768>>>(iters, out, 1e-3, 1e-3f, 0.999, 1.001, 1e-9, -1e-9);
   cudaEventRecord(e1);
   cudaEventSynchronize(e1);
   float ms;
@@ -117,5 +153,13 @@ int main() {
   run<6>("8 DFMA uniform-mult + 4 FFMA2", n);
   run<8>("8 DFMA distinct + 8 MUFU.SIN", n);
   run<9>("8 FFMA2", n);
+  run<10>("8 MUFU.RSQ", n);
+  run<11>("8 DFMA distinct + 8 MUFU.RSQ", n);
+  run<12>("16 DFMA distinct + 8 MUFU.RSQ", n);
+  run<13>("24 DFMA distinct + 8 MUFU.RSQ", n);
+  run<14>("8 DFMA distinct + 8 RCP64H", n);
+  run<15>("8 DFMA distinct + 8 F2F.F64.F32 (+8 LOP3)", n);
+  run<16>("8 DFMA distinct + 8 I2FP.F32.S32", n);
+  run<17>("8 DFMA distinct + 8 LDS.128 random (+8 DFMA, IMAD..)", n);
   return 0;
 }

@@ -44,7 +44,7 @@ def main_path(ins, epochs_per_iter):
             continue
         body = ins[addr[tgt]: addr[a] + 1]
         n_sin = sum("MUFU.SIN" in x[1] for x in body)
-        if n_sin == 2 * epochs_per_iter and (best is None or len(body) > len(best[2])):
+        if n_sin in (epochs_per_iter, 2 * epochs_per_iter) and (best is None or len(body) > len(best[2])):
             best = (tgt, a, body)
     if best is None:
         raise SystemExit("no epoch loop found")

@@ -24,7 +24,7 @@ for name, key in (("source_hash.txt", "source_sha256"), ("hot_kernel_regs.txt", 
     if os.path.exists(f):
         out[key] = open(f).read().strip()
 md += [f"* source hash of the profiled build (`_lib.source_hash()`): `{out.get('source_sha256')}`",
-       f"* `cuobjdump -res-usage` of `marginal_ll_kernel<2,false,PriorView>` in that library: "
+       f"* `cuobjdump -res-usage` of `marginal_ll_kernel<2,false,PriorView,EpochRowsParam>` in that library: "
        f"`{out.get('cuobjdump_hot_kernel')}`", ""]
 
 # ---- launch list --------------------------------------------------------------
@@ -103,6 +103,30 @@ if os.path.exists(rep):
                "", "| reason | warps stalled per issue |", "|---|---:|"]
         for k, x in sorted(stalls.items(), key=lambda kv: -kv[1]):
             md.append(f"| {k} | {x:.3f} |")
+        md.append("")
+        # how busy each unit is: the kernel is spread over four of them
+        pipes = collections.OrderedDict()
+        for label, key in (
+                ("FP64 pipe", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                ("issue slots", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                ("XU pipe (MUFU, F2F)", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+                ("shared-memory wavefronts", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+                ("FMA pipe (FP32, IMAD)", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                ("ALU pipe", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                ("LSU instructions", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+                ("uniform pipe", "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active")):
+            if key in h:
+                pipes[label] = float(v[h.index(key)])
+        for label, key in (("shared-memory wavefronts", "memory_l1_wavefronts_shared"),
+                           ("shared-memory wavefronts without bank conflicts", "memory_l1_wavefronts_shared_ideal")):
+            if key in h:
+                out["smem_" + key.split("memory_l1_")[1]] = float(v[h.index(key)])
+        out["pipe_pct"] = pipes
+        md += ["## Unit utilisation (same capture, % of peak)", "", "| unit | % |", "|---|---:|"]
+        md += [f"| {k} | {x:.1f} |" for k, x in pipes.items()]
+        if "smem_wavefronts_shared" in out:
+            md += ["", f"* shared-memory wavefronts {out['smem_wavefronts_shared']:.4g} "
+                   f"(conflict-free: {out.get('smem_wavefronts_shared_ideal', float('nan')):.4g})"]
         md.append("")
 
 open(os.path.join(P, f"{tag}_ncu_summary.md"), "w").write("\n".join(md) + "\n")
