@@ -315,6 +315,36 @@ def run_ours(args):
 
     e2e_value = time_e2e(e2e_columns)
 
+    # (1a) what the platform allows for exactly these bytes: the same four pinned columns
+    #      copied to the device and ll copied back with bare cudaMemcpyAsync on two streams,
+    #      all ranks at once, no kernel -- the ceiling `e2e.value` is to be read against
+    #      (8 ranks share the host's memory and PCIe fabric: tools/h2d_ceiling.py)
+    def copy_ceiling():
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        dev_cols = [torch.empty(n_e2e, dtype=torch.float64, device="cuda") for _ in range(4)]
+        dev_ll = ll[:n_e2e]
+        scratch_ll = torch.empty(n_e2e, dtype=torch.float64).pin_memory()
+
+        def once():
+            with torch.cuda.stream(s_in):
+                for d, h in zip(dev_cols, cols_host):
+                    d.copy_(h, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                scratch_ll.copy_(dev_ll, non_blocking=True)
+            s_in.synchronize(); s_out.synchronize()
+
+        once()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            once()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return n_e2e * world * e2e_steps / float(dt.item())
+
+    e2e_ceiling = copy_ceiling()
+
     # (1b) the same call on ordinary (pageable) numpy columns, as a user's JokerSamples
     #      holds them: staged through the library's page-locked ring by host threads
     e2e_pageable = e2e_public = None
@@ -436,7 +466,14 @@ def run_ours(args):
                    "n_prior": n_total, "n_epochs": N_EPOCHS, "sharding": f"contiguous x{world}"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_e2e * 32),
                 "d2h_bytes_per_step": int(n_e2e * 8), "n_per_rank": int(n_e2e), "steps": e2e_steps,
-                "rank0_cpu_binding": numa_cpus, "pageable_columns": e2e_pageable,
+                "rank0_cpu_binding": numa_cpus,
+                "copy_ceiling": {"value": e2e_ceiling, "unit": UNIT,
+                                 "frac": e2e_value / e2e_ceiling,
+                                 "what": "the same pinned columns in and ll out with bare "
+                                         "cudaMemcpyAsync on two streams, all ranks at once, no "
+                                         "kernel: what the host's memory and PCIe fabric allow "
+                                         "for these bytes"},
+                "pageable_columns": e2e_pageable,
                 "public_api": e2e_public,
                 "call": "TheJoker.marginal_ln_likelihood data path: pinned host columns P, e, "
                         "omega, M0 (s constant) in, host ll out (CJokerHelper."
