@@ -2,9 +2,13 @@
 // Host-side glue only: spec validation, the per-star constant tables (computed in
 // long double), kernel dispatch on n_linear, stream handling.  No CPU compute path.
 #include <cuda_runtime.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <functional>
 #include <cmath>
 #include <cstdio>
@@ -561,22 +565,141 @@ bool is_pageable(const void *ptr) {
   return a.type == cudaMemoryTypeUnregistered;
 }
 
-// dst[c][0..count) = src[c][0..count) for n_cols columns, split over host threads
+// ---- host copies between the caller's pageable arrays and the page-locked ring --------
+//
+// A persistent pool of copy threads (started on first use, never joined: the object is
+// leaked on purpose so that no destructor runs under threads parked on its condition
+// variable at process exit).  One job at a time; the calling thread works too.  Chunks of
+// 1 MB are copied with non-temporal stores: the destination (the ring, or the caller's ll
+// array) is not read again by the CPU, so the read-for-ownership of a cached store would
+// only add a third stream of memory traffic to a copy that is bound by memory bandwidth.
+struct CopyTask {
+  char *dst;
+  const char *src;
+  size_t bytes;
+};
+
+void nt_copy(char *dst, const char *src, size_t n) {
+#if defined(__SSE2__)
+  if (n >= 4096) {
+    const size_t head = (16 - ((uintptr_t)dst & 15)) & 15;
+    std::memcpy(dst, src, head);
+    dst += head; src += head; n -= head;
+    const size_t blocks = n / 64;
+    for (size_t i = 0; i < blocks; i++, dst += 64, src += 64) {
+      const __m128i a = _mm_loadu_si128((const __m128i *)(src));
+      const __m128i b = _mm_loadu_si128((const __m128i *)(src + 16));
+      const __m128i c = _mm_loadu_si128((const __m128i *)(src + 32));
+      const __m128i d = _mm_loadu_si128((const __m128i *)(src + 48));
+      _mm_stream_si128((__m128i *)(dst), a);
+      _mm_stream_si128((__m128i *)(dst + 16), b);
+      _mm_stream_si128((__m128i *)(dst + 32), c);
+      _mm_stream_si128((__m128i *)(dst + 48), d);
+    }
+    n -= blocks * 64;
+    _mm_sfence();
+  }
+#endif
+  std::memcpy(dst, src, n);
+}
+
+class CopyPool {
+ public:
+  static CopyPool &get() {
+    static CopyPool *pool = new CopyPool();  // leaked, see above
+    return *pool;
+  }
+  // copies every task; returns when all are done
+  void run(const std::vector<CopyTask> &tasks) {
+    if (tasks.empty()) return;
+    if (n_workers_ == 0 || tasks.size() == 1) {
+      for (const CopyTask &t : tasks) nt_copy(t.dst, t.src, t.bytes);
+      return;
+    }
+    std::lock_guard<std::mutex> job(job_mu_);  // one job at a time
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      tasks_ = &tasks;
+      next_.store(0, std::memory_order_relaxed);
+      pending_.store((long long)tasks.size(), std::memory_order_relaxed);
+      generation_++;
+    }
+    cv_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(mu_);
+    // all tasks copied and no worker still looking at the task list
+    done_cv_.wait(lk, [&] { return pending_.load(std::memory_order_acquire) == 0 && active_ == 0; });
+    tasks_ = nullptr;
+  }
+
+ private:
+  CopyPool() {
+    unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    // ranks of one node share the cores (torchrun sets LOCAL_WORLD_SIZE)
+    if (const char *e = std::getenv("LOCAL_WORLD_SIZE")) {
+      const int w = std::atoi(e);
+      if (w > 1) hw = std::max(1u, hw / (unsigned)w);
+    }
+    unsigned want = 15;
+    if (const char *e = std::getenv("TJB_COPY_THREADS")) want = (unsigned)std::max(0, std::atoi(e));
+    n_workers_ = (int)std::min(want, hw > 1 ? hw - 1 : 0u);
+    for (int i = 0; i < n_workers_; i++) std::thread([this] { loop(); }).detach();
+  }
+  void work() {
+    const std::vector<CopyTask> &tasks = *tasks_;
+    for (;;) {
+      const size_t i = next_.fetch_add(1, std::memory_order_relaxed);
+      if (i >= tasks.size()) return;
+      nt_copy(tasks[i].dst, tasks[i].src, tasks[i].bytes);
+      if (pending_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+        std::lock_guard<std::mutex> lk(mu_);
+        done_cv_.notify_all();
+      }
+    }
+  }
+  void loop() {
+    unsigned long long seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return generation_ != seen; });
+        seen = generation_;
+        if (!tasks_) continue;
+        active_++;
+      }
+      work();
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        active_--;
+        done_cv_.notify_all();
+      }
+    }
+  }
+  std::mutex job_mu_, mu_;
+  std::condition_variable cv_, done_cv_;
+  const std::vector<CopyTask> *tasks_ = nullptr;
+  std::atomic<size_t> next_{0};
+  std::atomic<long long> pending_{0};
+  unsigned long long generation_ = 0;
+  int active_ = 0;
+  int n_workers_ = 0;
+};
+
+// dst[c][0..count) = src[c][0..count) for n_cols columns, split over the copy pool
 void parallel_copy(double *const *dst, const double *const *src, int n_cols, size_t count) {
-  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-  const int per_col = (int)std::max(1u, std::min(n_cols == 1 ? 8u : 4u, hw / (unsigned)n_cols));
-  if (count < (1u << 16) || hw == 1) {
+  constexpr size_t kChunk = (size_t)1 << 17;  // doubles per task: 1 MB
+  if (count * (size_t)n_cols < ((size_t)1 << 16)) {
     for (int c = 0; c < n_cols; c++) std::memcpy(dst[c], src[c], count * sizeof(double));
     return;
   }
-  std::vector<std::thread> pool;
-  pool.reserve((size_t)n_cols * per_col);
-  for (int c = 0; c < n_cols; c++)
-    for (int k = 0; k < per_col; k++) {
-      const size_t a = count * k / per_col, b = count * (k + 1) / per_col;
-      pool.emplace_back([=] { std::memcpy(dst[c] + a, src[c] + a, (b - a) * sizeof(double)); });
+  std::vector<CopyTask> tasks;
+  tasks.reserve((size_t)n_cols * (count / kChunk + 1));
+  for (size_t a = 0; a < count; a += kChunk)
+    for (int c = 0; c < n_cols; c++) {
+      const size_t m = std::min(kChunk, count - a);
+      tasks.push_back({(char *)(dst[c] + a), (const char *)(src[c] + a), m * sizeof(double)});
     }
-  for (auto &t : pool) t.join();
+  CopyPool::get().run(tasks);
 }
 
 }  // namespace
