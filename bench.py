@@ -550,9 +550,15 @@ class ReferencePool:
 
         from thejoker_b200.helper import extract_spec
 
+        from oracle import ref_cython
+
         all_data, prior, trend_M = make_star()
         spec = extract_spec(all_data, prior, trend_M)
         self.cores = cores
+        # the compiled reference operator is loaded in this process too (the forked workers
+        # inherit the mapping), so that what ran is visible from the parent's loaded objects
+        ref_cython.load()
+        self.native_so = ref_cython.ext_path()
         self.pool = mp.get_context("fork").Pool(
             cores, initializer=_ref_worker_init,
             initargs=(spec, int(spec["n_poly"]), int(spec["n_offsets"])))
@@ -646,6 +652,7 @@ def run_reference(args):
                          "sample": sample + "; " + arm.what},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "native_so": getattr(arm, "native_so", None),  # the compiled reference operator, loaded here
     }
     print(json.dumps(rec))
 
