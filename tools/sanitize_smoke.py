@@ -43,6 +43,21 @@ for N, pt, kw in (() if only_multistar else ((7, 1, {}), (16, 2, {"n_surveys": 2
         assert np.array_equal(d_ll.cpu().numpy(), h_ll)
         assert np.array_equal(helper.batch_marginal_ln_likelihood(big), h_ll)
 if not only_multistar:
+    # the other two sources of the epoch rows: staged in shared memory, read from global memory
+    from thejoker_b200 import _lib
+
+    lib = _lib.load()
+    spec, data, prior = star_spec(33, 1)
+    helper = tj.CJokerHelper.from_spec(spec, device=0)
+    chunk = prior_chunk(700)
+    a = helper.batch_marginal_ln_likelihood(chunk)
+    _lib.check(lib.tjb_set_epoch_rows_mode(1))
+    assert np.array_equal(a, helper.batch_marginal_ln_likelihood(chunk))
+    _lib.check(lib.tjb_set_epoch_rows_mode(0))
+    spec, data, prior = star_spec(8000, 1)
+    big_helper = tj.CJokerHelper.from_spec(spec, device=0)
+    assert np.isfinite(big_helper.batch_marginal_ln_likelihood(prior_chunk(96))).all()
+if not only_multistar:
     prior = default_prior(1, sigma_K0=25.0, P_min=5.0, P_max=500.0)
     flat, _ = make_data(8, rng=np.random.default_rng(11), K=1e-4)
     ps = prior.sample(size=20_000, return_logprobs=True, rng=np.random.default_rng(1))
