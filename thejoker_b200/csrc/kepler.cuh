@@ -153,24 +153,11 @@ constexpr int kFineLog2 = TJB_FINE_LOG2;
 constexpr int kFineNodes = TJB_TRIG2 ? (1 << kFineLog2) : 0;
 constexpr int kTrigNodes = kTrigTableSize + kFineNodes;  // nodes of the table in global memory
 constexpr double kMagic2 = 6755399441055744.0 / (double)(1 << kFineLog2);  // ulp = 2^-kFineLog2
-// Shared-memory copies of the tables in the likelihood kernel.  A warp's 32 lookups are
-// random, and an LDS.128 serves 8 lanes per wavefront only if they hit 8 different 16-byte
-// bank groups: measured 10.4 wavefronts per lookup instead of 4 (ncu, profiles/r02c: the
-// shared-memory pipe is 58 % busy with two lookups per epoch).  With C interleaved copies
-// (copy c of node j at slot j C + c) lane l reads copy l mod C, so the 8 lanes of a wavefront
-// spread over C disjoint sets of bank groups (8 copies: conflict free).  Timed on B200 with
-// 2 x 8, 4 x 4, 1 x 8 and 1 x 4 copies of 2048 + 1024 nodes (192 KB, one CTA per SM): no
-// gain over single copies (profiles/r02c_tune_cta_shapes.jsonl) -- the wavefronts are not
-// what holds the kernel back -- so the default is one copy each.
-#ifndef TJB_COARSE_COPIES
-#define TJB_COARSE_COPIES 1
-#endif
-#ifndef TJB_FINE_COPIES
-#define TJB_FINE_COPIES 1
-#endif
-constexpr int kCoarseCopies = TJB_COARSE_COPIES;
-constexpr int kFineCopies = TJB_FINE_COPIES;
-constexpr int kTrigSlots = kTrigTableSize * kCoarseCopies + kFineNodes * kFineCopies;  // 16 B each
+// (Interleaved per-lane copies of the tables in shared memory -- which make the random
+// LDS.128 lookups bank-conflict free, 4 wavefronts instead of 10.4 -- were built and timed
+// in round 2c with 2 x 8, 4 x 4, 1 x 8 and 1 x 4 copies: no gain,
+// profiles/r02c_tune_cta_shapes.jsonl; the wavefronts are not what holds the kernel back.)
+constexpr int kTrigSlots = kTrigNodes;  // 16-byte slots of the staged tables
 // fixed-point phase (TJB_PHASE_FIXED): fraction bits that fit one revolution in 32 bits
 constexpr double kFixOne = 4294967296.0 / kUnitsPerRev;          // 2^(32-U)
 constexpr double kMagicFix = 6755399441055744.0 / kFixOne;       // 1.5 * 2^(52-(32-U))
@@ -311,19 +298,14 @@ struct TrigCoef {
   // then the fine nodes of TJB_TRIG2; null without a table
   const SinCos *table;
 #if TJB_TRIM && defined(__CUDA_ARCH__)
-  // 32-bit shared-window addresses of the tables where they are staged in shared memory (the
+  // 32-bit shared-window address of the tables where they are staged in shared memory (the
   // likelihood kernel; sincos_units<true>): ptxas otherwise re-derives the window base of
-  // a generic pointer inside the epoch loop (S2UR / UIADD3 / ULEA / moves).  They point at
-  // this lane's copy of the coarse / fine nodes in the kernel's shared memory (kCoarseCopies,
-  // kFineCopies above): node j of the lane's copy is at table_c + j * 16 * kCoarseCopies
-  unsigned table_c, table_f;
+  // a generic pointer inside the epoch loop (S2UR / UIADD3 / ULEA / moves).  The fine nodes
+  // follow the coarse ones, at a constant byte offset that goes into the load instruction.
+  unsigned table_s;
   TJB_D void use_shared_table(const SinCos *staged) {
-    const unsigned base = (unsigned)__cvta_generic_to_shared(staged);
-    const unsigned lane = threadIdx.x & 31;
-    table_c = base + (lane & (kCoarseCopies - 1)) * (unsigned)sizeof(SinCos);
-    table_f = base + (unsigned)(kTrigTableSize * kCoarseCopies * sizeof(SinCos)) +
-              (lane & (kFineCopies - 1)) * (unsigned)sizeof(SinCos);
-    asm volatile("" : "+r"(table_c), "+r"(table_f));  // opaque: keep them in registers
+    table_s = (unsigned)__cvta_generic_to_shared(staged);
+    asm volatile("" : "+r"(table_s));  // opaque: keep it in a register
   }
 #endif
   // `zero` must be a run-time 0.0 (a kernel parameter): coefficient + zero is an
@@ -352,8 +334,7 @@ TJB_HD void sincos_units(const TrigCoef &tc, double v, double &s, double &c) {
   SinCos node;
   if (kSharedTable) {
     unsigned addr;  // mask, then one multiply-add (the compiler's shift / mask / add is three)
-    asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(addr) : "r"(k & (kTrigTableSize - 1)), "r"(tc.table_c),
-        "n"(16 * kCoarseCopies));
+    asm("mad.lo.u32 %0, %1, 16, %2;" : "=r"(addr) : "r"(k & (kTrigTableSize - 1)), "r"(tc.table_s));
     asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(node.s), "=d"(node.c) : "r"(addr));
   } else {
     node = tc.table[k & (kTrigTableSize - 1)];
@@ -595,7 +576,7 @@ TJB_HD double z_from_step_rcp(const OrbitConsts &oc, double sE, double cE, doubl
 // the compiler).  dt[k] = t_n - t_ref [day]; z[k] receives z_n.  All lanes of a warp
 // must call together.  The result of a lane depends only on that lane's inputs (not
 // on its warp-mates): lanes that need extra passes iterate under a per-lane flag.
-template <int K, bool kCountStats, bool kSharedTable = false>
+template <int K, bool kCountStats, bool kSharedTable = false, bool kXZ = (TJB_XZ != 0)>
 TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const double *dt, double *z,
                             SolveStats *st, unsigned long long *gstats = nullptr) {
   double x4[K], D[K], sE[K], cE[K];  // x4: mean anomaly in angle units (unreduced)
@@ -659,13 +640,13 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
 #if defined(__CUDA_ARCH__)
       if (kSharedTable) {
         unsigned a1, a2;
-        asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(a1)
-            : "r"(((unsigned)idx >> kFineLog2) & (kTrigTableSize - 1)), "r"(tc.table_c),
-              "n"(16 * kCoarseCopies));
-        asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(a2) : "r"(idx & ((1 << kFineLog2) - 1)),
-            "r"(tc.table_f), "n"(16 * kFineCopies));
+        asm("mad.lo.u32 %0, %1, 16, %2;" : "=r"(a1)
+            : "r"(((unsigned)idx >> kFineLog2) & (kTrigTableSize - 1)), "r"(tc.table_s));
+        asm("mad.lo.u32 %0, %1, 16, %2;" : "=r"(a2) : "r"(idx & ((1 << kFineLog2) - 1)),
+            "r"(tc.table_s));
         asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(n1.s), "=d"(n1.c) : "r"(a1));
-        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(n2.s), "=d"(n2.c) : "r"(a2));
+        asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(n2.s), "=d"(n2.c)
+            : "r"(a2), "n"(kTrigTableSize * sizeof(SinCos)));
       } else
 #endif
       {
@@ -708,16 +689,14 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
     // the normal case: every lane of the warp converged in one pass
 #pragma unroll
     for (int k = 0; k < K; k++) TJB_MAIN_ROTATE(tc, del[k], sE[k], cE[k]);
-#if TJB_XZ
+    if (kXZ) {
 #pragma unroll
-    for (int k = 0; k < K; k++) z[k] = z_from_step_rcp(oc, sE[k], cE[k], r0[k]);
-    return;
-#endif
+      for (int k = 0; k < K; k++) z[k] = z_from_step_rcp(oc, sE[k], cE[k], r0[k]);
+      return;
+    }
   } else {
     // rare: see solve_extra_passes
-#if TJB_XZ
     bool redo[K];
-#endif
 #pragma unroll
     for (int k = 0; k < K; k++) {
       SinCos fr = {sE[k], cE[k]};
@@ -727,29 +706,26 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
 #elif TJB_TRIM
       need[k] = ((unsigned)hi32(del[k]) << 1) >= (kNeedHi << 1);
 #endif
-#if TJB_XZ
-      // a converged lane keeps exactly the z of the main path (its result must not depend
-      // on what its warp-mates needed)
+      // (kXZ) a converged lane keeps exactly the z of the main path: its result must not
+      // depend on what its warp-mates needed
       redo[k] = need[k];
-      z[k] = z_from_step_rcp(oc, fr.s, fr.c, r0[k]);
-#endif
+      if (kXZ) z[k] = z_from_step_rcp(oc, fr.s, fr.c, r0[k]);
       const SinCos r = solve_extra_passes<kCountStats>(oc.e, tc.table, x4[k], D[k] + del[k], fr,
                                                        need[k], st, gstats);
       sE[k] = r.s;
       cE[k] = r.c;
     }
-#if TJB_XZ
+    if (kXZ) {
 #pragma unroll
-    for (int k = 0; k < K; k++) {
-      const double r = rcp_pos(fma(-oc.e, cE[k], 1.0));
-      const double num = fma(oc.b, sE[k], fma(oc.a, cE[k], -oc.ea));
-      if (redo[k]) z[k] = fma(num, r, oc.ea);
+      for (int k = 0; k < K; k++) {
+        const double r = rcp_pos(fma(-oc.e, cE[k], 1.0));
+        const double num = fma(oc.b, sE[k], fma(oc.a, cE[k], -oc.ea));
+        if (redo[k]) z[k] = fma(num, r, oc.ea);
+      }
+      return;
     }
-    return;
-#endif
   }
 
-#if !TJB_XZ
   // ---- z = [a (cosE - e) + b sinE] / (1 - e cosE) + e a ---------------------
 #pragma unroll
   for (int k = 0; k < K; k++) {
@@ -757,14 +733,13 @@ TJB_HD void rv_unit_columns(const OrbitConsts &oc, const TrigCoef &tc, const dou
     const double num = fma(oc.b, sE[k], fma(oc.a, cE[k], -oc.ea));
     z[k] = fma(num, r, oc.ea);
   }
-#endif
 }
 
 // One epoch.
-template <bool kCountStats, bool kSharedTable = false>
+template <bool kCountStats, bool kSharedTable = false, bool kXZ = (TJB_XZ != 0)>
 TJB_HD double rv_unit_column(const OrbitConsts &oc, const TrigCoef &tc, double dt, SolveStats *st) {
   double z;
-  rv_unit_columns<1, kCountStats, kSharedTable>(oc, tc, &dt, &z, st);
+  rv_unit_columns<1, kCountStats, kSharedTable, kXZ>(oc, tc, &dt, &z, st);
   return z;
 }
 

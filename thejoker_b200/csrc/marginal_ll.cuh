@@ -45,11 +45,38 @@ struct PriorGenView {
 // in chi2.
 TJB_HD constexpr int row_stride(int L) { return (L + 2 + 1) & ~1; }
 
-// epochs processed per loop iteration of the constant-jitter kernel
+// Shape of the likelihood kernel: threads of the one CTA per SM, epochs per loop iteration
+// (independent Kepler chains for ILP), and whether z takes its reciprocal from the step
+// (kepler.cuh, TJB_XZ).  Timed on B200 (profiles/r02c_tune_cta_shapes.jsonl):
+//   * per-sample jitter (all the Gram sums in registers): 640 threads x 4 epochs, 96 registers;
+//     more threads lose to spills (1024 x 2: -7 % at L = 2, -35 % at L = 4);
+//   * constant jitter, L <= 4: 1024 threads x 2 epochs, 64 registers, without TJB_XZ:
+//     +2.7 % / +2.9 % / +3.4 % at L = 2 / 3 / 4 over 640 x 4 -- the shorter FP32 / FP64
+//     phases of more warps interleave better on the four units the kernel loads;
+//   * constant jitter, L > 4: the 640 x 4 shape (not timed wider).
+// A shape whose warp count is not a multiple of 4 leaves schedulers unevenly loaded.
 #ifndef TJB_EPOCHS_PER_ITER
 #define TJB_EPOCHS_PER_ITER 4
 #endif
-constexpr int kEpochsPerIter = TJB_EPOCHS_PER_ITER;
+#ifndef TJB_LL_THREADS
+#define TJB_LL_THREADS 640
+#endif
+#ifndef TJB_LL_MIN_CTAS
+#define TJB_LL_MIN_CTAS 1
+#endif
+#ifndef TJB_WIDE_THREADS  // 0: one shape for every kernel
+#define TJB_WIDE_THREADS 1024
+#endif
+#ifndef TJB_WIDE_EPOCHS
+#define TJB_WIDE_EPOCHS 2
+#endif
+template <int L, bool kJit>
+struct LLShape {
+  static constexpr bool kWide = TJB_WIDE_THREADS > 0 && !kJit && L <= 4;
+  static constexpr int kThreads = kWide ? TJB_WIDE_THREADS : TJB_LL_THREADS;
+  static constexpr int kEpochs = kWide ? TJB_WIDE_EPOCHS : TJB_EPOCHS_PER_ITER;
+  static constexpr bool kXZ = kWide ? false : (TJB_XZ != 0);
+};
 
 // header of the loop over groups of kEpochsPerIter epochs; leaves n at the first epoch of
 // the remainder.  The TJB_TRIM form counts groups down (one add + compare against zero per
@@ -138,6 +165,8 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab,
                         const SinCos *__restrict__ trig, double P, double e, double omega,
                         double M0, double s) {
   constexpr int RS = row_stride(L);
+  constexpr int kEpochsPerIter = LLShape<L, kJit>::kEpochs;
+  constexpr bool kXZ = LLShape<L, kJit>::kXZ;
   TrigCoef tc;
 #if TJB_TRIM && defined(__CUDA_ARCH__)
   // `trig` is the kernel's shared-memory staging of the tables (interleaved copies, see
@@ -180,7 +209,7 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab,
 #pragma unroll
       for (int j = 0; j < kEpochsPerIter; j++) dt[j] = row[j * RS];
 #endif
-      rv_unit_columns<kEpochsPerIter, false, kSh>(oc, tc, dt, z, nullptr, sp.stats);
+      rv_unit_columns<kEpochsPerIter, false, kSh, kXZ>(oc, tc, dt, z, nullptr, sp.stats);
 #pragma unroll
       for (int j = 0; j < kEpochsPerIter; j++) {
         const double *rj = row + j * RS;
@@ -195,7 +224,7 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab,
       }
     }
     for (; n < N; n++, row += RS) {
-      const double z = rv_unit_column<false, kSh>(oc, tc, row[0], nullptr);
+      const double z = rv_unit_column<false, kSh, kXZ>(oc, tc, row[0], nullptr);
       Szz = fma(z * z, row[1], Szz);
       Szy = fma(z, row[2], Szy);
 #pragma unroll
@@ -253,20 +282,20 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab,
         dt[j] = dv.x;
         vn[j] = dv.y;
       }
-      rv_unit_columns<kEpochsPerIter, false, kSh>(oc, tc, dt, z, nullptr, sp.stats);
+      rv_unit_columns<kEpochsPerIter, false, kSh, kXZ>(oc, tc, dt, z, nullptr, sp.stats);
 #pragma unroll
       for (int j = 0; j < kEpochsPerIter; j++) accumulate(row + j * RS, z[j], vn[j]);
 #else
 #pragma unroll
       for (int j = 0; j < kEpochsPerIter; j++) dt[j] = row[j * RS];
-      rv_unit_columns<kEpochsPerIter, false, kSh>(oc, tc, dt, z, nullptr, sp.stats);
+      rv_unit_columns<kEpochsPerIter, false, kSh, kXZ>(oc, tc, dt, z, nullptr, sp.stats);
 #pragma unroll
       for (int j = 0; j < kEpochsPerIter; j++) accumulate(row + j * RS, z[j], row[j * RS + 1]);
 #endif
       lp.renorm();  // at most kEpochsPerIter factors between renormalisations
     }
     for (; n < N; n++, row += RS) {
-      accumulate(row, rv_unit_column<false, kSh>(oc, tc, row[0], nullptr), row[1]);
+      accumulate(row, rv_unit_column<false, kSh, kXZ>(oc, tc, row[0], nullptr), row[1]);
       lp.renorm();
     }
     lp.renorm();
@@ -299,13 +328,7 @@ TJB_HD double sample_ll(const StarParams &sp, const double *__restrict__ tab,
 
 #if defined(__CUDACC__)
 
-#ifndef TJB_LL_THREADS
-#define TJB_LL_THREADS 640
-#endif
-#ifndef TJB_LL_MIN_CTAS
-#define TJB_LL_MIN_CTAS 1
-#endif
-constexpr int kLLThreads = TJB_LL_THREADS;
+
 
 // what varies between the two kernels below: where a sample's parameters come from
 template <bool kJit>
@@ -351,19 +374,16 @@ struct EpochRowsGlobal {  // rows read where they lie in global memory (sp.table
 };
 
 template <int L, bool kJit, typename View, typename Rows>
-__global__ void __launch_bounds__(kLLThreads, TJB_LL_MIN_CTAS)
+__global__ void __launch_bounds__((LLShape<L, kJit>::kThreads), TJB_LL_MIN_CTAS)
 marginal_ll_kernel(const __grid_constant__ StarParams sp, const View pv,
                    const long long n, double *__restrict__ ll_out, const MaxKeys mk,
                    const __grid_constant__ Rows rows) {
+  constexpr int kLLThreads = LLShape<L, kJit>::kThreads;
   constexpr bool kParamRows = sizeof(Rows) == sizeof(EpochRowsParam);
   constexpr bool kGlobalRows = sizeof(Rows) == sizeof(EpochRowsGlobal);
   // dynamic shared memory: [trig table (16-byte aligned) | epoch table if EpochRowsShared]
   extern __shared__ SinCos smem_trig[];
-  // coarse nodes in kCoarseCopies interleaved copies, then the fine nodes in kFineCopies
-  for (int i = threadIdx.x; i < kTrigTableSize * kCoarseCopies; i += blockDim.x)
-    smem_trig[i] = sp.trig_table[i / kCoarseCopies];
-  for (int i = threadIdx.x; i < kFineNodes * kFineCopies; i += blockDim.x)
-    smem_trig[kTrigTableSize * kCoarseCopies + i] = sp.trig_table[kTrigTableSize + i / kFineCopies];
+  for (int i = threadIdx.x; i < kTrigSlots; i += blockDim.x) smem_trig[i] = sp.trig_table[i];
   const double *tab;
   if constexpr (kParamRows) {
     tab = rows.v;

@@ -228,6 +228,7 @@ template <int L, bool J, typename View, typename Rows>
 int launch_ll_rows(TjbHandle *h, const StarParams &sp, const View &pv, long long n, double *d_ll,
                    long long *d_key, cudaStream_t stream, const Rows &rows) {
   constexpr bool kSharedRows = sizeof(Rows) == sizeof(EpochRowsShared);
+  constexpr int kLLThreads = LLShape<L, J>::kThreads;
   auto kern = marginal_ll_kernel<L, J, View, Rows>;
   const size_t smem = (size_t)kTrigSlots * sizeof(SinCos) +
                       (kSharedRows ? (size_t)h->N * row_stride(L) * sizeof(double) : 0);

@@ -30,8 +30,12 @@ ll = torch.empty(n, dtype=torch.float64, device="cuda")
 # span: time baseline in units of the 51.8 d fixture period (3 = the benchmark data, 155 d;
 # 77 = 4000 d, where the float phase reduction of the shipped loop starts to send warps
 # through the extra-pass path: tests/test_host_logic.py::test_phase_reduction_variants)
-for N, pt, jit, span in ((64, 1, False, 3.0), (64, 2, True, 3.0), (256, 1, False, 3.0),
-                         (16, 1, False, 3.0), (64, 1, False, 77.0), (64, 1, False, 193.0)):
+shapes = ((64, 1, False, 3.0), (64, 2, True, 3.0), (256, 1, False, 3.0),
+          (16, 1, False, 3.0), (64, 1, False, 77.0), (64, 1, False, 193.0))
+if os.environ.get("TJB_TUNE_SHAPES") == "L":  # how a CTA shape holds up as n_linear grows
+    shapes = ((64, 1, False, 3.0), (64, 2, False, 3.0), (64, 3, False, 3.0), (64, 1, True, 3.0),
+              (64, 2, True, 3.0), (64, 3, True, 3.0), (20, 2, True, 3.0))
+for N, pt, jit, span in shapes:
     spec, data, prior = star_spec(N, pt, t_span_periods=span)
     all_data, ids, trend_M = validate_prepare_data(data, prior.poly_trend, prior.n_offsets)
     h = tj.CJokerHelper(all_data, prior, trend_M, device=0)
