@@ -373,8 +373,8 @@ VARIANTS = [LEGACY, "TJB_NEED_LOG2=16", "TJB_NEED_LOG2=17", "TJB_VOTE_D2=1", "TJ
             "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_HALLEY=1 TJB_TRIG_TABLE_LOG2=11 TJB_EPOCHS_PER_ITER=3",
             "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_EPOCHS_PER_ITER=4",
             # round 2c defaults: two-level table, z reciprocal from the step's, 4 epochs / iteration
-            "TJB_TRIG2=0 TJB_XZ=0 TJB_EPOCHS_PER_ITER=3", "TJB_TRIG2=0", "TJB_XZ=0",
-            "TJB_EPOCHS_PER_ITER=2", "TJB_EPOCHS_PER_ITER=3"]
+            "TJB_TRIG2=0 TJB_EPOCHS_PER_ITER=3", "TJB_TRIG2=0", "TJB_XZ=1",
+            "TJB_XZ=1 TJB_WIDE_THREADS=0", "TJB_EPOCHS_PER_ITER=2", "TJB_EPOCHS_PER_ITER=3"]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
@@ -424,7 +424,7 @@ def test_host_emulated_tuning_variants(variant):
             "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_HALLEY=1 TJB_TRIG_TABLE_LOG2=11",
             "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_HALLEY=1 TJB_TRIG_TABLE_LOG2=11 TJB_EPOCHS_PER_ITER=3",
             "TJB_TRIM=1 TJB_PHASE_FIXED=1 TJB_EPOCHS_PER_ITER=4",
-                                     "TJB_TRIG2=0 TJB_XZ=0 TJB_EPOCHS_PER_ITER=3", "TJB_XZ=0"])
+                                     "TJB_TRIG2=0 TJB_EPOCHS_PER_ITER=3", "TJB_XZ=1"])
 def test_kepler_solver_extreme_cases(variant):
     """e -> 1 at M -> 0, phases beyond the FP32 stage's range (P = 0.05 d over 10 000 d):
     the safeguarded extra passes (kepler.cuh::solve_extra_passes) always converge to a

@@ -132,9 +132,12 @@ constexpr double kUnitsPerRev = 4.0;
 #ifndef TJB_TRIG2
 #define TJB_TRIG2 1
 #endif
-// z-stage reciprocal refined from the main step's (see rv_unit_columns); needs TJB_HALLEY
+// z-stage reciprocal refined from the main step's (see z_from_step_rcp; needs TJB_HALLEY).
+// Off by default: it won 0.4-0.8 % at 256- and 640-thread CTAs with 4 epochs per iteration,
+// and loses 1.5-2.5 % in the shipped shapes (profiles/r02c_tune_cta_shapes.jsonl: e2_1024 vs
+// e2_1024_xz0, jit_xz0) -- the two registers per chain it keeps alive cost more than the MUFU.
 #ifndef TJB_XZ
-#define TJB_XZ 1
+#define TJB_XZ 0
 #endif
 #if !TJB_HALLEY  // the third-order main step does not hand out its reciprocal
 #undef TJB_XZ

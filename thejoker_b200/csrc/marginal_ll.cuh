@@ -50,7 +50,7 @@ TJB_HD constexpr int row_stride(int L) { return (L + 2 + 1) & ~1; }
 // (kepler.cuh, TJB_XZ).  Timed on B200 (profiles/r02c_tune_cta_shapes.jsonl):
 //   * per-sample jitter (all the Gram sums in registers): 640 threads x 4 epochs, 96 registers;
 //     more threads lose to spills (1024 x 2: -7 % at L = 2, -35 % at L = 4);
-//   * constant jitter, L <= 4: 1024 threads x 2 epochs, 64 registers, without TJB_XZ:
+//   * constant jitter, L <= 4: 1024 threads x 2 epochs, 64 registers:
 //     +2.7 % / +2.9 % / +3.4 % at L = 2 / 3 / 4 over 640 x 4 -- the shorter FP32 / FP64
 //     phases of more warps interleave better on the four units the kernel loads;
 //   * constant jitter, L > 4: the 640 x 4 shape (not timed wider).
@@ -75,7 +75,7 @@ struct LLShape {
   static constexpr bool kWide = TJB_WIDE_THREADS > 0 && !kJit && L <= 4;
   static constexpr int kThreads = kWide ? TJB_WIDE_THREADS : TJB_LL_THREADS;
   static constexpr int kEpochs = kWide ? TJB_WIDE_EPOCHS : TJB_EPOCHS_PER_ITER;
-  static constexpr bool kXZ = kWide ? false : (TJB_XZ != 0);
+  static constexpr bool kXZ = TJB_XZ != 0;
 };
 
 // header of the loop over groups of kEpochsPerIter epochs; leaves n at the first epoch of
