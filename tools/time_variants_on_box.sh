@@ -8,7 +8,7 @@
 set -x
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-PROF=${@:-ucur_t2 ucur}
+PROF=${@:-shipped}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv > gpurun_out/tune_clocks.csv
 timeout 1200 python tools/tune_variants.py > gpurun_out/tune.log 2>&1
 for v in $PROF; do
