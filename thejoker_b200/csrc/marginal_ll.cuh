@@ -1,5 +1,7 @@
-// marginal_ll.cuh -- the hot kernel: one thread per prior sample, all epochs of
-// the star staged once per CTA in shared memory, Gram sums in registers.
+// marginal_ll.cuh -- the hot kernel: one thread per prior sample, one CTA per SM; the
+// star's epoch rows come in through the kernel's parameter block (uniform loads; shared or
+// global memory for long tables), the trig tables are staged in shared memory, the Gram
+// sums live in registers.
 //
 // Replaces CJokerHelper.batch_marginal_ln_likelihood
 // (thejoker/src/fast_likelihood.pyx:428-469) and everything it calls per sample
@@ -34,7 +36,7 @@ struct PriorGenView {
 
 // Per-star constants.  Passed by value as a kernel parameter (constant bank).
 //
-// Epoch table row n (stride row_stride(L) doubles, staged in shared memory):
+// Epoch table row n (stride row_stride(L) doubles):
 //   constant-jitter kernel (kJit=false): [dt_n, w_n, w_n y_n, w_n T_n1 .. w_n T_n,L-1]
 //        with w_n = ivar_n / (1 + s^2 ivar_n) for the one s of the call
 //   per-sample-jitter kernel (kJit=true): [dt_n, var_n, y_n, T_n1 .. T_n,L-1]
