@@ -1,6 +1,10 @@
-"""Multi-GPU paths (skipped on a single-GPU box): one process driving two GPUs, and
-two NCCL ranks (one per GPU) in SPMD mode, must both reproduce the single-GPU result
-bit for bit -- same ll, same accepted indices, same posterior samples."""
+"""Sharded paths: one process driving two GPUs, and two NCCL ranks (one per GPU) in SPMD
+mode, must both reproduce the single-GPU result bit for bit -- same ll, same accepted
+indices, same posterior samples.  The two-GPU tests are skipped on a single-GPU box; the
+one-process sharded path (shard offsets, per-shard PCG64 offsets, the fused max exchange
+through the shards' keys, the ordered merge of the accepted indices, the iterative sampler
+over shards, a drawn prior split over shards) is also run with two and three shards on ONE
+GPU, which a single-GPU box can do."""
 import os
 import socket
 import sys
@@ -45,6 +49,31 @@ def _run(joker, flat, ps):
     out["gen_P"], out["gen_K"] = s["P"].value, s["K"].value
     out["gen_lp"], out["gen_ll"] = s["ln_prior"].value, s["ln_likelihood"].value
     return out
+
+
+@pytest.mark.parametrize("devices", [[0, 0], [0, 0, 0]])
+def test_one_process_several_shards_on_one_gpu(devices):
+    """devices=[0, 0]: the same sharded code path as two GPUs (separate handles, streams and
+    max keys; the kernels' epilogues max-update the other shards' keys), on one device."""
+    if _n_gpus() < 1:
+        pytest.skip("needs a GPU")
+    tj, prior, flat, ps = _setup()
+    a = _run(tj.TheJoker(prior, rng=np.random.default_rng(42), devices=[0]), flat, ps)
+    b = _run(tj.TheJoker(prior, rng=np.random.default_rng(42), devices=devices), flat, ps)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    from thejoker_b200.sharding import DeviceEngine
+    j2 = tj.TheJoker(prior, rng=np.random.default_rng(42), devices=devices)
+    helper0 = j2._make_joker_helper(flat)
+    cols, _ = j2._columns(helper0, ps)
+    eng, _ = j2._engine(flat, cols)
+    assert isinstance(eng, DeviceEngine) and eng.peer_max and len(eng.shards) == len(devices)
+    assert len({id(sh.helper) for sh in eng.shards}) == len(devices)
+    eng.compute_ll()
+    eng.global_max_key()
+    eng.synchronize()
+    want = float(np.max(a["ll"]))
+    assert [sh.helper.llmax_value(sh.key) for sh in eng.shards] == [want] * len(devices)
 
 
 def test_one_process_two_gpus():

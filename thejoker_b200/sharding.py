@@ -320,7 +320,10 @@ class DeviceEngine:
         torch = self.torch
         sh = _Shard()
         sh.device, sh.lo, sh.hi = d, lo, hi
-        sh.helper = make_helper(d)
+        # a device listed twice gets one handle (stream, max key, peer list) per shard: two
+        # shards on one GPU exercise the whole sharded path on a single-GPU box
+        dup = any(o.device == d for o in self.shards)
+        sh.helper = make_helper(d, True) if dup else make_helper(d)
         sh.cols, sh.s = cols, s_dev
         with self._ctx(d):
             sh.ll = torch.full((hi - lo,), float("nan"), dtype=torch.float64, device=self._devstr(d))

@@ -154,7 +154,9 @@ class TheJoker:
         # for its device instead of creating a second handle for the same star
         helpers = {} if helper0 is None else {helper0.device: helper0}
 
-        def make(d):
+        def make(d, fresh=False):
+            if fresh:  # a second shard on the same device: its own handle
+                return self._make_joker_helper(data, device=d)
             if d not in helpers:
                 helpers[d] = self._make_joker_helper(data, device=d)
             return helpers[d]
@@ -186,7 +188,9 @@ class TheJoker:
         distribution family without a device sampler."""
         helpers = {}
 
-        def make(d):
+        def make(d, fresh=False):
+            if fresh:
+                return self._make_joker_helper(data, device=d)
             if d not in helpers:
                 helpers[d] = self._make_joker_helper(data, device=d)
             return helpers[d]
