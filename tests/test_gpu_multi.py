@@ -113,8 +113,32 @@ def _worker(rank, world, port, out_dir):
     joker = tj.TheJoker(prior, rng=np.random.default_rng(42), devices=[rank],
                         group=dist.group.WORLD)
     out = _run(joker, flat, ps)
+    # did the accept go through the library's own NCCL communicator?
+    helper0 = joker._make_joker_helper(flat)
+    eng, _ = joker._engine(flat, joker._columns(helper0, ps)[0])
+    out["lib_collectives"] = np.array(eng._lib_collectives())
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **out)
     dist.destroy_process_group()
+
+
+def test_one_nccl_rank_library_collectives(tmp_path):
+    """The cross-rank accept inside the library (tjb_comm_create, tjb_accept_dist: NCCL bound at
+    run time, MAX all-reduce, count / index all-gathers) on a world of ONE rank: the same code
+    path as test_two_nccl_ranks_spmd, runnable on a single-GPU box."""
+    if _n_gpus() < 1:
+        pytest.skip("needs a GPU")
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(1, port, str(tmp_path)), nprocs=1, join=True)
+    tj, prior, flat, ps = _setup()
+    want = _run(tj.TheJoker(prior, rng=np.random.default_rng(42), devices=[0]), flat, ps)
+    got = np.load(tmp_path / "rank0.npz")
+    for k in want:
+        assert np.array_equal(want[k], got[k]), k
+    assert bool(got["lib_collectives"])
 
 
 def test_two_nccl_ranks_spmd(tmp_path):
@@ -132,6 +156,7 @@ def test_two_nccl_ranks_spmd(tmp_path):
         got = np.load(tmp_path / f"rank{rank}.npz")
         for k in want:
             assert np.array_equal(want[k], got[k]), (rank, k)
+        assert bool(got["lib_collectives"])
 
 
 def test_multistar_sharded_over_two_gpus():
