@@ -268,8 +268,12 @@ class MultiStarJoker:
         ranks exchange their results (as packed arrays) and every rank returns all stars;
         ``gather=False``: no communication, a rank's list holds ``None`` for the stars of
         the other ranks (``last_stats`` likewise)."""
+        import time
+
         import torch
 
+        t_start = time.perf_counter()
+        timing = {}
         n_stars = len(stars)
         self._packed = {} if (self.group is not None and gather) else None
         seqs = self.rng.bit_generator._seed_seq.spawn(n_stars)
@@ -301,9 +305,12 @@ class MultiStarJoker:
         n_lin = self._helper0.n_linear
         native = (self.engine == "native" and self.draw == "device" and
                   min(max_keep, n_prior) * int(n_linear_samples) * n_lin <= self._NATIVE_MAX_NORMALS)
+        timing["setup_s"] = time.perf_counter() - t_start
         if native:
+            t0 = time.perf_counter()
             self._run_native(prepare, seqs, r_lo, dev_ranges, min(max_keep, n_prior),
                              int(n_linear_samples), return_logprobs, results, stats)
+            timing["star_loop_s"] = time.perf_counter() - t0
             dev_ranges = [(0, 0)] * len(self.devices)  # nothing left for the Python engine
 
         def run_slot(d, slot, star_indices):
@@ -363,12 +370,20 @@ class MultiStarJoker:
             # ~0.25 s and unpickling them ~0.1 s per sender, against ~40 us per star to
             # rebuild a table from its packed rows.
             parts = [None] * world
+            t0 = time.perf_counter()
             mine = _pack_for_exchange(list(range(r_lo, r_hi)), self._packed, stats)
+            timing["exchange_pack_s"] = time.perf_counter() - t0
+            t0 = time.perf_counter()
             dist.all_gather_object(parts, mine, group=self.group)
+            timing["exchange_gather_s"] = time.perf_counter() - t0
+            t0 = time.perf_counter()
             for r, part in enumerate(parts):
                 if r != rank:
                     _unpack_from_exchange(part, self.prior.poly_trend, self.prior.n_offsets,
                                           results, stats)
+            timing["exchange_unpack_s"] = time.perf_counter() - t0
             self._packed = None
+        timing["total_s"] = time.perf_counter() - t_start
+        self.last_timing = timing  # where the wall clock of this call went (this rank)
         self.last_stats = [stats.get(i) for i in range(n_stars)]
         return [results.get(i) for i in range(n_stars)]

@@ -65,7 +65,7 @@ rec = dict(n_gpus=world, engine=engine, streams_per_device=streams, n_stars=n_st
            prior_evaluations_per_s=n_stars * (1 << log2_prior) / dt,
            mean_epochs=float(np.mean([len(s[0]) + len(s[1]) for s in stars])),
            mean_posterior_samples=float(np.mean([len(o) for o in out if o is not None])),
-           gather=gather,
+           gather=gather, rank0_timing={k: round(v, 4) for k, v in ms.last_timing.items()},
            extrapolated_4096_stars_s=4096 * dt / n_stars)
 print(json.dumps(rec))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
