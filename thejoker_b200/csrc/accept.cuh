@@ -107,10 +107,21 @@ accept_flag_kernel(const double *__restrict__ ll, const long long n,
   const long long first = (long long)blockIdx.x * words_per_cta * 32 + threadIdx.x;
   const long long cta_end = min(n, ((long long)blockIdx.x + 1) * words_per_cta * 32);
   const long long n_words = (n + 31) / 32;
+  // PCG64 state of this thread's first sample: a two-level jump.  One thread takes the
+  // generator to the CTA's first sample (O(log n) 128-bit squarings, ~3000 instructions),
+  // every thread then advances that state by its own index within the CTA (<= 8 squarings).
+  // With the full jump in every thread a CTA of the smallest size (8192 samples: one star of
+  // a multi-star batch) spent more instructions on jumping than on its samples.
   u128 st = 0;
-  if (pp.enabled && first < n) {
-    const Lcg128 j = lcg_power(pp.inc, (uint64_t)first + 1);
-    st = j.mult * pp.state + j.plus;
+  if (pp.enabled) {
+    __shared__ u128 s_cta_state;
+    if (threadIdx.x == 0) {
+      const Lcg128 j = lcg_power(pp.inc, (uint64_t)((long long)blockIdx.x * words_per_cta * 32) + 1);
+      s_cta_state = j.mult * pp.state + j.plus;
+    }
+    __syncthreads();
+    const Lcg128 jt = lcg_power(pp.inc, (uint64_t)threadIdx.x);
+    st = jt.mult * s_cta_state + jt.plus;
   }
   unsigned cnt = 0, near = 0, nonfin = 0;
   const long long cta_end_round = ((cta_end + 31) / 32) * 32;
